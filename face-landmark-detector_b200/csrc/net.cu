@@ -1,0 +1,386 @@
+// net.cu — layer-graph executor behind fld_net_*: shape inference, BN folding, weight repacking for
+// the kernel layouts, workspace planning and per-layer dispatch (tcgen05 kernels in FLD_BF16 mode, fp32
+// CUDA-core kernels in FLD_F32 mode and for the non-GEMM layers).
+//
+// Replaces model.signatures["predict"] (reference prediction.py:84) and model.predict (prediction.py:208)
+// for graphs expressed in the vocabulary of networks/fcn.py / networks/utils.py.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "ops.cuh"
+
+namespace {
+
+struct TensorInfo {
+  int h = 0, w = 0, c = 0;
+  int dtype = FLD_F32;
+  size_t elems() const { return (size_t)h * w * c; }
+  size_t esz() const { return dtype == FLD_U8 ? 1 : dtype == FLD_BF16 ? 2 : 4; }
+};
+
+enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
+
+struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
+
+struct LayerRt {
+  fld_layer_desc d;
+  ConvGeom g{};
+  int path = PATH_SIMT;
+  int cout_pad = 0;
+  bool needs_weights = false, has_weights = false;
+  std::vector<float> w_host;  // folded fp32: conv [K][Cout]; deconv [k][k][Cin][Cout]; dense [In][Out]
+  std::vector<float> b_host;  // folded bias [Cout] (empty = none)
+  float* d_w = nullptr;
+  float* d_bias = nullptr;
+  __nv_bfloat16* d_wbf = nullptr;
+  std::vector<PlanEntry> plans;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct fld_net {
+  fld_handle* h;
+  int compute;
+  std::vector<TensorInfo> tensors;  // [0] = input
+  std::vector<LayerRt> layers;
+  bool finalized = false;
+};
+
+namespace {
+
+int infer_shapes(fld_net* net) {
+  const int bf = net->compute == FLD_BF16;
+  const int nL = (int)net->layers.size();
+  for (int i = 0; i < nL; ++i) {
+    LayerRt& L = net->layers[i];
+    const fld_layer_desc& d = L.d;
+    FLD_REQUIRE(d.in0 >= 0 && d.in0 <= i, "layer %d: in0=%d must reference an earlier tensor", i, d.in0);
+    const TensorInfo& a = net->tensors[d.in0];
+    TensorInfo o;
+    switch (d.op) {
+      case FLD_OP_CONV: {
+        FLD_REQUIRE(d.kh > 0 && d.kw > 0 && d.stride > 0 && d.cout > 0, "layer %d: bad conv parameters", i);
+        ConvGeom& g = L.g;
+        g.IH = a.h; g.IW = a.w; g.Cin = a.c;
+        g.kh = d.kh; g.kw = d.kw; g.stride = d.stride; g.pad_t = d.pad_t; g.pad_l = d.pad_l;
+        g.OH = (a.h + d.pad_t + d.pad_b - d.kh) / d.stride + 1;
+        g.OW = (a.w + d.pad_l + d.pad_r - d.kw) / d.stride + 1;
+        g.Cout = d.cout; g.act = d.act; g.pool = d.pool;
+        FLD_REQUIRE(g.OH > 0 && g.OW > 0, "layer %d: conv output is empty", i);
+        FLD_REQUIRE(d.pool == 0 || d.pool == 2, "layer %d: pool must be 0 or 2", i);
+        o.h = d.pool ? g.OH / 2 : g.OH; o.w = d.pool ? g.OW / 2 : g.OW; o.c = d.cout;
+        FLD_REQUIRE(o.h > 0 && o.w > 0, "layer %d: pooled output is empty", i);
+        L.needs_weights = true;
+        break;
+      }
+      case FLD_OP_DECONV:
+        FLD_REQUIRE(d.kh == d.kw && d.kh >= d.stride && d.stride > 0 && d.cout > 0, "layer %d: bad deconv parameters", i);
+        o.h = (a.h - 1) * d.stride + d.kh; o.w = (a.w - 1) * d.stride + d.kw; o.c = d.cout;
+        L.needs_weights = true;
+        break;
+      case FLD_OP_ADD: {
+        FLD_REQUIRE(d.in1 >= 0 && d.in1 <= i, "layer %d: in1=%d must reference an earlier tensor", i, d.in1);
+        const TensorInfo& b2 = net->tensors[d.in1];
+        FLD_REQUIRE(a.c == b2.c, "layer %d: ADD channel mismatch %d vs %d", i, a.c, b2.c);
+        o.h = a.h < b2.h ? a.h : b2.h; o.w = a.w < b2.w ? a.w : b2.w; o.c = a.c;
+        break;
+      }
+      case FLD_OP_DENSE:
+        FLD_REQUIRE(d.cout > 0, "layer %d: bad dense units", i);
+        o.h = 1; o.w = 1; o.c = d.cout;
+        L.needs_weights = true;
+        break;
+      case FLD_OP_SOFTMAX:
+        o = a;
+        break;
+      case FLD_OP_MAXPOOL:
+        FLD_REQUIRE(d.kh > 0 && d.stride > 0, "layer %d: bad pool parameters", i);
+        o.h = (a.h - d.kh) / d.stride + 1; o.w = (a.w - d.kh) / d.stride + 1; o.c = a.c;
+        break;
+      default:
+        fld_set_error("layer %d: op %d not implemented", i, d.op);
+        return FLD_ERR_INVALID;
+    }
+    o.dtype = FLD_F32;
+    net->tensors.push_back(o);
+  }
+  // dtype / kernel-path assignment for the tensor-core mode
+  if (bf) {
+    std::vector<int> f32_needed(net->tensors.size(), 0);
+    f32_needed.back() = 1;  // final tensor is handed out as fp32
+    for (int i = 0; i < nL; ++i) {
+      const fld_layer_desc& d = net->layers[i].d;
+      if (d.op == FLD_OP_ADD) { f32_needed[d.in0] = 1; f32_needed[d.in1] = 1; }
+      if (d.op == FLD_OP_SOFTMAX || d.op == FLD_OP_MAXPOOL) f32_needed[d.in0] = 1;
+    }
+    for (int i = 0; i < nL; ++i) {
+      LayerRt& L = net->layers[i];
+      TensorInfo& o = net->tensors[i + 1];
+      const TensorInfo& a = net->tensors[L.d.in0];
+      if (L.d.op != FLD_OP_CONV) { o.dtype = FLD_F32; continue; }
+      const bool want_f32 = f32_needed[i + 1] != 0;
+      const bool in_ok_first = (a.dtype == FLD_U8 || a.dtype == FLD_F32) && tc_conv_first_supported(L.g);
+      const bool in_ok_tma = (a.dtype == FLD_BF16) && tc_conv_supported(L.g);
+      if (in_ok_first && !want_f32) { L.path = PATH_TC_FIRST; o.dtype = FLD_BF16; }
+      else if (in_ok_tma && !(want_f32 && L.g.pool)) { L.path = PATH_TC_TMA; o.dtype = want_f32 ? FLD_F32 : FLD_BF16; }
+      else { L.path = PATH_SIMT; o.dtype = want_f32 ? FLD_F32 : FLD_BF16; }
+      if (L.path == PATH_TC_TMA) L.cout_pad = (int)align_up(L.g.Cout, L.g.Cout > 256 ? 128 : 16);
+    }
+  }
+  return FLD_OK;
+}
+
+void free_layer(LayerRt& L) {
+  if (L.d_w) cudaFree(L.d_w);
+  if (L.d_bias) cudaFree(L.d_bias);
+  if (L.d_wbf) cudaFree(L.d_wbf);
+  for (auto& pe : L.plans) tc_conv_plan_destroy(pe.plan);
+  L.d_w = nullptr; L.d_bias = nullptr; L.d_wbf = nullptr; L.plans.clear();
+}
+
+uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+extern "C" int fld_net_create(fld_handle* h, const fld_layer_desc* layers_h, int n_layers, int in_h, int in_w, int in_c, int in_dtype,
+                              int compute, fld_net** out) {
+  int rc = fld_enter(h);
+  if (rc) return rc;
+  FLD_REQUIRE(layers_h && out && n_layers > 0, "fld_net_create: null/empty layer list");
+  FLD_REQUIRE(in_h > 0 && in_w > 0 && in_c > 0, "fld_net_create: bad input shape");
+  FLD_REQUIRE(in_dtype == FLD_U8 || in_dtype == FLD_F32, "fld_net_create: input dtype must be FLD_U8 or FLD_F32");
+  FLD_REQUIRE(compute == FLD_F32 || compute == FLD_BF16, "fld_net_create: compute must be FLD_F32 or FLD_BF16");
+  fld_net* net = new fld_net();
+  net->h = h;
+  net->compute = compute;
+  TensorInfo in;
+  in.h = in_h; in.w = in_w; in.c = in_c; in.dtype = in_dtype;
+  net->tensors.push_back(in);
+  net->layers.resize(n_layers);
+  for (int i = 0; i < n_layers; ++i) net->layers[i].d = layers_h[i];
+  rc = infer_shapes(net);
+  if (rc) { delete net; return rc; }
+  *out = net;
+  return FLD_OK;
+}
+
+extern "C" void fld_net_destroy(fld_net* net) {
+  if (!net) return;
+  cudaSetDevice(net->h->device);
+  for (auto& L : net->layers) free_layer(L);
+  delete net;
+}
+
+extern "C" int fld_net_set_weights(fld_net* net, int layer, const float* kernel_h, const float* bias_h, const float* bn_h, float eps) {
+  FLD_REQUIRE(net, "fld_net_set_weights: null net");
+  FLD_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "fld_net_set_weights: layer %d out of range", layer);
+  LayerRt& L = net->layers[layer];
+  FLD_REQUIRE(L.needs_weights, "fld_net_set_weights: layer %d takes no weights", layer);
+  FLD_REQUIRE(kernel_h, "fld_net_set_weights: null kernel");
+  const fld_layer_desc& d = L.d;
+  const TensorInfo& a = net->tensors[d.in0];
+  const int Cout = d.cout;
+  std::vector<double> scale(Cout, 1.0), shift(Cout, 0.0);
+  for (int o = 0; o < Cout; ++o) {
+    double b = bias_h ? (double)bias_h[o] : 0.0;
+    if (bn_h) {
+      const double g = bn_h[o], be = bn_h[Cout + o], mu = bn_h[2 * Cout + o], var = bn_h[3 * Cout + o];
+      const double s = g / sqrt(var + (double)eps);
+      scale[o] = s;
+      shift[o] = (b - mu) * s + be;
+    } else {
+      shift[o] = b;
+    }
+  }
+  const bool any_bias = bias_h || bn_h;
+  if (d.op == FLD_OP_CONV) {
+    const size_t K = (size_t)d.kh * d.kw * a.c;
+    const double isc = d.in_scale != 0.f ? (double)d.in_scale : 1.0;
+    L.w_host.resize(K * Cout);
+    for (size_t k = 0; k < K; ++k)
+      for (int o = 0; o < Cout; ++o) L.w_host[k * Cout + o] = (float)((double)kernel_h[k * Cout + o] * scale[o] * isc);
+  } else if (d.op == FLD_OP_DECONV) {
+    FLD_REQUIRE(!bn_h && !bias_h, "fld_net_set_weights: Conv2DTranspose layers carry no bias/BN in the reference graphs");
+    const int k = d.kh, Cin = a.c;
+    L.w_host.resize((size_t)k * k * Cin * Cout);
+    for (int t = 0; t < k * k; ++t)
+      for (int o = 0; o < Cout; ++o)
+        for (int c = 0; c < Cin; ++c)
+          L.w_host[((size_t)t * Cin + c) * Cout + o] = kernel_h[((size_t)t * Cout + o) * Cin + c];
+  } else if (d.op == FLD_OP_DENSE) {
+    const size_t In = a.elems();
+    L.w_host.resize(In * Cout);
+    for (size_t k = 0; k < In; ++k)
+      for (int o = 0; o < Cout; ++o) L.w_host[k * Cout + o] = (float)((double)kernel_h[k * Cout + o] * scale[o]);
+  }
+  L.b_host.clear();
+  if (any_bias) {
+    L.b_host.resize(Cout);
+    for (int o = 0; o < Cout; ++o) L.b_host[o] = (float)shift[o];
+  }
+  L.has_weights = true;
+  net->finalized = false;
+  return FLD_OK;
+}
+
+extern "C" int fld_net_finalize(fld_net* net) {
+  FLD_REQUIRE(net, "fld_net_finalize: null net");
+  int rc = fld_enter(net->h);
+  if (rc) return rc;
+  for (size_t i = 0; i < net->layers.size(); ++i) {
+    LayerRt& L = net->layers[i];
+    if (!L.needs_weights) continue;
+    if (!L.has_weights) { fld_set_error("fld_net_finalize: layer %zu has no weights", i); return FLD_ERR_STATE; }
+    free_layer(L);
+    const int Cout = L.d.cout;
+    const TensorInfo& a = net->tensors[L.d.in0];
+    // bias (padded so the epilogue can always read 32 floats per chunk)
+    {
+      const size_t nb = align_up((size_t)std::max(Cout, L.cout_pad), 32) + 32;
+      std::vector<float> b(nb, 0.f);
+      for (size_t o = 0; o < L.b_host.size(); ++o) b[o] = L.b_host[o];
+      FLD_CUDA(cudaMalloc(&L.d_bias, nb * sizeof(float)));
+      FLD_CUDA(cudaMemcpy(L.d_bias, b.data(), nb * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (L.path == PATH_SIMT) {
+      FLD_CUDA(cudaMalloc(&L.d_w, L.w_host.size() * sizeof(float)));
+      FLD_CUDA(cudaMemcpy(L.d_w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else if (L.path == PATH_TC_FIRST) {
+      // [kg 4][ng Cout/8][r 8][e 8]  <-  w[k = kg*8+e][cout = ng*8+r], K = 27 padded to 32
+      std::vector<uint16_t> pk((size_t)Cout * 32, 0);
+      for (int kg = 0; kg < 4; ++kg)
+        for (int ng = 0; ng < Cout / 8; ++ng)
+          for (int r = 0; r < 8; ++r)
+            for (int e = 0; e < 8; ++e) {
+              const int k = kg * 8 + e, o = ng * 8 + r;
+              const float v = k < 27 ? L.w_host[(size_t)k * Cout + o] : 0.f;
+              pk[(((size_t)kg * (Cout / 8) + ng) * 8 + r) * 8 + e] = f2bf(v);
+            }
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else {
+      // [tap][cout_pad][Cin]  <-  w[(tap*Cin + c)][cout]
+      const int taps = L.d.kh * L.d.kw, Cin = a.c, cp = L.cout_pad;
+      std::vector<uint16_t> pk((size_t)taps * cp * Cin, 0);
+      for (int t = 0; t < taps; ++t)
+        for (int c = 0; c < Cin; ++c)
+          for (int o = 0; o < Cout; ++o) pk[((size_t)t * cp + o) * Cin + c] = f2bf(L.w_host[((size_t)t * Cin + c) * Cout + o]);
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    }
+  }
+  net->finalized = true;
+  return FLD_OK;
+}
+
+extern "C" int fld_net_tensor_shape(const fld_net* net, int tensor, int32_t* hwc) {
+  if (!net || !hwc || tensor < 0 || tensor >= (int)net->tensors.size()) { fld_set_error("fld_net_tensor_shape: bad argument"); return FLD_ERR_INVALID; }
+  const TensorInfo& t = net->tensors[tensor];
+  hwc[0] = t.h; hwc[1] = t.w; hwc[2] = t.c;
+  return t.dtype;
+}
+
+extern "C" int64_t fld_net_tensor_offset(const fld_net* net, int tensor, int B) {
+  if (!net || tensor < 1 || tensor >= (int)net->tensors.size() || B < 0) { fld_set_error("fld_net_tensor_offset: bad argument"); return FLD_ERR_INVALID; }
+  size_t off = 0;
+  for (int t = 1; t < tensor; ++t) off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+  return (int64_t)off;
+}
+
+extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
+  if (!net || B < 0) return 0;
+  size_t off = 0;
+  for (size_t t = 1; t < net->tensors.size(); ++t) off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+  return off + 1024;
+}
+
+extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {
+  FLD_REQUIRE(net, "fld_net_forward: null net");
+  int rc = fld_enter(net->h);
+  if (rc) return rc;
+  if (!net->finalized) { fld_set_error("fld_net_forward: call fld_net_finalize first"); return FLD_ERR_STATE; }
+  FLD_REQUIRE(in && workspace && B >= 0, "fld_net_forward: null pointer");
+  FLD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "fld_net_forward: workspace must be 1024-byte aligned");
+  if (ws_bytes < fld_net_workspace_bytes(net, B)) {
+    fld_set_error("fld_net_forward: workspace %zu < required %zu", ws_bytes, fld_net_workspace_bytes(net, B));
+    return FLD_ERR_WORKSPACE;
+  }
+  if (B == 0) return FLD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nT = (int)net->tensors.size();
+  std::vector<void*> ptr(nT);
+  ptr[0] = const_cast<void*>(in);
+  {
+    size_t off = 0;
+    for (int t = 1; t < nT; ++t) {
+      ptr[t] = (char*)workspace + off;
+      off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+    }
+  }
+  for (size_t i = 0; i < net->layers.size(); ++i) {
+    LayerRt& L = net->layers[i];
+    const fld_layer_desc& d = L.d;
+    const TensorInfo& a = net->tensors[d.in0];
+    const TensorInfo& o = net->tensors[i + 1];
+    const void* pin = ptr[d.in0];
+    void* pout = ptr[i + 1];
+    switch (d.op) {
+      case FLD_OP_CONV:
+        if (L.path == PATH_TC_FIRST) {
+          rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st);
+        } else if (L.path == PATH_TC_TMA) {
+          TcConvPlan* plan = nullptr;
+          for (auto& pe : L.plans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }
+          if (!plan) {
+            rc = tc_conv_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan);
+            if (rc) return rc;
+            if (L.plans.size() >= 8) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
+            L.plans.push_back({B, pin, plan});
+          }
+          rc = tc_conv_run(plan, L.d_bias, pout, o.dtype, st);
+        } else {
+          rc = simt_conv(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, pout, o.dtype, L.g, B, st);
+        }
+        break;
+      case FLD_OP_DECONV:
+        rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
+        break;
+      case FLD_OP_ADD: {
+        const TensorInfo& b2 = net->tensors[d.in1];
+        FLD_REQUIRE(a.dtype == FLD_F32 && b2.dtype == FLD_F32, "layer %zu: ADD inputs must be fp32", i);
+        rc = simt_add_crop((const float*)pin, a.h, a.w, (const float*)ptr[d.in1], b2.h, b2.w, (float*)pout, B, o.h, o.w, o.c, st);
+        break;
+      }
+      case FLD_OP_DENSE:
+        rc = simt_dense(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, (float*)pout, B, (int)a.elems(), o.c, d.act, st);
+        break;
+      case FLD_OP_SOFTMAX:
+        FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: SOFTMAX input must be fp32", i);
+        rc = simt_softmax((const float*)pin, (float*)pout, (long long)B * a.h * a.w, a.c, st);
+        break;
+      case FLD_OP_MAXPOOL:
+        FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: MAXPOOL input must be fp32", i);
+        rc = simt_maxpool((const float*)pin, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, d.kh, d.stride, st);
+        break;
+      default:
+        fld_set_error("layer %zu: op %d not implemented", i, d.op);
+        rc = FLD_ERR_INVALID;
+    }
+    if (rc) return rc;
+  }
+  if (out) {
+    const TensorInfo& o = net->tensors[nT - 1];
+    const size_t n = o.elems() * (size_t)B;
+    if (o.dtype == FLD_F32) FLD_CUDA(cudaMemcpyAsync(out, ptr[nT - 1], n * 4, cudaMemcpyDeviceToDevice, st));
+    else { rc = simt_cvt_bf16_f32(ptr[nT - 1], out, (long long)n, st); if (rc) return rc; }
+  }
+  return FLD_OK;
+}

@@ -1,0 +1,38 @@
+// ops.cuh — internal layer-op entry points shared by net.cu / simt_ops.cu / tc_conv.cu
+#pragma once
+#include "common.cuh"
+
+struct ConvGeom {
+  int IH, IW, Cin;      // input (un-padded)
+  int OH, OW, Cout;     // conv output BEFORE the optional fused pool
+  int kh, kw, stride;
+  int pad_t, pad_l;     // zero padding on top / left (bottom / right implied by OH, OW)
+  int act;              // fld_act
+  int pool;             // 0 or 2
+};
+
+// ---- fp32 CUDA-core kernels (simt_ops.cu)
+int simt_conv(const void* in, int in_dtype, const float* w /*[kh*kw*Cin][Cout]*/, const float* bias, void* out, int out_dtype,
+              const ConvGeom& g, int B, cudaStream_t st);
+int simt_deconv(const void* in, int in_dtype, const float* w /*[k][k][Cin][Cout]*/, float* out, int B, int IH, int IW, int Cin,
+                int OH, int OW, int Cout, int k, int s, cudaStream_t st);
+int simt_add_crop(const float* a, int AH, int AW, const float* b, int BH, int BW, float* out, int B, int OH, int OW, int C,
+                  cudaStream_t st);
+int simt_softmax(const float* in, float* out, long long n_px, int C, cudaStream_t st);
+int simt_dense(const void* in, int in_dtype, const float* w /*[In][Out]*/, const float* bias, float* out, int B, int In, int Out,
+               int act, cudaStream_t st);
+int simt_maxpool(const float* in, float* out, int B, int IH, int IW, int C, int OH, int OW, int k, int s, cudaStream_t st);
+int simt_cvt_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
+
+// ---- tcgen05 tensor-core kernels (tc_conv.cu)
+struct TcConvPlan;  // opaque: tensor maps + launch geometry for one (layer, batch, buffers) combination
+// first layer: 3x3, Cin = 3, pad 1, stride 1, fused bias + ReLU (+pool2); input u8 or f32 NHWC, output bf16 NHWC
+int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_bfloat16* w_packed /*[Cout][32]*/,
+                  const float* bias, __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st);
+bool tc_conv_first_supported(const ConvGeom& g);
+// generic: stride 1, Cin % 64 == 0, bf16 NHWC in; weights bf16 [kh*kw][Cout_pad][Cin]; out bf16 or f32 NHWC
+bool tc_conv_supported(const ConvGeom& g);
+int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
+                        TcConvPlan** out);
+void tc_conv_plan_destroy(TcConvPlan* p);
+int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype, cudaStream_t st);

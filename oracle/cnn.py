@@ -1,0 +1,220 @@
+"""Oracle: Keras-semantics CNN forward.  Test infrastructure only (oracle/__init__.py).
+
+PARITY UNPINNED for this file: the arithmetic lives in TensorFlow/Keras (unpinned in the
+reference — requirements.txt is empty, setup.py:6,25 — and not installable here), and the
+reference holds no tests or golden vectors.  The graphs are restated from the reference's
+model definitions with Keras layer semantics:
+
+  vanilla_encoder      networks/fcn.py:10-51
+  crop                 networks/fcn.py:55-86
+  fcn_8 / fcn_32       networks/fcn.py:89-150
+  segmentation softmax networks/utils.py:22-30
+  regression net       build-defined: vanilla_encoder@128 -> Flatten -> Dense(136)
+                       standing in for the opaque SavedModel at prediction.py:84
+
+Two independent restatements are kept and must agree: torch functional ops (``*_t``) and a numpy
+einsum/loop version (``*_np``, small cases only).
+
+Weights are a dict name -> ndarray in Keras layouts: Conv2D kernel [kh,kw,Cin,Cout], bias [Cout];
+BatchNormalization gamma/beta/moving_mean/moving_variance [C]; Conv2DTranspose kernel
+[kh,kw,Cout,Cin]; Dense kernel [In,Out].
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3  # Keras BatchNormalization default epsilon
+
+
+# ----------------------------------------------------------------------------- torch restatement
+def _t(a, dtype):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype)
+
+
+def conv2d_t(x, kernel, bias=None, stride=1, pad=(0, 0, 0, 0)):
+    """x NCHW; kernel HWIO; pad = (top, bottom, left, right) explicit zero padding; 'valid' conv."""
+    w = kernel.permute(3, 2, 0, 1).contiguous()
+    if any(pad):
+        x = F.pad(x, (pad[2], pad[3], pad[0], pad[1]))
+    return F.conv2d(x, w, bias, stride=stride)
+
+
+def same_pad(k):
+    """Keras/TF 'same' for stride 1: total k-1, extra on the bottom/right."""
+    tot = k - 1
+    lo = tot // 2
+    return (lo, tot - lo, lo, tot - lo)
+
+
+def bn_t(x, w, name):
+    g, b, m, v = w[name + "/gamma"], w[name + "/beta"], w[name + "/moving_mean"], w[name + "/moving_variance"]
+    sh = (1, -1, 1, 1)
+    return g.view(sh) * (x - m.view(sh)) / torch.sqrt(v.view(sh) + BN_EPS) + b.view(sh)
+
+
+def deconv_t(x, kernel, stride):
+    """Conv2DTranspose 'valid', no bias: out[n,o,i*s+a,j*s+b] += x[n,c,i,j]*K[a,b,o,c] (no flip)."""
+    w = kernel.permute(3, 2, 0, 1).contiguous()  # [Cin, Cout, kh, kw]
+    return F.conv_transpose2d(x, w, stride=stride)
+
+
+def vanilla_encoder_t(x, w, prefix=""):
+    """fcn.py:25-49: 5 x (ZeroPad1, Conv3x3 valid + bias, BN, ReLU, MaxPool2).  x NCHW."""
+    levels = []
+    for i in range(1, 6):
+        x = conv2d_t(x, w[f"{prefix}conv{i}/kernel"], w[f"{prefix}conv{i}/bias"], pad=(1, 1, 1, 1))
+        x = bn_t(x, w, f"{prefix}bn{i}")
+        x = F.relu(x)
+        x = F.max_pool2d(x, 2, 2)
+        levels.append(x)
+    return levels
+
+
+def _crop_pair(o1, o2):
+    """fcn.py:55-86 crop(o1, o2): crop the wider one's right columns and the taller one's bottom rows."""
+    h1, w1 = o1.shape[2:]
+    h2, w2 = o2.shape[2:]
+    cx = abs(w1 - w2); cy = abs(h2 - h1)
+    if w1 > w2:
+        o1 = o1[:, :, :, : w1 - cx]
+    else:
+        o2 = o2[:, :, :, : w2 - cx]
+    if h1 > h2:
+        o1 = o1[:, :, : h1 - cy, :]
+    else:
+        o2 = o2[:, :, : h2 - cy, :]
+    return o1, o2
+
+
+def fcn_head_t(f5, w):
+    """fcn.py:98-103: 7x7 same 4096 relu, (dropout=id), 1x1 4096 relu, 1x1 n_classes."""
+    o = F.relu(conv2d_t(f5, w["head7/kernel"], w["head7/bias"], pad=same_pad(7)))
+    o = F.relu(conv2d_t(o, w["head1/kernel"], w["head1/bias"]))
+    return conv2d_t(o, w["score5/kernel"], w["score5/bias"])
+
+
+def fcn_8_logits_t(levels, w):
+    """fcn.py:96-122 -> pre-softmax logits NCHW [B, n_classes, 8*h3+8, 8*w3+8]."""
+    f3, f4, f5 = levels[2], levels[3], levels[4]
+    o = fcn_head_t(f5, w)
+    o = deconv_t(o, w["up2a/kernel"], 2)                                   # :104
+    o2 = conv2d_t(f4, w["score4/kernel"], w["score4/bias"])                # :107-108
+    o, o2 = _crop_pair(o, o2)                                              # :110
+    o = o + o2                                                             # :112
+    o = deconv_t(o, w["up2b/kernel"], 2)                                   # :114
+    o2 = conv2d_t(f3, w["score3/kernel"], w["score3/bias"])                # :116-117
+    o2, o = _crop_pair(o2, o)                                              # :118
+    o = o2 + o                                                             # :119
+    return deconv_t(o, w["up8/kernel"], 8)                                 # :121
+
+
+def fcn_32_logits_t(levels, w):
+    """fcn.py:137-146."""
+    o = fcn_head_t(levels[4], w)
+    return deconv_t(o, w["up32/kernel"], 32)
+
+
+def segmentation_probs_t(logits):
+    """networks/utils.py:28-30: reshape (oh*ow, n) row-major over (y,x), softmax over classes."""
+    B, n, oh, ow = logits.shape
+    return torch.softmax(logits.permute(0, 2, 3, 1).reshape(B, oh * ow, n), dim=-1)
+
+
+def _prep(weights, dtype):
+    return {k: _t(v, dtype) for k, v in weights.items()}
+
+
+def regression_forward(x_u8_nhwc, weights, dtype=torch.float64, threads=None):
+    """uint8 RGB [B,128,128,3] -> [B,136].  Input scaled by 1/255 (build-defined, App. A.8)."""
+    if threads:
+        torch.set_num_threads(threads)
+    w = _prep(weights, dtype)
+    x = _t(x_u8_nhwc, dtype).permute(0, 3, 1, 2) / 255.0
+    f5 = vanilla_encoder_t(x, w)[4]
+    flat = f5.permute(0, 2, 3, 1).reshape(f5.shape[0], -1)                 # Flatten over (H,W,C)
+    out = flat @ w["fc/kernel"] + w["fc/bias"]
+    return out.numpy()
+
+
+def trunk_forward(x_nhwc, weights, dtype=torch.float64, scale=1.0):
+    """float NHWC -> list of 5 NHWC level arrays."""
+    w = _prep(weights, dtype)
+    x = _t(x_nhwc, dtype).permute(0, 3, 1, 2) * scale
+    return [l.permute(0, 2, 3, 1).contiguous().numpy() for l in vanilla_encoder_t(x, w)]
+
+
+def fcn_forward(x_nhwc, weights, variant="fcn_8", dtype=torch.float64, return_logits=False):
+    """float NHWC (output of get_image_array) -> probs [B, oh*ow, n] (and logits NHWC)."""
+    w = _prep(weights, dtype)
+    x = _t(x_nhwc, dtype).permute(0, 3, 1, 2)
+    levels = vanilla_encoder_t(x, w)
+    logits = fcn_8_logits_t(levels, w) if variant == "fcn_8" else fcn_32_logits_t(levels, w)
+    probs = segmentation_probs_t(logits).numpy()
+    if return_logits:
+        return probs, logits.permute(0, 2, 3, 1).contiguous().numpy()
+    return probs
+
+
+# ----------------------------------------------------------------------------- numpy restatement
+def conv2d_np(x, kernel, bias=None, pad=(0, 0, 0, 0)):
+    """x NHWC fp64, kernel HWIO; stride 1."""
+    x = np.pad(x, ((0, 0), (pad[0], pad[1]), (pad[2], pad[3]), (0, 0)))
+    kh, kw = kernel.shape[:2]
+    win = np.lib.stride_tricks.sliding_window_view(x, (kh, kw), axis=(1, 2))  # [B,oh,ow,C,kh,kw]
+    out = np.einsum("bhwcij,ijco->bhwo", win, kernel, optimize=True)
+    return out + bias if bias is not None else out
+
+
+def bn_np(x, w, name):
+    return w[name + "/gamma"] * (x - w[name + "/moving_mean"]) / np.sqrt(w[name + "/moving_variance"] + BN_EPS) \
+        + w[name + "/beta"]
+
+
+def maxpool2_np(x):
+    B, H, W, C = x.shape
+    x = x[:, : H // 2 * 2, : W // 2 * 2]
+    return x.reshape(B, H // 2, 2, W // 2, 2, C).max(axis=(2, 4))
+
+
+def deconv_np(x, kernel, s):
+    B, H, W, C = x.shape
+    kh, kw, Co, Ci = kernel.shape
+    out = np.zeros((B, (H - 1) * s + kh, (W - 1) * s + kw, Co), dtype=x.dtype)
+    for a in range(kh):
+        for b in range(kw):
+            out[:, a: a + (H - 1) * s + 1: s, b: b + (W - 1) * s + 1: s] += np.einsum("bhwc,oc->bhwo", x, kernel[a, b])
+    return out
+
+
+def vanilla_encoder_np(x, w):
+    levels = []
+    for i in range(1, 6):
+        x = conv2d_np(x, w[f"conv{i}/kernel"], w[f"conv{i}/bias"], pad=(1, 1, 1, 1))
+        x = np.maximum(bn_np(x, w, f"bn{i}"), 0)
+        x = maxpool2_np(x)
+        levels.append(x)
+    return levels
+
+
+def fcn_8_logits_np(levels, w):
+    f3, f4, f5 = levels[2], levels[3], levels[4]
+    o = np.maximum(conv2d_np(f5, w["head7/kernel"], w["head7/bias"], pad=same_pad(7)), 0)
+    o = np.maximum(conv2d_np(o, w["head1/kernel"], w["head1/bias"]), 0)
+    o = conv2d_np(o, w["score5/kernel"], w["score5/bias"])
+    o = deconv_np(o, w["up2a/kernel"], 2)
+    o2 = conv2d_np(f4, w["score4/kernel"], w["score4/bias"])
+    h = min(o.shape[1], o2.shape[1]); ww = min(o.shape[2], o2.shape[2])
+    o = o[:, :h, :ww] + o2[:, :h, :ww]
+    o = deconv_np(o, w["up2b/kernel"], 2)
+    o2 = conv2d_np(f3, w["score3/kernel"], w["score3/bias"])
+    h = min(o.shape[1], o2.shape[1]); ww = min(o.shape[2], o2.shape[2])
+    o = o2[:, :h, :ww] + o[:, :h, :ww]
+    return deconv_np(o, w["up8/kernel"], 8)
+
+
+def softmax_np(logits_nhwc):
+    B, oh, ow, n = logits_nhwc.shape
+    z = logits_nhwc.reshape(B, oh * ow, n)
+    z = z - z.max(axis=-1, keepdims=True)
+    e = np.exp(z)
+    return e / e.sum(axis=-1, keepdims=True)
