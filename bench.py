@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — aligned faces/sec of the hot path (crop/resize -> landmark CNN -> decode -> Umeyama + warp).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--dtype bf16|fp32] [--impl reference]
+
+A step = one pass of the hot path over one batch of B synthetic faces (BASELINE.json configs[1]: batch-256,
+vanilla trunk @128 + FC-136 head) taken from 1080p frames, 64 faces per frame; aligned 112x112 crops out.
+Under torchrun every rank owns one GPU and its own B faces (weak scaling, no data-path collective).
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "face-landmark-detector_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "aligned faces/sec (CNN fwd+decode+warp)"
+FRAME_H, FRAME_W, FACES_PER_FRAME = 1080, 1920, 64
+
+
+# ----------------------------------------------------------------------------------------- multi-rank plumbing
+def rank_shard(n, rank, world):
+    per = -(-n // world)
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
+def _reduce(val, device, op):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(val)
+    t = torch.tensor([float(val)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=op)
+    return float(t.item())
+
+
+def max_over_ranks(val, device):
+    import torch.distributed as dist
+    return _reduce(val, device, dist.ReduceOp.MAX)
+
+
+def sum_over_ranks(val, device):
+    import torch.distributed as dist
+    return _reduce(val, device, dist.ReduceOp.SUM)
+
+
+# ----------------------------------------------------------------------------------------- synthetic workload
+def make_set(batch, seed, device=None):
+    """One batch worth of inputs: frames uint8 [F,1080,1920,3], boxes int32 [B,4], face2frame int32 [B]."""
+    from keypoints_detector.data import synthetic
+    n_frames = -(-batch // FACES_PER_FRAME)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    noise = torch.randint(0, 256, (n_frames, FRAME_H, FRAME_W, 3), dtype=torch.uint8, generator=g)
+    yy = torch.arange(FRAME_H, dtype=torch.float32)[:, None]
+    xx = torch.arange(FRAME_W, dtype=torch.float32)[None, :]
+    smooth = (127.5 + 127.5 * torch.sin(xx * 0.013 + yy * 0.021 + seed)).to(torch.uint8)
+    frames = ((noise.to(torch.int16) + smooth[None, :, :, None].to(torch.int16)) // 2).to(torch.uint8)
+    boxes = torch.from_numpy(synthetic.make_boxes(batch, FRAME_H, FRAME_W, seed=seed, min_side=96, max_side=400))
+    f2f = (torch.arange(batch, dtype=torch.int32) // FACES_PER_FRAME).to(torch.int32)
+    if device is not None:
+        return frames.to(device), boxes.to(device), f2f.to(device)
+    return frames, boxes, f2f
+
+
+def valid_tap_macs(h, w, cin, cout, k=3):
+    """MACs of a kxk pad-(k//2) stride-1 conv on an h x w map counting only in-image taps."""
+    def taps(n):
+        return sum(min(n, i + k // 2 + 1) - max(0, i - k // 2) for i in range(n))
+    return taps(h) * taps(w) * cin * cout
+
+
+TRUNK = [(128, 3, 64), (64, 64, 128), (32, 128, 256), (16, 256, 256), (8, 256, 256)]  # (map size, Cin, Cout)
+
+
+def flops_per_face():
+    macs = [valid_tap_macs(s, s, ci, co) for s, ci, co in TRUNK]
+    return [2.0 * m for m in macs], 2.0 * 4096 * 136
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU reference arm
+def cpu_pipeline(frames, boxes, f2f, weights):
+    """The reference's CPU path for the same step (oracle port; third-party cv2 / torch-CPU do the arithmetic the
+    reference delegates to OpenCV / TensorFlow): prediction.py:76-94 per face + build-defined alignment."""
+    import cv2
+    from oracle import align as o_align, cnn as o_cnn, decode as o_decode, preprocess as o_pre
+    crops, fbs = [], []
+    for i in range(len(boxes)):
+        fb = o_pre.square_box(boxes[i])
+        fr = frames[f2f[i]]
+        face = fr[max(fb[1], 0):fb[3], max(fb[0], 0):fb[2]]
+        face = cv2.cvtColor(cv2.resize(face, (128, 128)), cv2.COLOR_BGR2RGB)
+        crops.append(face); fbs.append(fb)
+    crops = np.stack(crops)
+    outs = [o_cnn.regression_forward(crops[s:s + 32], weights, torch.float32) for s in range(0, len(crops), 32)]  # Keras predict batch 32
+    out = np.concatenate(outs)
+    aligned = []
+    for i in range(len(boxes)):
+        marks, _ = o_decode.regression_decode(out[i], fbs[i])
+        M = o_align.umeyama(o_align.five_points(marks), o_align.TEMPLATE_112)
+        aligned.append(cv2.warpAffine(frames[f2f[i]], M, (112, 112), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT))
+    return np.stack(aligned)
+
+
+def time_cpu(sample_faces, steps, warmup, seed=0):
+    import cv2
+    from keypoints_detector.networks.regression import landmark_regressor
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cv2.setNumThreads(cores)
+    model = landmark_regressor().init_weights(seed)
+    frames, boxes, f2f = make_set(sample_faces, seed)
+    frames, boxes, f2f = frames.numpy(), boxes.numpy(), f2f.numpy()
+    for _ in range(warmup):
+        cpu_pipeline(frames, boxes, f2f, model.weights)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pipeline(frames, boxes, f2f, model.weights)
+    dt = time.perf_counter() - t0
+    return sample_faces * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    sample = 64
+    fps, ms, cores = time_cpu(sample, max(1, min(args.steps, 5)), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "faces/s", "n_gpus": args.gpus, "steps": min(args.steps, 5),
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch-256 crops, vanilla trunk@128 + FC-136 head, + decode + 5-point align warp "
+                                   "to 112x112 from 1080p frames", "sample_faces_per_step": sample},
+            "cpu_baseline": {"value": fps, "unit": "faces/s", "cores": cores, "kind": "port",
+                             "sample": "%d faces/step: cv2.resize+cvtColor, torch-CPU fp32 restatement of the Keras graph "
+                                       "(TensorFlow not installable), numpy decode, fp64 Umeyama, cv2.warpAffine" % sample},
+            "e2e": {"value": fps, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, world, local_rank):
+    from keypoints_detector import _native, prediction
+    from keypoints_detector.networks.regression import landmark_regressor
+    import __graft_entry__ as entry
+    if local_rank == 0:
+        entry.build()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    dtype = "bfloat16" if args.dtype == "bf16" else "float32"
+    model = landmark_regressor().init_weights(seed=0)
+    pipe = prediction.LandmarkPipeline(model, dtype=dtype, device=dev)
+
+    n_sets = args.sets
+    host_sets = [make_set(B, 100 + 10 * rank + s) for s in range(n_sets)]
+    dev_sets = [tuple(t.to(dev) for t in hs) for hs in host_sets]
+    set_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            fn(k)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)
+
+    # ---- device-resident throughput
+    def step_resident(k):
+        pipe.run_device(*dev_sets[k % n_sets])
+
+    for k in range(args.warmup):
+        step_resident(k)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _native.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _native.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    total_faces = sum_over_ranks(B, dev)
+    value = total_faces * args.steps / (ms * 1e-3)
+
+    # ---- second timed pass with per-layer CUDA events: live duration of the dominant kernel (roofline)
+    model.set_profiling(True, dev, dtype)
+    per_layer = np.zeros(len(model.graph.layers))
+    barrier()
+    for k in range(args.steps):
+        step_resident(k)
+        per_layer += np.array([t for _, t in model.layer_times(dev, dtype)])
+    model.set_profiling(False, dev, dtype)
+    per_layer /= args.steps
+    conv_flops, fc_flops = flops_per_face()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if dtype == "bfloat16":
+        # dominant kernel: conv_tma_kernel (conv2..conv5, four launches per step)
+        t_dom = float(per_layer[1:5].sum()) * 1e-3
+        fl = sum(conv_flops[1:5]) * B
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        roof = {"kernel": "conv_tma_kernel (conv2..conv5, 4 launches/step)", "bound": "tensor", "achieved": fl / t_dom / 1e12,
+                "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (sustained, B200_PROFILING.md)",
+                "unit": "TFLOP/s", "traffic": None, "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3}
+    else:
+        t_dom = float(per_layer[0:5].sum()) * 1e-3
+        fl = sum(conv_flops) * B
+        peak = 75.0  # fp32 FMA nominal: 148 SMs x 128 lanes x 2 x ~1.97 GHz
+        roof = {"kernel": "conv_simt_kernel (conv1..conv5, fp32 CUDA cores)", "bound": "fp32-fma", "achieved": fl / t_dom / 1e12, "peak": peak,
+                "peak_source": "nominal fp32 FMA (no measured fp32 peak in MEASURED_PEAKS.json)", "unit": "TFLOP/s", "traffic": None,
+                "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["layer_ms"] = {L["name"]: round(float(t), 5) for L, t in zip(model.graph.layers, per_layer)}
+
+    # ---- end to end through the public API objects with HOST (pinned) buffers: H2D + compute + D2H every step
+    pin_sets = [tuple(t.pin_memory() for t in hs) for hs in host_sets]
+    marks_h = [torch.empty((B, 68, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    crops_h = [torch.empty((B, 112, 112, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(2)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_comp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+
+    def step_e2e(k):
+        sl = k % 2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_comp[sl])                      # slot's previous compute finished
+            for d, h in zip(slots[sl], pin_sets[k % n_sets]):
+                d.copy_(h, non_blocking=True)
+            ev_in[sl].record(s_in)
+        main.wait_event(ev_in[sl])
+        r = pipe.run_device(*slots[sl])
+        ev_comp[sl].record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_comp[sl])
+            s_out.wait_event(ev_out[sl])                      # pinned slot's previous D2H finished
+            r["marks"].record_stream(s_out); r["aligned"].record_stream(s_out)
+            marks_h[sl].copy_(r["marks"], non_blocking=True)
+            crops_h[sl].copy_(r["aligned"], non_blocking=True)
+            ev_out[sl].record(s_out)
+
+    def e2e_all(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for k in range(steps):
+            step_e2e(k)
+        main.wait_stream(s_out); main.wait_stream(s_in)
+        e1.record(main)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)
+
+    e2e_all(max(args.warmup, 2))
+    ms_e2e = e2e_all(args.steps)
+    e2e_val = total_faces * args.steps / (ms_e2e * 1e-3)
+    d2h = marks_h[0].numel() * 4 + crops_h[0].numel()
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            fps, cms, cores = time_cpu(64, 3, 1)
+            cpu = {"value": fps, "unit": "faces/s", "cores": cores, "kind": "port",
+                   "sample": "3 steps x 64 faces of the same workload: cv2.resize+cvtColor, torch-CPU fp32 restatement of the Keras "
+                             "graph (TensorFlow not installable), numpy decode, fp64 Umeyama, cv2.warpAffine"}
+        line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if dtype == "bfloat16" else "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: batch-%d crops/GPU from %d 1080p frames, vanilla trunk@128 + FC-136 head, "
+                                       "+ decode + 5-point align warp to 112x112" % (B, -(-B // FACES_PER_FRAME)),
+                           "batch_per_gpu": B, "global_batch": int(total_faces), "parallelism": "faces sharded, no collective",
+                           "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2; activations workspace rewritten every step"
+                                 % (n_sets, n_sets * set_bytes / 1e6)},
+                "e2e": {"value": e2e_val, "unit": "faces/s", "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--sets", type=int, default=6)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        return run_gpu(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -46,6 +46,9 @@ struct fld_net {
   std::vector<TensorInfo> tensors;  // [0] = input
   std::vector<LayerRt> layers;
   bool finalized = false;
+  bool profiling = false;
+  bool profiled_once = false;
+  std::vector<cudaEvent_t> events;  // n_layers + 1, recorded around every layer when profiling
 };
 
 namespace {
@@ -176,6 +179,7 @@ extern "C" void fld_net_destroy(fld_net* net) {
   if (!net) return;
   cudaSetDevice(net->h->device);
   for (auto& L : net->layers) free_layer(L);
+  for (auto e : net->events) cudaEventDestroy(e);
   delete net;
 }
 
@@ -325,6 +329,7 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
       off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
     }
   }
+  if (net->profiling) FLD_CUDA(cudaEventRecord(net->events[0], st));
   for (size_t i = 0; i < net->layers.size(); ++i) {
     LayerRt& L = net->layers[i];
     const fld_layer_desc& d = L.d;
@@ -375,7 +380,9 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
         rc = FLD_ERR_INVALID;
     }
     if (rc) return rc;
+    if (net->profiling) FLD_CUDA(cudaEventRecord(net->events[i + 1], st));
   }
+  if (net->profiling) net->profiled_once = true;
   if (out) {
     const TensorInfo& o = net->tensors[nT - 1];
     const size_t n = o.elems() * (size_t)B;
@@ -383,4 +390,28 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
     else { rc = simt_cvt_bf16_f32(ptr[nT - 1], out, (long long)n, st); if (rc) return rc; }
   }
   return FLD_OK;
+}
+
+extern "C" int fld_net_set_profiling(fld_net* net, int enable) {
+  FLD_REQUIRE(net, "fld_net_set_profiling: null net");
+  int rc = fld_enter(net->h);
+  if (rc) return rc;
+  if (enable && net->events.empty()) {
+    net->events.resize(net->layers.size() + 1);
+    for (auto& e : net->events) FLD_CUDA(cudaEventCreate(&e));
+  }
+  net->profiling = enable != 0;
+  net->profiled_once = false;
+  return FLD_OK;
+}
+
+extern "C" int fld_net_layer_times(fld_net* net, float* ms_h, int n) {
+  FLD_REQUIRE(net && ms_h, "fld_net_layer_times: null pointer");
+  FLD_REQUIRE(n >= (int)net->layers.size(), "fld_net_layer_times: need room for %zu layers", net->layers.size());
+  if (!net->profiled_once) { fld_set_error("fld_net_layer_times: no profiled forward yet"); return FLD_ERR_STATE; }
+  int rc = fld_enter(net->h);
+  if (rc) return rc;
+  FLD_CUDA(cudaEventSynchronize(net->events.back()));
+  for (size_t i = 0; i < net->layers.size(); ++i) FLD_CUDA(cudaEventElapsedTime(&ms_h[i], net->events[i], net->events[i + 1]));
+  return (int)net->layers.size();
 }

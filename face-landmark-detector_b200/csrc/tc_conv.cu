@@ -248,7 +248,10 @@ conv_first_kernel(const FirstParams p) {
     mbar_init(smem_u32(&mma_bar), 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();

@@ -1,0 +1,317 @@
+"""Model object of the B200 build: a layer list in the vocabulary of the reference's Keras graphs,
+host weights in Keras layouts, and per-(GPU, dtype) compiled fld_net instances.
+
+It honours the duck type the reference's callers use (reference
+networks/utils.py:31-37, prediction.py:84,128,181-185,208):
+  attributes  output_width, output_height, n_classes, input_height, input_width, model_name
+  methods     predict(np[B,H,W,C]) -> np, load_weights(path), signatures["predict"](uint8[1,128,128,3])['output']
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+BN_EPS = 1e-3  # Keras BatchNormalization default
+
+
+class Graph:
+    """Records layers; tensor 0 is the input, layer i produces tensor i+1 (include/fld.h)."""
+
+    def __init__(self, input_height, input_width, channels):
+        self.input_shape = (int(input_height), int(input_width), int(channels))
+        self.layers = []   # dicts: name, op, in0, in1, kh, kw, stride, pads, cout, act, pool, has_bias, has_bn, in_scale
+        self.shapes = [self.input_shape]
+
+    def _add(self, **kw):
+        self.layers.append(kw)
+        return len(self.layers)  # tensor id
+
+    def conv(self, x, name, cout, k, pad=(0, 0, 0, 0), stride=1, act=N.ACT_NONE, pool=0, bias=True, bn=False, in_scale=1.0,
+             bn_name=None):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        if pad == "same":
+            th, tw = kh - 1, kw - 1
+            pad = (th // 2, th - th // 2, tw // 2, tw - tw // 2)
+        h, w, _ = self.shapes[x]
+        oh = (h + pad[0] + pad[1] - kh) // stride + 1
+        ow = (w + pad[2] + pad[3] - kw) // stride + 1
+        if pool:
+            oh, ow = oh // 2, ow // 2
+        self.shapes.append((oh, ow, cout))
+        return self._add(name=name, op=N.OP_CONV, in0=x, in1=-1, kh=kh, kw=kw, stride=stride, pad=tuple(pad), cout=cout,
+                         act=act, pool=pool, has_bias=bias, has_bn=bn, in_scale=in_scale,
+                         bn_name=bn_name or name.replace("conv", "bn"))
+
+    def deconv(self, x, name, cout, k, stride):
+        h, w, _ = self.shapes[x]
+        self.shapes.append(((h - 1) * stride + k, (w - 1) * stride + k, cout))
+        return self._add(name=name, op=N.OP_DECONV, in0=x, in1=-1, kh=k, kw=k, stride=stride, pad=(0, 0, 0, 0), cout=cout,
+                         act=0, pool=0, has_bias=False, has_bn=False, in_scale=1.0)
+
+    def add(self, a, b, name):
+        ha, wa, c = self.shapes[a]
+        hb, wb, _ = self.shapes[b]
+        self.shapes.append((min(ha, hb), min(wa, wb), c))
+        return self._add(name=name, op=N.OP_ADD, in0=a, in1=b, kh=0, kw=0, stride=1, pad=(0, 0, 0, 0), cout=c, act=0, pool=0,
+                         has_bias=False, has_bn=False, in_scale=1.0)
+
+    def dense(self, x, name, units, act=N.ACT_NONE):
+        self.shapes.append((1, 1, units))
+        return self._add(name=name, op=N.OP_DENSE, in0=x, in1=-1, kh=0, kw=0, stride=1, pad=(0, 0, 0, 0), cout=units, act=act,
+                         pool=0, has_bias=True, has_bn=False, in_scale=1.0)
+
+    def softmax(self, x, name="softmax"):
+        self.shapes.append(self.shapes[x])
+        return self._add(name=name, op=N.OP_SOFTMAX, in0=x, in1=-1, kh=0, kw=0, stride=1, pad=(0, 0, 0, 0), cout=self.shapes[x][2],
+                         act=0, pool=0, has_bias=False, has_bn=False, in_scale=1.0)
+
+
+def weight_specs(graph):
+    """name -> shape for every weight array, in Keras layouts."""
+    specs = {}
+    for L in graph.layers:
+        cin = graph.shapes[L["in0"]][2]
+        n = L["name"]
+        if L["op"] == N.OP_CONV:
+            specs[n + "/kernel"] = (L["kh"], L["kw"], cin, L["cout"])
+            if L["has_bias"]:
+                specs[n + "/bias"] = (L["cout"],)
+            if L["has_bn"]:
+                bn = L["bn_name"]
+                for s in ("gamma", "beta", "moving_mean", "moving_variance"):
+                    specs[bn + "/" + s] = (L["cout"],)
+        elif L["op"] == N.OP_DECONV:
+            specs[n + "/kernel"] = (L["kh"], L["kw"], L["cout"], cin)
+        elif L["op"] == N.OP_DENSE:
+            h, w, c = graph.shapes[L["in0"]]
+            specs[n + "/kernel"] = (h * w * c, L["cout"])
+            specs[n + "/bias"] = (L["cout"],)
+    return specs
+
+
+class _Signature:
+    """model.signatures["predict"](uint8[B,S,S,3]) -> {'output': float32[B,136]} (reference prediction.py:84)."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def __call__(self, x, **_):
+        x = np.asarray(x)
+        return {"output": self._m.predict(x)}
+
+
+class Model:
+    def __init__(self, graph, kind, model_name="", n_classes=None, in_dtype="float32"):
+        self.graph = graph
+        self.kind = kind                     # "segmentation" | "regression"
+        self.model_name = model_name
+        self.input_height, self.input_width, self.channels = graph.input_shape
+        oh, ow, oc = graph.shapes[-1]
+        if kind == "segmentation":
+            self.output_height, self.output_width = oh, ow
+            self.n_classes = oc if n_classes is None else n_classes
+        else:
+            self.output_height = self.output_width = 1
+            self.n_classes = oc
+        self.in_dtype = in_dtype             # "uint8" | "float32"
+        self.compute_dtype = "float32"       # "float32" (parity mode) | "bfloat16" (tensor cores)
+        self.weights = {}
+        self._specs = weight_specs(graph)
+        self._nets = {}                      # (device index, compute) -> (net handle, ...)
+        self._ws = {}                        # (device index, compute) -> torch.uint8 workspace
+        self.signatures = {"predict": _Signature(self)}
+
+    # ------------------------------------------------------------------ weights
+    def weight_specs(self):
+        return dict(self._specs)
+
+    def set_weights(self, weights):
+        for k, shp in self._specs.items():
+            if k not in weights:
+                raise KeyError("missing weight %r" % k)
+            a = np.ascontiguousarray(weights[k], dtype=np.float32)
+            if tuple(a.shape) != tuple(shp):
+                raise ValueError("weight %r has shape %s, expected %s" % (k, a.shape, shp))
+            self.weights[k] = a
+        self._release()
+
+    def get_weights(self):
+        return dict(self.weights)
+
+    def init_weights(self, seed=0, nontrivial_bn=True):
+        from .init import random_weights
+        self.set_weights(random_weights(self, seed, nontrivial_bn))
+        return self
+
+    def save_weights(self, path):
+        np.savez(path if path.endswith(".npz") else path + ".npz", **self.weights)
+
+    def load_weights(self, path):
+        """Weights container of this build: .npz keyed by layer name in Keras layouts (the reference's
+        TF-checkpoint format cannot be read without TensorFlow)."""
+        p = path if os.path.exists(path) else path + ".npz"
+        with np.load(p) as z:
+            self.set_weights({k: z[k] for k in z.files})
+        return None
+
+    # ------------------------------------------------------------------ device side
+    def _release(self):
+        lib = N.load_library() if self._nets else None
+        for (net, _) in self._nets.values():
+            lib.fld_net_destroy(net)
+        self._nets.clear()
+        self._ws.clear()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _compute_code(self, dtype=None):
+        d = dtype or self.compute_dtype
+        if d in ("float32", "fp32", torch.float32):
+            return N.FLD_F32
+        if d in ("bfloat16", "bf16", torch.bfloat16):
+            return N.FLD_BF16
+        raise ValueError("compute dtype must be float32 or bfloat16, got %r" % (d,))
+
+    def compiled(self, device=None, dtype=None):
+        """fld_net for (device, dtype); built and weight-loaded on first use."""
+        if not self.weights:
+            raise N.FldError("model has no weights: call init_weights() or load_weights() first")
+        lib = N.load_library()
+        h = N.handle(device)
+        dev = torch.cuda.current_device() if device is None else torch.device(device).index
+        comp = self._compute_code(dtype)
+        key = (dev, comp)
+        if key in self._nets:
+            return self._nets[key][0]
+        g = self.graph
+        descs = (N.LayerDesc * len(g.layers))()
+        for i, L in enumerate(g.layers):
+            d = descs[i]
+            d.op, d.in0, d.in1 = L["op"], L["in0"], L["in1"]
+            d.kh, d.kw, d.stride = L["kh"], L["kw"], L["stride"]
+            d.pad_t, d.pad_b, d.pad_l, d.pad_r = L["pad"]
+            d.cout, d.act, d.pool = L["cout"], L["act"], L["pool"]
+            d.has_bias, d.has_bn, d.in_scale = int(L["has_bias"]), int(L["has_bn"]), float(L["in_scale"])
+        net = N._vp()
+        ih, iw, ic = g.input_shape
+        with torch.cuda.device(dev):
+            N.check(lib.fld_net_create(h, descs, len(g.layers), ih, iw, ic, N.FLD_U8 if self.in_dtype == "uint8" else N.FLD_F32,
+                                       comp, ctypes.byref(net)))
+            for i, L in enumerate(g.layers):
+                n = L["name"]
+                if L["op"] not in (N.OP_CONV, N.OP_DECONV, N.OP_DENSE):
+                    continue
+                k = self.weights[n + "/kernel"]
+                b = self.weights.get(n + "/bias") if L["has_bias"] else None
+                bn = None
+                if L["has_bn"]:
+                    bname = L["bn_name"]
+                    bn = np.ascontiguousarray(np.concatenate([self.weights[bname + "/" + s] for s in
+                                                              ("gamma", "beta", "moving_mean", "moving_variance")]), dtype=np.float32)
+                N.check(lib.fld_net_set_weights(net, i, N.host_ptr(k), N.host_ptr(b), N.host_ptr(bn), BN_EPS))
+            N.check(lib.fld_net_finalize(net))
+        self._nets[key] = (net, h)
+        return net
+
+    def set_profiling(self, enable, device=None, dtype=None):
+        """Bracket every layer with CUDA events in forward_device (bench.py's live per-kernel timing)."""
+        N.check(N.load_library().fld_net_set_profiling(self.compiled(device, dtype), int(enable)))
+
+    def layer_times(self, device=None, dtype=None):
+        """[(layer name, ms)] of the last profiled forward (waits for it)."""
+        n = len(self.graph.layers)
+        buf = (ctypes.c_float * n)()
+        rc = N.load_library().fld_net_layer_times(self.compiled(device, dtype), buf, n)
+        if rc < 0:
+            N.check(rc)
+        return [(L["name"], float(buf[i])) for i, L in enumerate(self.graph.layers)]
+
+    def tensor_info(self, tensor, device=None, dtype=None):
+        net = self.compiled(device, dtype)
+        hwc = (ctypes.c_int32 * 3)()
+        dt = N.load_library().fld_net_tensor_shape(net, tensor, hwc)
+        if dt < 0:
+            N.check(dt)
+        return tuple(hwc), dt
+
+    def forward_device(self, x, dtype=None, out=None, return_workspace=False):
+        """x: CUDA tensor [B,H,W,C] (uint8 or float32 per model.in_dtype) -> float32 CUDA tensor of the final layer."""
+        lib = N.load_library()
+        assert x.is_cuda and x.is_contiguous()
+        exp = torch.uint8 if self.in_dtype == "uint8" else torch.float32
+        if x.dtype != exp:
+            raise TypeError("model expects %s input, got %s" % (exp, x.dtype))
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != self.graph.input_shape:
+            raise ValueError("input shape %s != model input %s" % (tuple(x.shape[1:]), self.graph.input_shape))
+        dev = x.device.index
+        with torch.cuda.device(dev):
+            net = self.compiled(dev, dtype)
+            comp = self._compute_code(dtype)
+            need = lib.fld_net_workspace_bytes(net, B)
+            ws = self._ws.get((dev, comp))
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+                self._ws[(dev, comp)] = ws
+            base = ws.data_ptr()
+            al = (-base) % 1024
+            oh, ow, oc = self.graph.shapes[-1]
+            if out is None:
+                out = torch.empty((B, oh * ow, oc) if self.kind == "segmentation" else (B, oc), dtype=torch.float32, device=x.device)
+            N.check(lib.fld_net_forward(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(out), N.stream_ptr(dev)))
+        if return_workspace:
+            return out, ws, al
+        return out
+
+    def intermediate(self, x, tensor, dtype=None):
+        """Run forward and return intermediate tensor `tensor` ([B,h,w,c] float32 CUDA) — parity checks of the levels."""
+        out, ws, al = self.forward_device(x, dtype, return_workspace=True)
+        lib = N.load_library()
+        net = self.compiled(x.device.index, dtype)
+        (h, w, c), dt = self.tensor_info(tensor, x.device.index, dtype)
+        off = lib.fld_net_tensor_offset(net, tensor, x.shape[0])
+        B = x.shape[0]
+        n = B * h * w * c
+        tdt = {N.FLD_F32: torch.float32, N.FLD_BF16: torch.bfloat16, N.FLD_U8: torch.uint8}[dt]
+        esz = {N.FLD_F32: 4, N.FLD_BF16: 2, N.FLD_U8: 1}[dt]
+        raw = ws[al + off: al + off + n * esz]
+        return raw.view(tdt).view(B, h, w, c).float()
+
+    def predict(self, x, batch_size=None, dtype=None, device=None):
+        """Keras-style predict on a NumPy batch [B,H,W,C]; returns NumPy (segmentation: [B, oh*ow, n_classes]
+        softmax probabilities as networks/utils.py:28-30; regression: [B, 136])."""
+        x = np.ascontiguousarray(x, dtype=np.uint8 if self.in_dtype == "uint8" else np.float32)
+        if x.ndim == 3:
+            x = x[None]
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index) \
+            if torch.cuda.is_available() else None
+        if dev is None:
+            N.handle()  # raises the no-GPU error
+        B = x.shape[0]
+        if batch_size is None:
+            oh, ow, oc = self.graph.shapes[-1]
+            per_item = 64 * self.input_height * self.input_width * 4 + oh * ow * oc * 16
+            batch_size = max(1, min(B, int(8e9 // max(per_item, 1))))
+        outs = []
+        for s in range(0, B, batch_size):
+            xt = torch.from_numpy(x[s:s + batch_size]).to(dev, non_blocking=False)
+            outs.append(self.forward_device(xt, dtype).cpu().numpy())
+        return np.concatenate(outs, axis=0)
+
+    # ------------------------------------------------------------------ config sidecar (reference training.py:187-200)
+    def config_dict(self, model_class=None):
+        return {"model_class": model_class or self.model_name, "n_classes": int(self.n_classes),
+                "input_height": int(self.input_height), "input_width": int(self.input_width),
+                "output_height": int(self.output_height), "output_width": int(self.output_width)}
+
+    def save_config(self, checkpoints_path, model_class=None):
+        with open(checkpoints_path + "_config.json", "w") as f:
+            json.dump(self.config_dict(model_class), f)

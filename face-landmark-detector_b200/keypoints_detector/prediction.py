@@ -1,0 +1,334 @@
+"""keypoints_detector.prediction — drop-in for the reference module of the same name, with the arithmetic
+on a B200 (sm_100a CUDA kernels behind libfld_sm100.so).
+
+Unchanged entry points (reference prediction.py): detect_marks :16-96, video_predict :99-113,
+model_from_checkpoint_path :116-133, keypts_predict :158-196, _prediction :199-222.
+Additions: detect_marks_batch, align_faces, LandmarkPipeline (device-resident batched path used by
+bench.py and example.py), shard_faces (multi-GPU batch sharding).
+
+Where the reference crashes as written behaviour is defined and documented inline.
+"""
+import json
+import os
+import typing
+
+import numpy as np
+import six
+import torch
+
+from . import _native as N
+from .data.config import IMAGE_ORDERING
+from .data.generator import get_image_array
+from .training import find_latest_checkpoint
+from .utils.plots import class_colors, draw_marks, visualize_keypoints
+
+# widely used 112x112 five-point alignment template
+TEMPLATE_112 = np.array([[38.2946, 51.6963], [73.5318, 51.5014], [56.0252, 71.7366],
+                         [41.5493, 92.3655], [70.7299, 92.2041]], dtype=np.float64)
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        N.handle()  # raises: CUDA-only, no CPU fallback
+    return torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index)
+
+
+# ----------------------------------------------------------------------------------------------- device ops
+def preprocess_faces_device(frames, boxes, face2frame, size=128, swap_rb=True):
+    """frames uint8 CUDA [F,H,W,3] BGR; boxes int32 CUDA [B,4]; face2frame int32 CUDA [B].
+    -> (crops uint8 [B,size,size,3] RGB, faceboxes int32 [B,4]); reference prediction.py:76-83."""
+    lib = N.load_library()
+    F, H, W, C = frames.shape
+    assert C == 3 and frames.dtype == torch.uint8
+    B = boxes.shape[0]
+    out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=frames.device)
+    fb = torch.empty((B, 4), dtype=torch.int32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        N.check(lib.fld_preprocess_faces(N.handle(frames.device), N.ptr(frames), F, H, W, N.ptr(boxes), N.ptr(face2frame), B, size,
+                                         int(swap_rb), N.ptr(out), N.ptr(fb), N.stream_ptr(frames.device)))
+    return out, fb
+
+
+def decode_regress_device(out136, faceboxes, want_uint=True):
+    """reference prediction.py:88-94 on device: -> (marks float32 [B,68,2], marks uint64-as-int64 [B,68,2] or None)."""
+    lib = N.load_library()
+    B = out136.shape[0]
+    marks = torch.empty((B, 68, 2), dtype=torch.float32, device=out136.device)
+    marks_u = torch.empty((B, 68, 2), dtype=torch.int64, device=out136.device) if want_uint else None
+    with torch.cuda.device(out136.device):
+        N.check(lib.fld_decode_regress(N.handle(out136.device), N.ptr(out136), out136.shape[1], N.ptr(faceboxes), B, N.ptr(marks),
+                                       N.ptr(marks_u), N.stream_ptr(out136.device)))
+    return marks, marks_u
+
+
+def align_device(frames, face2frame, marks, template=None, out_size=(112, 112), five_point=True, return_matrix=True):
+    """Umeyama fit + cv2.warpAffine-exact warp on device.  marks float32 CUDA [B,N,2] in frame pixels."""
+    lib = N.load_library()
+    F, H, W, C = frames.shape
+    B, Np = marks.shape[0], marks.shape[1]
+    tmpl = TEMPLATE_112 if template is None else np.asarray(template, dtype=np.float64)
+    t = torch.from_numpy(np.ascontiguousarray(tmpl, dtype=np.float64)).to(frames.device)
+    oh, ow = out_size
+    crops = torch.empty((B, oh, ow, C), dtype=torch.uint8, device=frames.device)
+    M = torch.empty((B, 2, 3), dtype=torch.float64, device=frames.device) if return_matrix else None
+    with torch.cuda.device(frames.device):
+        N.check(lib.fld_align(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(marks), Np, N.ptr(t),
+                              t.shape[0], int(five_point), B, oh, ow, N.ptr(M), N.ptr(crops), N.stream_ptr(frames.device)))
+    return crops, M
+
+
+def warp_affine_device(frames, face2frame, M, out_size=(112, 112)):
+    lib = N.load_library()
+    F, H, W, C = frames.shape
+    B = M.shape[0]
+    oh, ow = out_size
+    crops = torch.empty((B, oh, ow, C), dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        N.check(lib.fld_warp_affine(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(M), B, oh, ow,
+                                    N.ptr(crops), N.stream_ptr(frames.device)))
+    return crops
+
+
+def class_map_device(scores, oh, ow):
+    """reference prediction.py:209 on device: scores float32 CUDA [B, oh*ow, L] -> int64 [B,oh,ow]."""
+    lib = N.load_library()
+    B, hw, L = scores.shape
+    out = torch.empty((B, oh, ow), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        N.check(lib.fld_decode_classmap(N.handle(scores.device), N.ptr(scores), B, hw, L, N.ptr(out), N.stream_ptr(scores.device)))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- batched pipeline
+class LandmarkPipeline:
+    """frames + detector boxes -> 68 landmarks -> aligned crops, entirely on one GPU:
+    crop/resize (a1) -> regression CNN (a2) -> decode (a3) -> Umeyama + warp (a10)."""
+
+    def __init__(self, model, dtype="float32", out_size=(112, 112), template=None, device=None):
+        self.model = model
+        self.dtype = dtype
+        self.out_size = tuple(out_size)
+        self.template = TEMPLATE_112 if template is None else np.asarray(template, dtype=np.float64)
+        self.device = _device(device)
+        self.input_size = model.input_height
+        model.compiled(self.device, dtype)
+
+    def run_device(self, frames, boxes, face2frame, want_uint=False):
+        crops128, fb = preprocess_faces_device(frames, boxes, face2frame, self.input_size, True)
+        out = self.model.forward_device(crops128, self.dtype)
+        marks, marks_u = decode_regress_device(out, fb, want_uint)
+        aligned, M = align_device(frames, face2frame, marks, self.template, self.out_size, True, True)
+        return {"marks": marks, "marks_uint": marks_u, "aligned": aligned, "M": M, "faceboxes": fb, "crops": crops128}
+
+    def __call__(self, frames, boxes, face2frame=None):
+        """NumPy in / NumPy out convenience (H2D, run, D2H)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+        if face2frame is None:
+            face2frame = np.zeros(len(boxes), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            r = self.run_device(torch.from_numpy(frames).to(self.device), torch.from_numpy(boxes).to(self.device),
+                                torch.from_numpy(np.ascontiguousarray(face2frame, dtype=np.int32)).to(self.device), True)
+            return {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+
+
+def shard_faces(n_faces, n_shards):
+    """Contiguous split of a face batch over GPUs: [(start, stop)] per shard."""
+    per = -(-n_faces // max(n_shards, 1))
+    return [(min(i * per, n_faces), min((i + 1) * per, n_faces)) for i in range(n_shards)]
+
+
+# ----------------------------------------------------------------------------------------------- reference API
+def detect_marks(img, model, face, dtype=None):
+    """Find the 68 facial landmarks of one face (reference prediction.py:16-96).
+
+    img: np.uint8 [H,W,3] BGR; model: landmark_regressor (or any object whose forward_device maps uint8
+    [B,128,128,3] RGB to [B,>=136]); face: (x0, y0, x1, y1).  Returns np.uint (68,2) — same dtype/shape.
+    Box math, crop, cv2.resize-exact resize, BGR2RGB, CNN, scale-back and the uint cast all run on the GPU.
+    A box that leaves the image on the top/left makes the reference raise inside cv2.resize; here it raises
+    ValueError (use detect_marks_batch for clipping behaviour)."""
+    fbx = _square_box_host(face)
+    if fbx[0] < 0 or fbx[1] < 0 or fbx[0] >= img.shape[1] or fbx[1] >= img.shape[0] or fbx[2] <= fbx[0]:
+        raise ValueError("face box %s leaves the image on the top/left: empty crop (the reference fails in cv2.resize here)" % (fbx,))
+    marks_u = detect_marks_batch(img[None], [face], [0], model, dtype=dtype)[1]
+    return marks_u[0].astype(np.uint)
+
+
+def detect_marks_batch(frames, faces, face2frame, model, dtype=None, device=None):
+    """Batched detect_marks: frames uint8 [F,H,W,3] BGR, faces [B,4], face2frame [B] ->
+    (marks float32 [B,68,2] pre-cast, marks np.uint64 [B,68,2])."""
+    dev = _device(device)
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    boxes = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 4)
+    f2f = np.ascontiguousarray(face2frame, dtype=np.int32)
+    with torch.cuda.device(dev):
+        fr = torch.from_numpy(frames).to(dev)
+        crops, fb = preprocess_faces_device(fr, torch.from_numpy(boxes).to(dev), torch.from_numpy(f2f).to(dev), model.input_height)
+        out = model.forward_device(crops, dtype)
+        marks, marks_u = decode_regress_device(out, fb, True)
+        return marks.cpu().numpy(), marks_u.cpu().numpy().astype(np.uint64)
+
+
+def _square_box_host(face):
+    """prediction.py:36-78 on the host (argument checking only; the kernel recomputes it)."""
+    x0, y0, x1, y1 = [int(v) for v in face]
+    off = int(abs((y1 - y0) * 0.1))
+    y0 += off
+    y1 += off
+    diff = (y1 - y0) - (x1 - x0)
+    delta = int(abs(diff) / 2)
+    if diff > 0:
+        x0 -= delta
+        x1 += delta + (1 if diff % 2 == 1 else 0)
+    elif diff < 0:
+        y0 -= delta
+        y1 += delta + (1 if diff % 2 == 1 else 0)
+    return [x0, y0, x1, y1]
+
+
+def align_faces(frames, marks, face2frame=None, template=None, out_size=(112, 112), mode="5pt", device=None, return_matrix=False):
+    """New in this build (the reference has no alignment): similarity-align faces.
+
+    frames uint8 [F,H,W,C] or [H,W,C]; marks [B,68,2] (mode "5pt": reduced to eye centres / nose / mouth corners and
+    fitted to the 112x112 five-point template) or [B,N,2] with a caller-supplied [N,2] template (mode "full").
+    Returns aligned uint8 crops [B,oh,ow,C] (and the fp64 2x3 matrices)."""
+    dev = _device(device)
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    if frames.ndim == 3:
+        frames = frames[None]
+    marks = np.ascontiguousarray(marks, dtype=np.float32)
+    if marks.ndim == 2:
+        marks = marks[None]
+    if face2frame is None:
+        face2frame = np.zeros(marks.shape[0], dtype=np.int32)
+    five = mode == "5pt"
+    if not five and template is None:
+        raise ValueError("mode='full' needs a template with one row per landmark")
+    with torch.cuda.device(dev):
+        crops, M = align_device(torch.from_numpy(frames).to(dev), torch.from_numpy(np.ascontiguousarray(face2frame, np.int32)).to(dev),
+                                torch.from_numpy(marks).to(dev), template, out_size, five, True)
+        crops = crops.cpu().numpy()
+        return (crops, M.cpu().numpy()) if return_matrix else crops
+
+
+def video_predict(facedetector_fn, landmark_model, capture=0, max_frames=None, show=True):
+    """reference prediction.py:99-113, with all faces of a frame decoded in one batched GPU call."""
+    import cv2
+    cap = cv2.VideoCapture(capture)
+    n = 0
+    while True:
+        ok, img = cap.read()
+        if not ok:
+            break
+        rects = list(facedetector_fn(img))
+        if rects:
+            _, marks_u = detect_marks_batch(img[None], rects, [0] * len(rects), landmark_model)
+            for marks in marks_u:
+                draw_marks(img, marks.astype(np.int64))
+        if show:
+            cv2.imshow("image", img)
+            if cv2.waitKey(1) & 0xFF == ord('q'):
+                break
+        n += 1
+        if max_frames is not None and n >= max_frames:
+            break
+    cap.release()
+    if show:
+        cv2.destroyAllWindows()
+
+
+def model_from_checkpoint_path(checkpoints_path: str):
+    """reference prediction.py:116-133.  The sidecar keeps the reference schema (training.py:195-200) plus the
+    input_height/input_width keys the reference loader reads but its trainer never writes (App. D); when they are
+    absent the builder defaults are used.  Weights are .npz (see Model.load_weights)."""
+    from .networks.basic_models import LANDMARKS_MODELS
+    assert (os.path.isfile(checkpoints_path + "_config.json")), "Checkpoint not found."
+    model_config = json.loads(open(checkpoints_path + "_config.json", "r").read())
+    latest_weights = find_latest_checkpoint(checkpoints_path)
+    assert (latest_weights is not None), "Checkpoint not found."
+    kwargs = {}
+    if model_config.get('input_height') is not None:
+        kwargs['input_height'] = model_config['input_height']
+    if model_config.get('input_width') is not None:
+        kwargs['input_width'] = model_config['input_width']
+    model = LANDMARKS_MODELS[model_config['model_class']](model_config['n_classes'], **kwargs)
+    print("loaded weights ", latest_weights)
+    model.load_weights(latest_weights)
+    return model
+
+
+def keypts_predict(
+        model=None,
+        inp: typing.Union[np.ndarray, str] = None,
+        out_fname: str = None,
+        checkpoints_path: str = None, overlay_img: bool = False,
+        class_names=None, show_legends: bool = False, colors: typing.List[tuple] = class_colors,
+        pred_dim: typing.Tuple[int] = None, read_image_type=1
+) -> np.ndarray:
+    """reference prediction.py:158-196.  Differences, all where the reference crashes (App. D): the os.path.isdir
+    test is only applied to string inputs (a directory is iterated), and the class map is returned."""
+    import cv2
+    if model is None and checkpoints_path is None:
+        raise ValueError("Both model and checkpoint_path cannot be empty")
+
+    if model is None and (checkpoints_path is not None):
+        model = model_from_checkpoint_path(checkpoints_path)
+
+    assert (inp is not None), "Invalid input, should be either directory, ndarray or image path"
+    assert ((type(inp) is np.ndarray) or isinstance(inp, six.string_types)), \
+        "Input should be the CV image or the input file name"
+
+    args = (model.input_width, model.input_height, model.output_height, model.output_width, model.n_classes, colors,
+            show_legends, class_names, pred_dim, overlay_img)
+    if isinstance(inp, six.string_types) and os.path.isdir(inp):
+        results = []
+        for name in sorted(os.listdir(inp)):
+            if os.path.splitext(name)[1].lower() in (".jpg", ".jpeg", ".png", ".bmp"):
+                img = cv2.imread(os.path.join(inp, name), read_image_type)
+                of = None if out_fname is None else os.path.join(out_fname, name)
+                results.append(_prediction(model, img, *args, of))
+        return results
+
+    if isinstance(inp, six.string_types):
+        inp = cv2.imread(inp, read_image_type)
+
+    assert (len(inp.shape) == 3 or len(inp.shape) == 1 or len(inp.shape) == 4), "Image should be h,w,3 "
+    return _prediction(model, inp, *args, out_fname)
+
+
+def _prediction(
+        model, inp: np.ndarray,
+        input_width: int, input_height: int,
+        output_height: int, output_width: int,
+        n_classes: int, colors: typing.List[typing.Tuple],
+        show_legends: bool, class_names: typing.List[str],
+        pred_dim: typing.Tuple[int], overlay_img: bool, out_fname: str
+):
+    """reference prediction.py:199-222: pre-process, forward, per-pixel argmax over classes -> (oh,ow) int64.
+    The softmax output stays on the GPU; only the class map is copied back."""
+    import cv2
+    dev = _device()
+    if hasattr(model, "forward_device"):
+        x = get_image_array(inp, input_width, input_height, ordering=IMAGE_ORDERING, as_tensor=True)
+        with torch.cuda.device(dev):
+            probs = model.forward_device(x[None].contiguous())
+            pr = class_map_device(probs, output_height, output_width)[0].cpu().numpy()
+    else:  # foreign model object with a Keras-style predict()
+        x = get_image_array(inp, input_width, input_height, ordering=IMAGE_ORDERING)
+        pr = model.predict(np.array([x]))[0]
+        pr = pr.reshape((output_height, output_width, n_classes)).argmax(axis=2)
+
+    seg_img = visualize_keypoints(
+        pr, inp, n_classes=n_classes,
+        colors=colors, overlay_img=overlay_img,
+        show_legends=show_legends,
+        class_names=class_names,
+        pred_dim=pred_dim,
+    )
+
+    if out_fname is not None:
+        cv2.imwrite(out_fname, seg_img)
+
+    return pr

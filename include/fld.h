@@ -130,6 +130,12 @@ FLD_API int64_t fld_net_tensor_offset(const fld_net* net, int tensor, int B);
  * bf16 in FLD_BF16 mode), may be NULL when only the workspace copy is wanted. */
 FLD_API int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream);
 
+/* Per-layer device timing (bench.py's live roofline measurement): when enabled, fld_net_forward brackets
+ * every layer with CUDA events on the launching stream; fld_net_layer_times waits for the last profiled
+ * forward and writes one duration (ms) per layer, returning the layer count. */
+FLD_API int fld_net_set_profiling(fld_net* net, int enable);
+FLD_API int fld_net_layer_times(fld_net* net, float* ms_h, int n);
+
 /* ------------------------------------------------------------------------------------------
  * Landmark decode
  * ------------------------------------------------------------------------------------------ */

@@ -47,15 +47,18 @@ def average_xy(hmi, n_points=4, thresh=0.0):
         n = n_points
         flat = hmi.reshape(-1)
         ind = np.argsort(flat, kind="stable")[-n_points:]                              # :66
-        i0 = i1 = hsum = 0.0
+        # :68-77 with the reference's scalar dtypes: `hsum` accumulates in the heat-map's dtype
+        # (int 0 + np.float32 -> np.float32), i0/i1 in float64 (np.int64 * np.float32 -> float64)
+        i0, i1, hsum = 0, 0, 0
         for k in ind:                                                                   # :70-74 ascending order
-            h = float(flat[k])
-            r, c = divmod(int(k), W)
+            h = flat[k]
+            r, c = np.int64(int(k) // W), np.int64(int(k) % W)
             hsum += h
             i0 += r * h
             i1 += c * h
         i0 /= hsum
         i1 /= hsum
+        i0, i1, hsum = float(i0), float(i1), float(hsum)
     if hsum / n <= thresh:                                                              # :78-79
         i0, i1 = -1, -1
     return [i1, i0]

@@ -1,0 +1,172 @@
+"""CPU tests of the host side: the C-ABI library builds, loads and exports exactly what include/fld.h
+declares; the drop-in package keeps the reference's names; shape inference of the builders matches the oracle;
+the product fails loudly without a GPU; multi-GPU sharding logic under gloo (world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "face-landmark-detector_b200")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, PKG)
+    import build as fld_build
+    fld_build.build()
+    from keypoints_detector import _native
+    return _native.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from keypoints_detector import _native
+    header = open(os.path.join(ROOT, "include", "fld.h")).read()
+    declared = set(re.findall(r"FLD_API [a-z_0-9\* ]+?(fld_[a-z_0-9]+)\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fld_abi_version() == 1
+    assert lib.fld_launch_count() == 0
+
+
+def test_no_gpu_fails_loudly(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes
+    from keypoints_detector import _native, prediction
+    from keypoints_detector.networks.regression import landmark_regressor
+    h = ctypes.c_void_p()
+    assert lib.fld_create(0, ctypes.byref(h)) == -3           # FLD_ERR_NODEVICE
+    assert b"no CPU fallback" in lib.fld_last_error()
+    m = landmark_regressor().init_weights(0)
+    with pytest.raises(_native.FldError):
+        prediction.detect_marks(np.zeros((480, 640, 3), np.uint8), m, [200, 120, 400, 360])
+    with pytest.raises(_native.FldError):
+        m.predict(np.zeros((1, 128, 128, 3), np.uint8))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+
+
+def test_reference_api_surface():
+    from keypoints_detector import prediction, training
+    from keypoints_detector.data import generator
+    from keypoints_detector.networks import basic_models, config, fcn
+    from keypoints_detector.utils import metrics, plots
+    for name in ("detect_marks", "video_predict", "model_from_checkpoint_path", "keypts_predict", "_prediction", "align_faces",
+                 "detect_marks_batch"):
+        assert callable(getattr(prediction, name))
+    assert set(basic_models.LANDMARKS_MODELS) >= {"fcn_8_resnet50", "fcn_8_mobilenet", "fcn_8_vgg", "default"}
+    assert config.IMAGE_ORDERING == "channels_last"
+    for name in ("get_average_xy", "transfer_xy_coord", "transfer_target"):
+        assert callable(getattr(metrics, name))
+    assert callable(generator.get_image_array) and issubclass(generator.DataLoaderError, Exception)
+    assert callable(training.find_latest_checkpoint) and callable(plots.draw_marks)
+    import inspect
+    sig = inspect.signature(prediction.keypts_predict)
+    assert list(sig.parameters)[:10] == ["model", "inp", "out_fname", "checkpoints_path", "overlay_img", "class_names",
+                                         "show_legends", "colors", "pred_dim", "read_image_type"]
+    sig = inspect.signature(metrics.get_average_xy)
+    assert [(p.name, p.default) for p in sig.parameters.values()][1:] == [("height", 96), ("width", 96), ("n_points", 4),
+                                                                          ("thresh", 0)]
+    assert callable(fcn.vanilla_encoder) and callable(fcn.fcn_8) and callable(fcn.fcn_32)
+
+
+def test_builder_shapes_match_reference_arithmetic():
+    from keypoints_detector.networks.basic_models import LANDMARKS_MODELS
+    from keypoints_detector.networks.fcn import fcn_8, fcn_32, fcn_8_vgg
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = fcn_8(68, input_height=224, input_width=224)
+    assert (m.output_height, m.output_width, m.n_classes) == (232, 232, 68)      # 8*(H/8)+8 (fcn.py:121)
+    assert (m.input_height, m.input_width, m.model_name) == (224, 224, "fcn_8")
+    m = fcn_8(68)                                                                # reference defaults 416x608
+    assert (m.output_height, m.output_width) == (424, 616)
+    m = fcn_32(68, input_height=224, input_width=224)
+    assert (m.output_height, m.output_width) == (256, 256)                       # 32*h5+32 (fcn.py:144)
+    m = fcn_8_vgg(68, input_height=224, input_width=224)
+    assert (m.output_height, m.output_width, m.model_name) == (232, 232, "fcn_8_vgg")
+    assert len([L for L in m.graph.layers if L["name"].startswith("block")]) == 13
+    m = LANDMARKS_MODELS["default"](68)
+    assert m.model_name == "default" and m.n_classes == 68
+    r = landmark_regressor()
+    assert r.graph.shapes[5] == (4, 4, 256) and r.graph.shapes[-1] == (1, 1, 136)
+    specs = r.weight_specs()
+    assert specs["conv1/kernel"] == (3, 3, 3, 64) and specs["fc/kernel"] == (4096, 136) and specs["bn5/gamma"] == (256,)
+    nparams = sum(int(np.prod(s)) for s in specs.values())
+    assert abs(nparams - 2.11e6) < 0.02e6
+
+
+def test_oracle_shapes_agree_with_builders():
+    """The oracle's forward (restated from the reference) yields the shapes the builders infer."""
+    import torch as th
+    from oracle import cnn
+    from keypoints_detector.networks.fcn import fcn_8
+    rng = np.random.default_rng(0)
+    from test_oracle_pinning import _small_weights
+    w = _small_weights(rng)
+    probs = cnn.fcn_forward(rng.normal(0, 1, (1, 64, 96, 3)), w, "fcn_8", th.float64)
+    m = fcn_8(5, input_height=64, input_width=96)
+    assert probs.shape == (1, m.output_height * m.output_width, 5)
+
+
+def test_checkpoint_sidecar_roundtrip(tmp_path):
+    from keypoints_detector import training
+    from keypoints_detector.networks.regression import landmark_regressor
+    ck = str(tmp_path / "ck")
+    assert training.find_latest_checkpoint(ck) is None
+    with pytest.raises(ValueError):
+        training.find_latest_checkpoint(ck, fail_safe=False)
+    m = landmark_regressor().init_weights(3)
+    m.save_weights(ck + ".00002")
+    m.save_weights(ck + ".00010")
+    open(ck + ".notanumber", "w").close()
+    assert training.find_latest_checkpoint(ck) == ck + ".00010"
+    m2 = landmark_regressor()
+    m2.load_weights(training.find_latest_checkpoint(ck))
+    assert all(np.array_equal(m.weights[k], m2.weights[k]) for k in m.weights)
+    with pytest.raises(ValueError):
+        m2.set_weights({**m.weights, "fc/bias": np.zeros(3, np.float32)})
+
+
+def test_shard_faces():
+    from keypoints_detector.prediction import shard_faces
+    assert shard_faces(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard_faces(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    for n in (0, 1, 255, 256, 65536):
+        for g in (1, 2, 4, 8):
+            sh = shard_faces(n, g)
+            assert sh[0][0] == 0 and sh[-1][1] == n and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+
+
+def test_bench_sharding_under_gloo_world2():
+    """bench.py's multi-rank plumbing (rank shard + max-over-ranks timing reduction) on CPU with gloo."""
+    code = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bench
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+lo, hi = bench.rank_shard(1000, r, w)
+t = bench.max_over_ranks(float(r + 1), "cpu")
+tot = bench.sum_over_ranks(float(hi - lo), "cpu")
+assert t == float(w) and tot == 1000.0, (t, tot)
+print("OK", r, lo, hi)
+dist.destroy_process_group()
+""" % (ROOT, PKG)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", "--no-python", sys.executable, "-c", code],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 2
