@@ -5,6 +5,7 @@
 // Replaces model.signatures["predict"] (reference prediction.py:84) and model.predict (prediction.py:208)
 // for graphs expressed in the vocabulary of networks/fcn.py / networks/utils.py.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "ops.cuh"
@@ -116,7 +117,8 @@ int infer_shapes(fld_net* net) {
     for (int i = 0; i < nL; ++i) {
       const fld_layer_desc& d = net->layers[i].d;
       if (d.op == FLD_OP_ADD) { f32_needed[d.in0] = 1; f32_needed[d.in1] = 1; }
-      if (d.op == FLD_OP_SOFTMAX || d.op == FLD_OP_MAXPOOL) f32_needed[d.in0] = 1;
+      // logits feeding transposed convs / softmax stay fp32 (they are tiny; bf16 there only costs accuracy)
+      if (d.op == FLD_OP_SOFTMAX || d.op == FLD_OP_MAXPOOL || d.op == FLD_OP_DECONV) f32_needed[d.in0] = 1;
     }
     for (int i = 0; i < nL; ++i) {
       LayerRt& L = net->layers[i];
@@ -285,6 +287,14 @@ extern "C" int fld_net_finalize(fld_net* net) {
   return FLD_OK;
 }
 
+static size_t dense_scratch_bytes(const fld_net* net, int B) {
+  size_t m = 0;
+  for (size_t i = 0; i < net->layers.size(); ++i)
+    if (net->layers[i].d.op == FLD_OP_DENSE)
+      m = std::max(m, simt_dense_scratch_bytes(B, (int)net->tensors[net->layers[i].d.in0].elems(), net->layers[i].d.cout));
+  return m;
+}
+
 extern "C" int fld_net_tensor_shape(const fld_net* net, int tensor, int32_t* hwc) {
   if (!net || !hwc || tensor < 0 || tensor >= (int)net->tensors.size()) { fld_set_error("fld_net_tensor_shape: bad argument"); return FLD_ERR_INVALID; }
   const TensorInfo& t = net->tensors[tensor];
@@ -303,7 +313,7 @@ extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
   if (!net || B < 0) return 0;
   size_t off = 0;
   for (size_t t = 1; t < net->tensors.size(); ++t) off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
-  return off + 1024;
+  return off + align_up(dense_scratch_bytes(net, B), 1024) + 1024;
 }
 
 extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {
@@ -322,13 +332,16 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
   const int nT = (int)net->tensors.size();
   std::vector<void*> ptr(nT);
   ptr[0] = const_cast<void*>(in);
+  float* dense_scratch = nullptr;
   {
     size_t off = 0;
     for (int t = 1; t < nT; ++t) {
       ptr[t] = (char*)workspace + off;
       off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
     }
+    dense_scratch = (float*)((char*)workspace + off);
   }
+  static const bool debug_sync = getenv("FLD_DEBUG_SYNC") != nullptr;
   if (net->profiling) FLD_CUDA(cudaEventRecord(net->events[0], st));
   for (size_t i = 0; i < net->layers.size(); ++i) {
     LayerRt& L = net->layers[i];
@@ -365,7 +378,8 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
         break;
       }
       case FLD_OP_DENSE:
-        rc = simt_dense(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, (float*)pout, B, (int)a.elems(), o.c, d.act, st);
+        rc = simt_dense(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, (float*)pout, dense_scratch, B, (int)a.elems(), o.c, d.act,
+                        st);
         break;
       case FLD_OP_SOFTMAX:
         FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: SOFTMAX input must be fp32", i);
@@ -380,6 +394,14 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
         rc = FLD_ERR_INVALID;
     }
     if (rc) return rc;
+    if (debug_sync) {  // FLD_DEBUG_SYNC=1: localise an asynchronous fault to its layer
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        fld_set_error("layer %zu (op %d, path %d, in %dx%dx%d -> out %dx%dx%d, B=%d) failed: %s", i, d.op, L.path, a.h, a.w, a.c, o.h,
+                      o.w, o.c, B, cudaGetErrorString(e));
+        return FLD_ERR_CUDA;
+      }
+    }
     if (net->profiling) FLD_CUDA(cudaEventRecord(net->events[i + 1], st));
   }
   if (net->profiling) net->profiled_once = true;

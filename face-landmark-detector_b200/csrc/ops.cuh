@@ -19,8 +19,9 @@ int simt_deconv(const void* in, int in_dtype, const float* w /*[k][k][Cin][Cout]
 int simt_add_crop(const float* a, int AH, int AW, const float* b, int BH, int BW, float* out, int B, int OH, int OW, int C,
                   cudaStream_t st);
 int simt_softmax(const float* in, float* out, long long n_px, int C, cudaStream_t st);
-int simt_dense(const void* in, int in_dtype, const float* w /*[In][Out]*/, const float* bias, float* out, int B, int In, int Out,
-               int act, cudaStream_t st);
+size_t simt_dense_scratch_bytes(int B, int In, int Out);
+int simt_dense(const void* in, int in_dtype, const float* w /*[In][Out]*/, const float* bias, float* out, float* scratch /*split-K partials*/,
+               int B, int In, int Out, int act, cudaStream_t st);
 int simt_maxpool(const float* in, float* out, int B, int IH, int IW, int C, int OH, int OW, int k, int s, cudaStream_t st);
 int simt_cvt_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
 

@@ -201,28 +201,41 @@ __global__ void softmax_kernel(const float* __restrict__ in, float* __restrict__
   for (int c = lane; c < C; c += 32) q[c] = expf(p[c] - mx) / sum;
 }
 
-// Flatten + Dense: out[b][j] = sum_k in[b][k] * W[k][j] + bias[j].  One CTA = 8 items x 128 outputs.
-constexpr int DF = 8, DK = 128;
+// Flatten + Dense, split-K: out[b][j] = sum_k in[b][k] * W[k][j] + bias[j].
+// pass 1: one CTA = 8 items x 128 outputs x one K slice -> partial sums; pass 2: fixed-order reduction over the
+// slices + bias + activation (deterministic; no atomics).  K = 4096 in one serial loop was latency-bound.
+constexpr int DF = 8, DK = 128, DSLICE = 256;
 template <typename TIn>
 __global__ void __launch_bounds__(128)
-dense_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                  int B, int In, int Out, int act) {
+dense_partial_kernel(const TIn* __restrict__ in, const float* __restrict__ w, float* __restrict__ part, int B, int In, int Out) {
   __shared__ float xs[DF][DK];
   const int b0 = blockIdx.x * DF;
   const int j = blockIdx.y * 128 + threadIdx.x;
+  const int kbeg = blockIdx.z * DSLICE, kend = min(In, kbeg + DSLICE);
   float acc[DF];
 #pragma unroll
   for (int f = 0; f < DF; ++f) acc[f] = 0.f;
-  for (int k0 = 0; k0 < In; k0 += DK) {
+  for (int k0 = kbeg; k0 < kend; k0 += DK) {
     for (int e = threadIdx.x; e < DF * DK; e += 128) {
       const int f = e / DK, k = e - f * DK;
-      xs[f][k] = (b0 + f < B && k0 + k < In) ? ld_f<TIn>(in + (size_t)(b0 + f) * In + k0 + k) : 0.f;
+      xs[f][k] = (b0 + f < B && k0 + k < kend) ? ld_f<TIn>(in + (size_t)(b0 + f) * In + k0 + k) : 0.f;
     }
     __syncthreads();
     if (j < Out) {
-      const int kmax = min(DK, In - k0);
-      for (int k = 0; k < kmax; ++k) {
-        const float wv = __ldg(w + (size_t)(k0 + k) * Out + j);
+      const int kmax = min(DK, kend - k0);
+      const float* wp = w + (size_t)k0 * Out + j;
+      int k = 0;
+      for (; k + 8 <= kmax; k += 8) {
+        float wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(wp + (size_t)(k + u) * Out);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int f = 0; f < DF; ++f) acc[f] = fmaf(xs[f][k + u], wv[u], acc[f]);
+      }
+      for (; k < kmax; ++k) {
+        const float wv = __ldg(wp + (size_t)k * Out);
 #pragma unroll
         for (int f = 0; f < DF; ++f) acc[f] = fmaf(xs[f][k], wv, acc[f]);
       }
@@ -230,11 +243,19 @@ dense_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const
     __syncthreads();
   }
   if (j < Out) {
-    const float bv = bias ? bias[j] : 0.f;
 #pragma unroll
     for (int f = 0; f < DF; ++f)
-      if (b0 + f < B) out[(size_t)(b0 + f) * Out + j] = apply_act(acc[f] + bv, act);
+      if (b0 + f < B) part[((size_t)blockIdx.z * B + b0 + f) * Out + j] = acc[f];
   }
+}
+
+__global__ void dense_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ out, int B,
+                                    int Out, int KS, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Out) return;
+  float s = 0.f;
+  for (int z = 0; z < KS; ++z) s += part[(size_t)z * B * Out + i];
+  out[i] = apply_act(s + (bias ? bias[i % Out] : 0.f), act);
 }
 
 __global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int IH, int IW, int C, int OH, int OW,
@@ -326,14 +347,18 @@ int simt_softmax(const float* in, float* out, long long n_px, int C, cudaStream_
   return FLD_OK;
 }
 
-int simt_dense(const void* in, int in_dtype, const float* w, const float* bias, float* out, int B, int In, int Out, int act,
-               cudaStream_t st) {
+size_t simt_dense_scratch_bytes(int B, int In, int Out) { return (size_t)fld_div_up(In, DSLICE) * B * Out * sizeof(float); }
+
+int simt_dense(const void* in, int in_dtype, const float* w, const float* bias, float* out, float* scratch, int B, int In, int Out,
+               int act, cudaStream_t st) {
   if (B == 0) return FLD_OK;
-  dim3 grid(fld_div_up(B, DF), fld_div_up(Out, 128));
-  if (in_dtype == FLD_F32) dense_simt_kernel<float><<<grid, 128, 0, st>>>((const float*)in, w, bias, out, B, In, Out, act);
-  else if (in_dtype == FLD_BF16)
-    dense_simt_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, bias, out, B, In, Out, act);
+  const int KS = fld_div_up(In, DSLICE);
+  dim3 grid(fld_div_up(B, DF), fld_div_up(Out, 128), KS);
+  if (in_dtype == FLD_F32) dense_partial_kernel<float><<<grid, 128, 0, st>>>((const float*)in, w, scratch, B, In, Out);
+  else if (in_dtype == FLD_BF16) dense_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, scratch, B, In, Out);
   else { fld_set_error("simt_dense: unsupported input dtype"); return FLD_ERR_INVALID; }
+  FLD_LAUNCHED();
+  dense_reduce_kernel<<<fld_div_up(B * Out, 256), 256, 0, st>>>(scratch, bias, out, B, Out, KS, act);
   FLD_LAUNCHED();
   return FLD_OK;
 }

@@ -144,6 +144,7 @@ struct EpiOut {
   void* ptr;       // pointer to channel (n0 + chunk*32) of this thread's output pixel (pooled pixel when pooling)
   bool valid;      // pixel inside the output
   int c_left;      // channels left from the chunk start (Cout - n0 - chunk*32), may be <= 0
+  bool vec_ok;     // pixel pitch keeps 16-byte vector stores aligned (Cout % 8 == 0 for bf16, % 4 for f32)
 };
 
 template <bool POOL, bool OUT_F32>
@@ -182,7 +183,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float*
   } else if (!OUT_F32) {
     if (!o.valid) return;
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.ptr);
-    if (o.c_left >= 32) {
+    if (o.c_left >= 32 && o.vec_ok) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
@@ -197,7 +198,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float*
   } else {
     if (!o.valid) return;
     float* p = reinterpret_cast<float*>(o.ptr);
-    if (o.c_left >= 32) {
+    if (o.c_left >= 32 && o.vec_ok) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else {
@@ -315,6 +316,7 @@ conv_first_kernel(const FirstParams p) {
     // ---- epilogue: thread = TMEM lane = tile pixel tid
     const int ly = tid >> 3, lx = tid & 7;
     EpiOut eo;
+    eo.vec_ok = true;  // Cout % 16 == 0 here
     if (p.pool) {
       const int py = (y0 + ly) >> 1, px = (x0 + lx) >> 1;
       eo.valid = (py < PH) && (px < PW);
@@ -450,6 +452,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int tb = m / p.tiles_y;
       const int ox = tx * p.TW + lx, oy = ty * p.TH + ly, b = tb * p.NB + nb, n0 = nt * p.BN;
       EpiOut eo;
+      eo.vec_ok = OUT_F32 ? (p.Cout % 4 == 0) : (p.Cout % 8 == 0);
       size_t pix;
       if (p.pool) {
         eo.valid = (b < p.B) && ((oy >> 1) < PH) && ((ox >> 1) < PW);
