@@ -260,16 +260,9 @@ extern "C" int fld_net_finalize(fld_net* net) {
       FLD_CUDA(cudaMalloc(&L.d_w, L.w_host.size() * sizeof(float)));
       FLD_CUDA(cudaMemcpy(L.d_w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
-      // [kg 4][ng Cout/8][r 8][e 8]  <-  w[k = kg*8+e][cout = ng*8+r], K = 27 padded to 32
-      std::vector<uint16_t> pk((size_t)Cout * 32, 0);
-      for (int kg = 0; kg < 4; ++kg)
-        for (int ng = 0; ng < Cout / 8; ++ng)
-          for (int r = 0; r < 8; ++r)
-            for (int e = 0; e < 8; ++e) {
-              const int k = kg * 8 + e, o = ng * 8 + r;
-              const float v = k < 27 ? L.w_host[(size_t)k * Cout + o] : 0.f;
-              pk[(((size_t)kg * (Cout / 8) + ng) * 8 + r) * 8 + e] = f2bf(v);
-            }
+      // core-matrix packed [6 kgroups][Cout/8][8][8], k' = kh*12 + kw*4 + c (see tc_conv_first.cu)
+      std::vector<uint16_t> pk((size_t)Cout * 48, 0);
+      tc_conv_first_pack(L.w_host.data(), Cout, f2bf, pk.data());
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else {
