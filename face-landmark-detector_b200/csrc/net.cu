@@ -22,6 +22,7 @@ struct TensorInfo {
 enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 
 struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
+struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
 
 struct LayerRt {
   fld_layer_desc d;
@@ -35,6 +36,7 @@ struct LayerRt {
   float* d_bias = nullptr;
   __nv_bfloat16* d_wbf = nullptr;
   std::vector<PlanEntry> plans;
+  std::vector<HaloPlanEntry> hplans;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -142,6 +144,8 @@ void free_layer(LayerRt& L) {
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_wbf) cudaFree(L.d_wbf);
   for (auto& pe : L.plans) tc_conv_plan_destroy(pe.plan);
+  for (auto& pe : L.hplans) tc_halo_plan_destroy(pe.plan);
+  L.hplans.clear();
   L.d_w = nullptr; L.d_bias = nullptr; L.d_wbf = nullptr; L.plans.clear();
 }
 
@@ -347,6 +351,16 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
       case FLD_OP_CONV:
         if (L.path == PATH_TC_FIRST) {
           rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st);
+        } else if (L.path == PATH_TC_TMA && o.dtype == FLD_BF16 && tc_halo_supported(L.g, L.cout_pad)) {
+          TcHaloPlan* plan = nullptr;
+          for (auto& pe : L.hplans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }
+          if (!plan) {
+            rc = tc_halo_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan);
+            if (rc) return rc;
+            if (L.hplans.size() >= 8) { tc_halo_plan_destroy(L.hplans.front().plan); L.hplans.erase(L.hplans.begin()); }
+            L.hplans.push_back({B, pin, plan});
+          }
+          rc = tc_halo_run(plan, L.d_bias, pout, st);
         } else if (L.path == PATH_TC_TMA) {
           TcConvPlan* plan = nullptr;
           for (auto& pe : L.plans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }

@@ -38,3 +38,11 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
                         TcConvPlan** out);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype, cudaStream_t st);
+
+// 3x3 halo-reuse / stationary-weight variant (tc_conv_halo.cu); bf16 in, bf16 out
+struct TcHaloPlan;
+bool tc_halo_supported(const ConvGeom& g, int cout_pad);
+int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
+                        TcHaloPlan** out);
+void tc_halo_plan_destroy(TcHaloPlan* p);
+int tc_halo_run(const TcHaloPlan* p, const float* bias, void* out, cudaStream_t st);

@@ -112,6 +112,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t min_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// one lane of the (converged) warp; lets the compiler keep the enclosing loop on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
@@ -133,11 +143,26 @@ struct EpiOut {
 template <bool POOL, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float* __restrict__ bias, int act, int lane, int TW,
                                                const EpiOut& o) {
+  // bias: 8 x 16-byte loads (the pointer is 64-byte aligned: n0 and the chunk offset are multiples of 16 floats)
   float v[32];
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = act_f(__uint_as_float(acc[j]) + bias[j], act);
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(b4 + q);
+      v[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) + b.x;
+      v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b.y;
+      v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b.z;
+      v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b.w;
+    }
+  }
+  if (!POOL) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], act);
+  }
   if (POOL) {
-    // bf16 output only.  round first (monotone, so max commutes), then max on packed pairs
+    // bf16 output only.  Round first, then max on packed pairs, then the activation on the 4 pooled words: rounding,
+    // ReLU / ReLU6 and max are all monotone, so act(max(round(x))) == round(max(act(x))) — 4 ops instead of 32.
     uint32_t w[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
@@ -157,6 +182,13 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float*
       const uint32_t send = by ? k1[i] : k1[i + 4];
       const uint32_t keep = by ? k1[i + 4] : k1[i];
       k2[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, TW));
+    }
+    if (act != FLD_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        k2[i] = max_bf16x2(k2[i], 0u);
+        if (act == FLD_ACT_RELU6) k2[i] = min_bf16x2(k2[i], 0x40c040c0u);  // bf16(6.0) = 0x40c0
+      }
     }
     const int cb = (bx ? 8 : 0) + (by ? 16 : 0);
     if (o.valid && cb + 8 <= o.c_left) {

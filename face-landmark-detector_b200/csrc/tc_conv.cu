@@ -1,35 +1,36 @@
-// tc_conv.cu — tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (FLD_BF16 mode).
+// tc_conv.cu — generic tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (FLD_BF16 mode).
 //
-// Replaces the TensorFlow conv arithmetic behind reference networks/fcn.py:25-49 (ZeroPad -> Conv3x3 ->
-// BN -> ReLU -> MaxPool2 stages), fcn.py:98-103,108,117 (7x7 / 1x1 head and score convs).  BN is folded
-// into weights/bias on the host (net.cu); bias + ReLU + 2x2 max-pool are fused into the epilogue so a
-// stage's pre-pool map never touches HBM.
+// Replaces the TensorFlow conv arithmetic behind reference networks/fcn.py:33-49 (ZeroPad -> Conv3x3 -> BN -> ReLU
+// -> MaxPool2 stages 2..5), fcn.py:98-103,108,117 (7x7 / 1x1 head and score convs) and networks/vgg16.py:27-73.
+// BN is folded into weights/bias on the host (net.cu); bias + ReLU + 2x2 max-pool are fused into the epilogue so
+// a stage's pre-pool map never touches HBM.
 //
-// GEMM view: D[M = output pixels][N = Cout] = A[M][K = taps*Cin] * B[N][K]^T, bf16 operands, fp32
-// accumulation in TMEM.  An M tile is a TW x TH x NB pixel patch (128 pixels) so that
-//   (1) one 4-D TMA box per (tap, 64-channel chunk) fetches the shifted input patch, with TMA's
-//       out-of-bounds zero fill supplying the convolution's zero padding, and
-//   (2) the four pixels of every 2x2 pool window sit in one warp's 32 TMEM lanes (lane^1, lane^TW):
-//       pooling is two rounds of warp shuffles on packed bf16x2.
+// GEMM view: D[M = output pixels][N = Cout] = A[M][K = taps*Cin] * B[N][K]^T, bf16 operands, fp32 accumulation
+// in TMEM.  An M tile is a TW x TH x NB pixel patch (128 pixels) so that
+//   (1) one 4-D TMA box per (tap, 64-channel chunk) fetches the shifted input patch, with TMA's out-of-bounds
+//       zero fill supplying the convolution's zero padding, and
+//   (2) the four pixels of every 2x2 pool window sit in one warp's 32 TMEM lanes (lane^1, lane^TW): pooling is
+//       two rounds of warp shuffles on packed bf16x2 (tc_common.cuh).
 //
-// Two kernels:
-//   conv_first_kernel  3x3xCin=3 first layer straight from the u8 / f32 image: the CTA builds the
-//                      im2col tile (K = 27 -> 32) in shared memory itself (no padded copy of the input),
-//                      2 MMAs of 128xCoutx16 per tile.
-//   conv_tma_kernel    generic kh x kw, Cin % 64 == 0, stride 1: warp-specialised (TMA producer / MMA
-//                      issuer / 4 epilogue warps), multi-stage mbarrier ring, double-buffered TMEM
-//                      accumulators, persistent over tiles.
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer        multi-stage mbarrier ring (A box + B box per k-block of 64 channels)
+//   warp 1      MMA issuer          4 x tcgen05.mma (128 x BN x 16) per k-block, tcgen05.commit frees the stage
+//   warps 2..9  epilogue            two warps per TMEM lane quadrant, alternating 32-column chunks; double-buffered
+//                                   accumulators (2 x 256 TMEM columns) overlap tile i's epilogue with tile i+1's MMAs
+// The role loops are WARP-UNIFORM: all 32 lanes walk the loop and wait on the barriers, one elected lane issues
+// the TMA / MMA / commit.  Measured with the clock64 trace below (FLD_TC_TRACE): the first version ran the loops
+// inside `if (lane == 0)`, which made nvcc wrap every UTMALDG / UTCHMMA / UTCBAR in R2UR + ELECT waterfall loops —
+// ~730 cycles per k-block in BOTH roles, i.e. 70 % tensor-active at N = 256 and 31 % at N = 128.
 
+#include <stdlib.h>
+#include <vector>
 #include "tc_common.cuh"
 
 namespace {
 using namespace tc;
 
-// ================================================================================================
-// Generic conv: warp-specialised TMA -> tcgen05.mma -> epilogue, persistent over tiles.
-// ================================================================================================
 struct TmaConvParams {
-  const float* bias;   // [Cout_pad]
+  const float* bias;   // [Cout_pad + 32]
   void* out;
   int B, OH, OW, Cout; // conv output (pre-pool) dims
   int Cin, kh, kw, pad_t, pad_l;
@@ -38,10 +39,20 @@ struct TmaConvParams {
   int tiles_x, tiles_y, tiles_b, total_tiles;
   int stages;
   int act, pool;
+  unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
+  int dbg;             // FLD_TC_DBG bisect switches (results are garbage when set): 1 skip epilogue math/stores,
+                       // 2 skip TMEM loads too, 4 skip the A-operand TMA, 8 skip the B-operand TMA, 16 skip the MMAs
 };
 
-constexpr int kTmaThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kTmaThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kMaxStages = 8;
+constexpr int kTraceN = 2048;
+#define TRACE(role, idx, tag)                                                                                         \
+  do {                                                                                                                \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (idx) < kTraceN)                                                   \
+      p.trace[(role) * kTraceN + (idx)++] = ((unsigned long long)clock64() << 4) | (tag);                             \
+  } while (0)
 
 template <bool OUT_F32>
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -54,10 +65,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;  // BN multiple of 16 -> b_bytes multiple of 2048 -> 1024-aligned stages
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiWarps); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -70,76 +83,106 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int kchunks = p.Cin >> 6;
   const int kblocks = p.kh * p.kw * kchunks;
+  const int mtiles = p.tiles_x * p.tiles_y * p.tiles_b;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_ntiles;
-        int m = tile / p.n_ntiles;
-        const int tx = m % p.tiles_x; m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int tb = m / p.tiles_y;
-        const int x0 = tx * p.TW - p.pad_l, y0 = ty * p.TH - p.pad_t, b0 = tb * p.NB, n0 = nt * p.BN;
-        for (int tap = 0; tap < p.kh * p.kw; ++tap) {
-          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    uint32_t stage = 0, phase = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile / mtiles;             // N tile is the slow index: concurrent CTAs share the weight tile
+      int m = tile - nt * mtiles;
+      const int tb = m / (p.tiles_x * p.tiles_y);
+      m -= tb * (p.tiles_x * p.tiles_y);
+      const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
+      const int x0 = tx * p.TW - p.pad_l, y0 = ty * p.TH - p.pad_t, b0 = tb * p.NB, n0 = nt * p.BN;
+      int wrow = n0;                            // row of the [taps*cout_pad][Cin] weight matrix
+      for (int ky = 0; ky < p.kh; ++ky) {
+        for (int kx = 0; kx < p.kw; ++kx, wrow += p.cout_pad) {
           for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_arrive_expect_tx(fb, stage_bytes);
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            tma_load_4d(sa, &tmA, fb, kc * 64, x0 + kx, y0 + ky, b0);
-            tma_load_2d(sa + a_bytes, &tmB, fb, kc * 64, tap * p.cout_pad + n0);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            TRACE(0, ti, 1);
+            if (elect_one()) {
+              const uint32_t fb = full0 + 8 * stage;
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              const uint32_t bytes = ((p.dbg & 4) ? 0u : a_bytes) + ((p.dbg & 8) ? 0u : b_bytes);
+              TRACE(0, ti, 5);
+              mbar_arrive_expect_tx(fb, bytes);
+              TRACE(0, ti, 6);
+              if (!(p.dbg & 4)) tma_load_4d(sa, &tmA, fb, kc * 64, x0 + kx, y0 + ky, b0);
+              TRACE(0, ti, 7);
+              if (!(p.dbg & 8)) tma_load_2d(sa + a_bytes, &tmB, fb, kc * 64, wrow);
+              TRACE(0, ti, 8);
+            }
+            __syncwarp();
+            TRACE(0, ti, 2);
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // The issue loop is one thread: keep it to a barrier wait + 4 MMAs + a commit per k-block.  Descriptors are
-      // built once; per stage / per 16-element K step only the 14-bit start-address field moves (units of 16 B).
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
-      const uint64_t adesc0 = umma_desc(smem_base, 16, 1024, 2);
-      const uint64_t bdesc0 = umma_desc(smem_base + a_bytes, 16, 1024, 2);
-      const uint32_t stage_step = stage_bytes >> 4;
-      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    // Descriptors are built once; per stage / per 16-element K step only the 14-bit start-address field moves
+    // (units of 16 bytes).
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+    const uint64_t adesc0 = umma_desc(smem_base, 16, 1024, 2);
+    const uint64_t bdesc0 = umma_desc(smem_base + a_bytes, 16, 1024, 2);
+    const uint32_t stage_step = stage_bytes >> 4;
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      TRACE(1, ti, 0);
+      mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+      TRACE(1, ti, 3);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 256;
+      uint32_t accum = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        TRACE(1, ti, 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * 256;
-        uint32_t accum = 0;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full0 + stage * 8, phase);
-          tc_fence_after();
+        TRACE(1, ti, 5);
+        if (elect_one()) {
+          TRACE(1, ti, 6);
           const uint64_t ad = adesc0 + (uint64_t)(stage * stage_step);
           const uint64_t bd = bdesc0 + (uint64_t)(stage * stage_step);
-          umma_bf16(d, ad, bd, idesc, accum);
-          umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-          umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-          umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-          accum = 1u;
-          umma_commit(empty0 + stage * 8);
-          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          if (!(p.dbg & 16)) {
+            umma_bf16(d, ad, bd, idesc, accum);
+            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+          }
+          TRACE(1, ti, 7);
+          umma_commit(empty0 + 8 * stage);                       // stage reusable once these MMAs have read it
+          if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+          TRACE(1, ti, 8);
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        accum = 1u;
+        TRACE(1, ti, 2);
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    const int sub = warp & 3;            // TMEM sub-partition this warp may access
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int ew = warp - 2;
+    const int sub = warp & 3;            // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
+    const int half = ew >> 2;            // the quadrant's two warps take alternating 32-column chunks
     const int r = sub * 32 + lane;       // tile row = pixel index inside the M tile
     const int lx = r % p.TW, ly = (r / p.TW) % p.TH, nb = r / (p.TW * p.TH);
     const int PH = p.OH >> 1, PW = p.OW >> 1;
     uint32_t acc = 0, acc_phase = 0;
+    int ti = 0;
+    const bool tr = (warp == 2);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_ntiles;
-      int m = tile / p.n_ntiles;
-      const int tx = m % p.tiles_x; m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int tb = m / p.tiles_y;
+      const int nt = tile / mtiles;
+      int m = tile - nt * mtiles;
+      const int tb = m / (p.tiles_x * p.tiles_y);
+      m -= tb * (p.tiles_x * p.tiles_y);
+      const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
       const int ox = tx * p.TW + lx, oy = ty * p.TH + ly, b = tb * p.NB + nb, n0 = nt * p.BN;
       EpiOut eo;
       eo.vec_ok = OUT_F32 ? (p.Cout % 4 == 0) : (p.Cout % 8 == 0);
@@ -151,12 +194,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         eo.valid = (b < p.B) && (oy < p.OH) && (ox < p.OW);
         pix = ((size_t)b * p.OH + oy) * p.OW + ox;
       }
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      if (tr) TRACE(2, ti, 1);
       tc_fence_after();
-      for (int ch = 0; ch < p.BN; ch += 32) {
+      for (int ch = half * 32; ch < p.BN; ch += 64) {
+        if (p.dbg & 2) break;
         uint32_t regs[32];
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 256 + ch, regs);
         tmem_ld_wait();
+        if (p.dbg & 1) { if ((regs[0] ^ regs[31]) == 0x7fc12345u) eo.valid = false; continue; }
         EpiOut e2 = eo;
         e2.c_left = p.Cout - n0 - ch;
         if (OUT_F32) e2.ptr = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0 + ch;
@@ -166,7 +212,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (tr) TRACE(2, ti, 2);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -207,19 +254,16 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.B = B; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout;
   p.Cin = g.Cin; p.kh = g.kh; p.kw = g.kw; p.pad_t = g.pad_t; p.pad_l = g.pad_l;
   p.act = g.act; p.pool = g.pool;
-  // M-tile geometry: TW*TH*NB = 128, TW in {4, 8, 16}; prefer 8x16 (pool partner lane^8)
-  int TW, TH, NB;
-  if (g.OW >= 16 && g.OW % 16 == 0 && g.OW % 8 != 0) { TW = 16; }
-  else if (g.OW > 4) TW = 8;
-  else TW = 4;
-  const int rows_left = 128 / TW;
-  TH = 1;
-  while (TH * 2 <= rows_left && TH < g.OH) TH *= 2;
-  if (TH < 2) TH = 2;
-  NB = 128 / (TW * TH);
+  { const char* e = getenv("FLD_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.trace = nullptr;
+  // M-tile geometry: TW*TH*NB = 128 pixels, TW in {4, 8}: the pool partners are lane^1 and lane^TW
+  const int TW = g.OW > 4 ? 8 : 4;
+  int TH = 2;
+  while (TH * 2 <= 128 / TW && TH < g.OH) TH *= 2;
+  const int NB = 128 / (TW * TH);
   p.TW = TW; p.TH = TH; p.NB = NB;
   // N tile
-  int BN = cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128);
+  const int BN = cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128);
   if (cout_pad % BN != 0 || BN % 16 != 0) { delete pl; fld_set_error("tc_conv: bad cout_pad %d", cout_pad); return FLD_ERR_INVALID; }
   p.BN = BN; p.cout_pad = cout_pad; p.n_ntiles = cout_pad / BN;
   p.tiles_x = fld_div_up(g.OW, TW); p.tiles_y = fld_div_up(g.OH, TH); p.tiles_b = fld_div_up(B, NB);
@@ -263,6 +307,12 @@ int tc_conv_run(const TcConvPlan* pl, const float* bias, void* out, int out_dtyp
   if (pl->p.total_tiles == 0) return FLD_OK;
   TmaConvParams p = pl->p;
   p.bias = bias; p.out = out;
+  if (getenv("FLD_TC_TRACE")) {
+    static unsigned long long* tbuf = nullptr;
+    if (!tbuf) FLD_CUDA(cudaMalloc(&tbuf, 3 * kTraceN * 8));
+    FLD_CUDA(cudaMemsetAsync(tbuf, 0, 3 * kTraceN * 8, st));
+    p.trace = tbuf;
+  }
   if (p.pool && out_dtype != FLD_BF16) { fld_set_error("tc_conv: fused pool needs bf16 output"); return FLD_ERR_INVALID; }
   if (out_dtype == FLD_F32) {
     FLD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -272,5 +322,19 @@ int tc_conv_run(const TcConvPlan* pl, const float* bias, void* out, int out_dtyp
     conv_tma_kernel<false><<<pl->grid, kTmaThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
   }
   FLD_LAUNCHED();
+  if (p.trace) {  // dump CTA 0's event log: "<role> <tag> <clock>" per line
+    static int n_dump = 0;
+    std::vector<unsigned long long> hbuf(3 * kTraceN);
+    FLD_CUDA(cudaStreamSynchronize(st));
+    FLD_CUDA(cudaMemcpy(hbuf.data(), p.trace, hbuf.size() * 8, cudaMemcpyDeviceToHost));
+    char name[256];
+    snprintf(name, sizeof(name), "%s/trace_%02d_cin%d_cout%d_oh%d.txt", getenv("FLD_TC_TRACE"), n_dump++, p.Cin, p.Cout, p.OH);
+    if (FILE* f = fopen(name, "w")) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < kTraceN && hbuf[r * kTraceN + i]; ++i)
+          fprintf(f, "%d %llu %llu\n", r, hbuf[r * kTraceN + i] & 15, hbuf[r * kTraceN + i] >> 4);
+      fclose(f);
+    }
+  }
   return FLD_OK;
 }
