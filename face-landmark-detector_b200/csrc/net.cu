@@ -266,7 +266,7 @@ extern "C" int fld_net_finalize(fld_net* net) {
     } else if (L.path == PATH_TC_FIRST) {
       // core-matrix packed [6 kgroups][Cout/8][8][8], k' = kh*12 + kw*4 + c (see tc_conv_first.cu)
       std::vector<uint16_t> pk((size_t)Cout * 48, 0);
-      tc_conv_first_pack(L.w_host.data(), Cout, f2bf, pk.data());
+      tc_conv_first_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data());
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else {

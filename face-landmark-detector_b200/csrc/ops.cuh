@@ -31,7 +31,8 @@ struct TcConvPlan;  // opaque: tensor maps + launch geometry for one (layer, bat
 int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_bfloat16* w_packed /*[Cout][32]*/,
                   const float* bias, __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st);
 bool tc_conv_first_supported(const ConvGeom& g);
-void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, int Cout, uint16_t (*f2bf)(float), uint16_t* out /*[Cout*48]*/);
+void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_host /*[Cout] or null*/, int Cout,
+                        uint16_t (*f2bf)(float), uint16_t* out /*[Cout*48]*/);
 // generic: stride 1, Cin % 64 == 0, bf16 NHWC in; weights bf16 [kh*kw][Cout_pad][Cin]; out bf16 or f32 NHWC
 bool tc_conv_supported(const ConvGeom& g);
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,

@@ -140,12 +140,12 @@ struct EpiOut {
   bool vec_ok;     // pixel pitch keeps 16-byte vector stores aligned (Cout % 8 == 0 for bf16, % 4 for f32)
 };
 
-template <bool POOL, bool OUT_F32>
+template <bool POOL, bool OUT_F32, bool BIAS = true>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float* __restrict__ bias, int act, int lane, int TW,
                                                const EpiOut& o) {
   // bias: 8 x 16-byte loads (the pointer is 64-byte aligned: n0 and the chunk offset are multiples of 16 floats)
   float v[32];
-  {
+  if (BIAS) {
     const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -155,6 +155,9 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float*
       v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b.z;
       v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b.w;
     }
+  } else {  // bias already accumulated by the tensor core (first layer: spare K slots)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   }
   if (!POOL) {
 #pragma unroll

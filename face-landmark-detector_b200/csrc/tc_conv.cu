@@ -17,8 +17,8 @@
 //   warp 1      MMA issuer          4 x tcgen05.mma (128 x BN x 16) per k-block, tcgen05.commit frees the stage
 //   warps 2..9  epilogue            two warps per TMEM lane quadrant, alternating 32-column chunks; double-buffered
 //                                   accumulators (2 x 256 TMEM columns) overlap tile i's epilogue with tile i+1's MMAs
-// The role loops are WARP-UNIFORM: all 32 lanes walk the loop and wait on the barriers, one elected lane issues
-// the TMA / MMA / commit.  Measured with the clock64 trace below (FLD_TC_TRACE): the first version ran the loops
+// Each of the two issue roles runs its whole loop inside ONE `elect.sync`-elected lane (the compiler then knows
+// the region is single-lane and emits plain UTMALDG / UTCHMMA / UTCBAR).  Measured with the clock64 trace below (FLD_TC_TRACE): the first version ran the loops
 // inside `if (lane == 0)`, which made nvcc wrap every UTMALDG / UTCHMMA / UTCBAR in R2UR + ELECT waterfall loops —
 // ~730 cycles per k-block in BOTH roles, i.e. 70 % tensor-active at N = 256 and 31 % at N = 128.
 
@@ -86,7 +86,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int mtiles = p.tiles_x * p.tiles_y * p.tiles_b;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    // ------------------------------------------------------------------ TMA producer: one elected lane runs the loop
+    if (elect_one()) {
     uint32_t stage = 0, phase = 0;
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -102,7 +103,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             TRACE(0, ti, 1);
-            if (elect_one()) {
+            {
               const uint32_t fb = full0 + 8 * stage;
               const uint32_t sa = smem_base + stage * stage_bytes;
               const uint32_t bytes = ((p.dbg & 4) ? 0u : a_bytes) + ((p.dbg & 8) ? 0u : b_bytes);
@@ -114,15 +115,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (!(p.dbg & 8)) tma_load_2d(sa + a_bytes, &tmB, fb, kc * 64, wrow);
               TRACE(0, ti, 8);
             }
-            __syncwarp();
             TRACE(0, ti, 2);
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    // ------------------------------------------------------------------ MMA issuer: one elected lane runs the loop
+    if (elect_one()) {
     // Descriptors are built once; per stage / per 16-element K step only the 14-bit start-address field moves
     // (units of 16 bytes).
     const uint32_t idesc = umma_idesc_bf16(128, p.BN);
@@ -143,7 +146,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         TRACE(1, ti, 1);
         tc_fence_after();
         TRACE(1, ti, 5);
-        if (elect_one()) {
+        {
           TRACE(1, ti, 6);
           const uint64_t ad = adesc0 + (uint64_t)(stage * stage_step);
           const uint64_t bd = bdesc0 + (uint64_t)(stage * stage_step);
@@ -158,7 +161,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
           TRACE(1, ti, 8);
         }
-        __syncwarp();
         accum = 1u;
         TRACE(1, ti, 2);
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
@@ -166,6 +168,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
     const int ew = warp - 2;

@@ -9,9 +9,12 @@
 //      writes its 48-element K row (k = kh*12 + kw*4 + c; 36 real taps, 12 zero) with five 16-byte stores in the
 //      UMMA no-swizzle K-major core-matrix layout;
 //   3. one thread issues 3 MMAs (128 x Cout x 16) into TMEM; the fused epilogue of tc_common.cuh pools and stores.
+//      The folded bias rides in two of the spare K slots (A = 1.0, B = bf16 hi / lo halves of the bias, fp32
+//      accumulation: error <= 2^-17 |bias|), which removes 64 FADD + 16 bias loads per thread per tile.
 // The next tile's pixels are prefetched into registers before the current tile's MMA/epilogue, so the global
 // load latency (the dominant stall of the first version: ~31 % of samples on the staging store) is hidden.
 // TMEM-read bound in the limit: 128 x Cout fp32 accumulators per 128 pixels at 64 B/clk/SM.
+#include <string.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -26,6 +29,7 @@ struct FirstParams {
   int Cout;                // 16..256, multiple of 16
   int act, pool;
   int tiles_x, tiles_y, n_tiles;
+  unsigned long long mul_x, mul_y;  // ceil(2^40 / tiles_x), ceil(2^40 / tiles_y): exact division for n < 2^21
 };
 
 constexpr int TWc = 8, THc = 16, PW_ = TWc + 2, PH_ = THc + 2, NPIX = PW_ * PH_;  // 10 x 18 = 180 halo pixels
@@ -43,7 +47,7 @@ __device__ __forceinline__ void load_pixel(const TIn* __restrict__ img, int H, i
 }
 
 template <typename TIn>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 conv_first_kernel(const FirstParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // A [6 kgroups][16 rowgroups][8 rows][16 B] = 12 KB | B [6 kgroups][Cout/8][8][16 B] = Cout*96 B | patch [18][10] x 8 B
@@ -87,10 +91,10 @@ conv_first_kernel(const FirstParams p) {
   const int r1 = e1 / PW_, c1 = e1 - r1 * PW_;
 
   auto tile_origin = [&](int tile, int& b, int& x0, int& y0) {
-    const int tx = tile % p.tiles_x;
-    const int t2 = tile / p.tiles_x;
-    const int ty = t2 % p.tiles_y;
-    b = t2 / p.tiles_y;
+    const int t2 = (int)(((unsigned long long)(unsigned)tile * p.mul_x) >> 40);
+    const int tx = tile - t2 * p.tiles_x;
+    b = (int)(((unsigned long long)(unsigned)t2 * p.mul_y) >> 40);
+    const int ty = t2 - b * p.tiles_y;
     x0 = tx * TWc; y0 = ty * THc;
   };
   auto fetch = [&](int tile, Raw3<TIn>& v0, Raw3<TIn>& v1) {
@@ -130,18 +134,21 @@ conv_first_kernel(const FirstParams p) {
       *reinterpret_cast<uint4*>(row + 1 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
       *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
       *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
-      *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0u, 0u);
+      *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0x3f803f80u, 0u);  // k 36,37 = 1.0 (bias)
     }
     fence_async_smem();
     __syncthreads();
     // ---- 3. three K = 16 MMAs (k groups 0-1, 2-3, 4-5); LBO field moves by 2 groups per step
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      const uint64_t astep = (uint64_t)((2 * a_lbo) >> 4), bstep = (uint64_t)((2 * b_lbo) >> 4);
-      umma_bf16(tmem_base, adesc0, bdesc0, idesc, 0u);
-      umma_bf16(tmem_base, adesc0 + astep, bdesc0 + bstep, idesc, 1u);
-      umma_bf16(tmem_base, adesc0 + 2 * astep, bdesc0 + 2 * bstep, idesc, 1u);
-      umma_commit(smem_u32(&mma_bar));
+      if (elect_one()) {  // single-lane region known to the compiler: plain UTCHMMA / UTCBAR, no waterfall loops
+        const uint64_t astep = (uint64_t)((2 * a_lbo) >> 4), bstep = (uint64_t)((2 * b_lbo) >> 4);
+        umma_bf16(tmem_base, adesc0, bdesc0, idesc, 0u);
+        umma_bf16(tmem_base, adesc0 + astep, bdesc0 + bstep, idesc, 1u);
+        umma_bf16(tmem_base, adesc0 + 2 * astep, bdesc0 + 2 * bstep, idesc, 1u);
+        umma_commit(smem_u32(&mma_bar));
+      }
+      __syncwarp();
     }
     mbar_wait(smem_u32(&mma_bar), phase);
     phase ^= 1;
@@ -164,8 +171,8 @@ conv_first_kernel(const FirstParams p) {
       EpiOut e2 = eo;
       e2.ptr = reinterpret_cast<__nv_bfloat16*>(eo.ptr) + ch;
       e2.c_left = p.Cout - ch;
-      if (p.pool) epilogue_chunk<true, false>(acc, p.bias + ch, p.act, lane, TWc, e2);
-      else epilogue_chunk<false, false>(acc, p.bias + ch, p.act, lane, TWc, e2);
+      if (p.pool) epilogue_chunk<true, false, false>(acc, p.bias + ch, p.act, lane, TWc, e2);
+      else epilogue_chunk<false, false, false>(acc, p.bias + ch, p.act, lane, TWc, e2);
     }
     tc_fence_before();
     __syncthreads();  // TMEM, A tile and patch are free for the next tile
@@ -182,8 +189,8 @@ bool tc_conv_first_supported(const ConvGeom& g) {
 }
 
 // host-side weight packing for conv_first_kernel: w_host fp32 [27][Cout] (k = (kh*3+kw)*3 + c) -> bf16 bits
-// [6][Cout/8][8][8] with k' = kh*12 + kw*4 + c
-void tc_conv_first_pack(const float* w_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out) {
+// [6][Cout/8][8][8] with k' = kh*12 + kw*4 + c; k' = 36 / 37 carry the bias split into bf16 hi / lo
+void tc_conv_first_pack(const float* w_host, const float* bias_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out) {
   for (int kg = 0; kg < 6; ++kg)
     for (int ng = 0; ng < Cout / 8; ++ng)
       for (int r = 0; r < 8; ++r)
@@ -192,6 +199,13 @@ void tc_conv_first_pack(const float* w_host, int Cout, uint16_t (*f2bf)(float), 
           const int kh = kp / 12, kw = (kp % 12) / 4, c = kp % 4;
           float v = 0.f;
           if (kp < 36 && c < 3) v = w_host[(size_t)((kh * 3 + kw) * 3 + c) * Cout + o];
+          if (bias_host && (kp == 36 || kp == 37)) {  // bias = hi + lo (both bf16), multiplied by A[k] = 1.0
+            uint16_t hb = f2bf(bias_host[o]);
+            uint32_t hu = (uint32_t)hb << 16;
+            float hi;
+            memcpy(&hi, &hu, 4);
+            v = (kp == 36) ? hi : bias_host[o] - hi;
+          }
           out[(((size_t)kg * (Cout / 8) + ng) * 8 + r) * 8 + e] = f2bf(v);
         }
 }
@@ -204,10 +218,15 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
   p.B = B; p.H = g.IH; p.W = g.IW; p.Cout = g.Cout; p.act = g.act; p.pool = g.pool;
   p.tiles_x = fld_div_up(g.OW, TWc); p.tiles_y = fld_div_up(g.OH, THc);
   p.n_tiles = B * p.tiles_x * p.tiles_y;
+  p.mul_x = ((1ull << 40) + p.tiles_x - 1) / p.tiles_x;
+  p.mul_y = ((1ull << 40) + p.tiles_y - 1) / p.tiles_y;
+  if (p.n_tiles >= (1 << 21)) { fld_set_error("tc_conv_first: too many tiles (%d)", p.n_tiles); return FLD_ERR_INVALID; }
   const size_t smem = 12288 + (size_t)g.Cout * 96 + NPIX * 8 + 64;
   const int ncols = g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : g.Cout <= 128 ? 128 : 256;
   const int cta_per_sm = std::max(1, std::min(512 / ncols, 8));
   const int grid = std::min(p.n_tiles, h->sm_count * cta_per_sm);
+  FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   if (in_dtype == FLD_U8) {
     if (smem > 48 * 1024) FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv_first_kernel<uint8_t><<<grid, 128, smem, st>>>(p);

@@ -78,99 +78,95 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int txy = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    auto issue_halo = [&](int g) {  // all lanes call; one lane issues
-      const int lt = g / kchunks, kc = g - lt * kchunks;
-      const int tile = blockIdx.x + lt * gridDim.x;
-      const int b = tile / txy;
-      const int m = tile - b * txy;
-      const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
-      const int slot = g & 1;
-      mbar_wait(emptyA0 + 8 * slot, ((g >> 1) & 1) ^ 1);
-      if (elect_one()) {
+    // ------------------------------------------------------------------ TMA producer: ONE elected lane runs the whole
+    // loop (the compiler then knows the region is single-lane: plain UTMALDG / SYNCS, no per-instruction waterfall)
+    if (elect_one()) {
+      auto issue_halo = [&](int g) {
+        const int lt = g / kchunks, kc = g - lt * kchunks;
+        const int tile = blockIdx.x + lt * gridDim.x;
+        const int b = tile / txy;
+        const int m = tile - b * txy;
+        const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
+        const int slot = g & 1;
+        mbar_wait(emptyA0 + 8 * slot, ((g >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(fullA0 + 8 * slot, kHaloBytes);
         tma_load_4d(smemA + slot * kHaloBytes, &tmA, fullA0 + 8 * slot, kc * 64, tx * 8 - 1, ty * 16 - 1, b);
-      }
-      __syncwarp();
-    };
-    if (stationary) {
-      if (elect_one()) {
+      };
+      if (stationary) {
         mbar_arrive_expect_tx(wfull0, 9u * kchunks * b_bytes);
         for (int t = 0; t < 9; ++t)
           for (int kc = 0; kc < kchunks; ++kc)
             tma_load_2d(smemB + (t * kchunks + kc) * b_bytes, &tmB, wfull0, kc * 64, t * p.cout_pad);
-      }
-      __syncwarp();
-      for (int g = 0; g < G; ++g) issue_halo(g);
-    } else {
-      uint32_t sb = 0, phb = 0;
-      if (G > 0) issue_halo(0);
-      for (int g = 0; g < G; ++g) {
-        const int kc = g % kchunks;
-        for (int t = 0; t < 9; ++t) {
-          if (t == 2 && g + 1 < G) issue_halo(g + 1);  // prefetch the next halo a few taps ahead
-          mbar_wait(emptyB0 + 8 * sb, phb ^ 1);
-          if (elect_one()) {
+        for (int g = 0; g < G; ++g) issue_halo(g);
+      } else {
+        uint32_t sb = 0, phb = 0;
+        if (G > 0) issue_halo(0);
+        for (int g = 0; g < G; ++g) {
+          const int kc = g % kchunks;
+          for (int t = 0; t < 9; ++t) {
+            if (t == 2 && g + 1 < G) issue_halo(g + 1);  // prefetch the next halo a few taps ahead
+            mbar_wait(emptyB0 + 8 * sb, phb ^ 1);
             mbar_arrive_expect_tx(fullB0 + 8 * sb, b_bytes);
             tma_load_2d(smemB + sb * b_bytes, &tmB, fullB0 + 8 * sb, kc * 64, t * p.cout_pad);
+            if (++sb == (uint32_t)p.SB) { sb = 0; phb ^= 1; }
           }
-          __syncwarp();
-          if (++sb == (uint32_t)p.SB) { sb = 0; phb ^= 1; }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
-    // A: K-major SW128, rows of 128 B, 8-row groups 2048 B apart (one halo row of 16 pixels)
-    const uint64_t adesc0 = umma_desc(smemA, 16, kHaloW * 128, 2);
-    const uint64_t bdesc0 = umma_desc(smemB, 16, 1024, 2);
-    uint32_t sb = 0, phb = 0, acc = 0, acc_phase = 0;
-    if (stationary) { mbar_wait(wfull0, 0); tc_fence_after(); }
-    for (int g = 0; g < G; ++g) {
-      const int kc = g % kchunks;
-      if (kc == 0) {
-        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+    // ------------------------------------------------------------------ MMA issuer: one elected lane, taps unrolled
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+      // A: K-major SW128, rows of 128 B, 8-row groups 2048 B apart (one halo row of 16 pixels)
+      const uint64_t adesc0 = umma_desc(smemA, 16, kHaloW * 128, 2);
+      const uint64_t bdesc0 = umma_desc(smemB, 16, 1024, 2);
+      const uint32_t b_step = b_bytes >> 4;
+      uint32_t sb = 0, phb = 0, acc = 0, acc_phase = 0;
+      if (stationary) { mbar_wait(wfull0, 0); tc_fence_after(); }
+      for (int g = 0; g < G; ++g) {
+        const int kc = g % kchunks;
+        if (kc == 0) {
+          mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t d = tmem_base + acc * 256;
+        const int slot = g & 1;
+        mbar_wait(fullA0 + 8 * slot, (g >> 1) & 1);
         tc_fence_after();
-      }
-      const uint32_t d = tmem_base + acc * 256;
-      const int slot = g & 1;
-      mbar_wait(fullA0 + 8 * slot, (g >> 1) & 1);
-      tc_fence_after();
-      const uint64_t a_slot = adesc0 + (uint64_t)((slot * kHaloBytes) >> 4);
-#pragma unroll 1
-      for (int ky = 0; ky < 3; ++ky) {
+        const uint64_t a_slot = adesc0 + (uint64_t)((slot * kHaloBytes) >> 4);
+        uint64_t bd = bdesc0 + (uint64_t)(kc * b_step);   // stationary: tile (t*kchunks + kc)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int t = ky * 3 + kx;
-          uint64_t bd;
-          if (stationary) {
-            bd = bdesc0 + (uint64_t)(((t * kchunks + kc) * b_bytes) >> 4);
-          } else {
+        for (int t = 0; t < 9; ++t) {
+          const int ky = t / 3, kx = t - 3 * ky;
+          if (!stationary) {
             mbar_wait(fullB0 + 8 * sb, phb);
             tc_fence_after();
-            bd = bdesc0 + (uint64_t)((sb * b_bytes) >> 4);
+            bd = bdesc0 + (uint64_t)(sb * b_step);
           }
-          if (elect_one()) {
-            // shifted window: + (ky*16 + kx) pixels of 128 B; swizzle phase of the start = kx
-            uint64_t ad = a_slot + (uint64_t)((ky * kHaloW + kx) * 8);
-            if (p.baseoff) ad = with_base_offset(ad, (uint32_t)kx);
-            umma_bf16(d, ad, bd, idesc, (kc | t) ? 1u : 0u);
-            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-            if (!stationary) umma_commit(emptyB0 + 8 * sb);
-            if (t == 8) {
-              umma_commit(emptyA0 + 8 * slot);
-              if (kc == kchunks - 1) umma_commit(tfull0 + 8 * acc);
-            }
+          // shifted window: + (ky*16 + kx) pixels of 128 B (8 units of 16 B each); no base_offset (see header)
+          uint64_t ad = a_slot + (uint64_t)((ky * kHaloW + kx) * 8);
+          if (p.baseoff) ad = with_base_offset(ad, (uint32_t)kx);
+          umma_bf16(d, ad, bd, idesc, (kc | t) ? 1u : 0u);
+          umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+          umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+          if (stationary) {
+            bd += (uint64_t)(kchunks * b_step);
+          } else {
+            umma_commit(emptyB0 + 8 * sb);
+            if (++sb == (uint32_t)p.SB) { sb = 0; phb ^= 1; }
           }
-          __syncwarp();
-          if (!stationary) { if (++sb == (uint32_t)p.SB) { sb = 0; phb ^= 1; } }
+        }
+        umma_commit(emptyA0 + 8 * slot);
+        if (kc == kchunks - 1) {
+          umma_commit(tfull0 + 8 * acc);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
       }
-      if (kc == kchunks - 1) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (same mapping as tc_conv.cu, TW = 8)
     const int ew = warp - 2, sub = warp & 3, half = ew >> 2;
