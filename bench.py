@@ -82,6 +82,24 @@ def valid_tap_macs(h, w, cin, cout, k=3):
 TRUNK = [(128, 3, 64), (64, 64, 128), (32, 128, 256), (16, 256, 256), (8, 256, 256)]  # (map size, Cin, Cout)
 
 
+def ncu_traffic_bytes(kernels=("conv_halo_kernel", "conv_tma_kernel")):
+    """dram__bytes_read + dram__bytes_write of the dominant kernel family for ONE step (= one launch set), from the
+    newest committed `ncu --set full` summary under profiles/ (tools/summarize_profiles.py); None if there is none."""
+    import glob, re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_conv_full.txt")))
+    if not files:
+        return None, None
+    total, cur = 0.0, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(files[-1]):
+        if line.startswith("=="):
+            cur = line
+        m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+        if m and cur and any(k in cur for k in kernels):
+            total += float(m.group(2)) * unit.get(m.group(3), 1.0)
+    return (total or None), os.path.basename(files[-1])
+
+
 def flops_per_face():
     macs = [valid_tap_macs(s, s, ci, co) for s, ci, co in TRUNK]
     return [2.0 * m for m in macs], 2.0 * 4096 * 136
@@ -262,9 +280,12 @@ def run_gpu(args, rank, world, local_rank):
         t_dom = float(per_layer[1:5].sum()) * 1e-3
         fl = sum(conv_flops[1:5]) * B
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        roof = {"kernel": "conv_tma_kernel (conv2..conv5, 4 launches/step)", "bound": "tensor", "achieved": fl / t_dom / 1e12,
+        traffic, traffic_src = ncu_traffic_bytes()
+        roof = {"kernel": "tcgen05 conv trunk: conv_halo_kernel x3 (conv2..conv4) + conv_tma_kernel (conv5), 4 launches/step",
+                "bound": "tensor", "achieved": fl / t_dom / 1e12,
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (sustained, B200_PROFILING.md)",
-                "unit": "TFLOP/s", "traffic": None, "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3}
+                "unit": "TFLOP/s", "traffic": traffic, "traffic_source": traffic_src, "traffic_note": "DRAM bytes per launch set at batch 256",
+                "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3}
     else:
         t_dom = float(per_layer[0:5].sum()) * 1e-3
         fl = sum(conv_flops) * B

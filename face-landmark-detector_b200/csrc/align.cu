@@ -7,7 +7,11 @@
 // One CTA per face.  Thread 0 fits (sequential fp64 sums, no FMA contraction, so M is bit-identical
 // to the CPU oracle), the CTA builds the per-column / per-row fixed-point coordinate tables in shared
 // memory, then every thread produces 4 consecutive output pixels (12 bytes -> three 32-bit stores)
-// from 8-byte-aligned source loads.  HBM-bound: ~37.6 kB written + source footprint read per face.
+// from 8-byte-aligned source loads.  Algorithmic traffic ~37.6 kB written + source footprint read per face.
+// MEASURED (ncu, round 1, config C4): DRAM runs at 17 % while the L1 tag stage is the busiest unit — every warp-level
+// load touches ~21 sectors on many lines (rotated faces put each lane on its own source row).  Two leaner-ALU rewrites
+// (IDP.4A blends, 32-bit funnel loads, loads hoisted for MLP) were SLOWER (0.34 / 0.39 ms vs 0.32 ms) because they issue
+// more, narrower requests; the next step is a 2-D warp->pixel mapping with shared-memory staged stores.
 #include "common.cuh"
 
 namespace {
@@ -97,14 +101,15 @@ __global__ void __launch_bounds__(kAlignThreads)
 align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const int32_t* __restrict__ face2frame,
                   const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int Nt, int five_point,
                   const double* __restrict__ M_in, double* __restrict__ M_out, uint8_t* __restrict__ crops,
-                  int out_h, int out_w, int rtC) {
+                  int out_h, int out_w, int rtC, int rows_per) {
   __shared__ Fit fit;
-  extern __shared__ int tab[];  // adelta[out_w], bdelta[out_w], X0[out_h], Y0[out_h]
+  extern __shared__ int tab[];  // adelta[out_w], bdelta[out_w], X0[rows_per], Y0[rows_per]
   int* adelta = tab;
   int* bdelta = tab + out_w;
   int* X0 = tab + 2 * out_w;
-  int* Y0 = tab + 2 * out_w + out_h;
+  int* Y0 = tab + 2 * out_w + rows_per;
   const int face = blockIdx.x;
+  const int y_beg = blockIdx.y * rows_per, y_end = min(out_h, y_beg + rows_per);  // this CTA's rows of the face
   const int tid = threadIdx.x;
   const int nc = FAST ? C : rtC;
 
@@ -120,12 +125,12 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
     if (fr < 0 || fr >= F) ok = 0;
     if (ok) invert_affine(fit.M, fit.iM);
     fit.ok = ok;
-    if (M_out) for (int i = 0; i < 6; ++i) M_out[(size_t)face * 6 + i] = fit.M[i];
+    if (M_out && blockIdx.y == 0) for (int i = 0; i < 6; ++i) M_out[(size_t)face * 6 + i] = fit.M[i];
   }
   __syncthreads();
   uint8_t* crop = crops + (size_t)face * out_h * out_w * nc;
   if (!fit.ok) {
-    for (int i = tid; i < out_h * out_w * nc; i += kAlignThreads) crop[i] = 0;
+    for (int i = y_beg * out_w * nc + tid; i < y_end * out_w * nc; i += kAlignThreads) crop[i] = 0;
     return;
   }
   const double AB = 1024.0;
@@ -133,9 +138,9 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
     adelta[x] = (int)__double2ll_rn(dm(dm(fit.iM[0], (double)x), AB));
     bdelta[x] = (int)__double2ll_rn(dm(dm(fit.iM[3], (double)x), AB));
   }
-  for (int y = tid; y < out_h; y += kAlignThreads) {
-    X0[y] = (int)__double2ll_rn(dm(da(dm(fit.iM[1], (double)y), fit.iM[2]), AB)) + 16;
-    Y0[y] = (int)__double2ll_rn(dm(da(dm(fit.iM[4], (double)y), fit.iM[5]), AB)) + 16;
+  for (int y = y_beg + tid; y < y_end; y += kAlignThreads) {
+    X0[y - y_beg] = (int)__double2ll_rn(dm(da(dm(fit.iM[1], (double)y), fit.iM[2]), AB)) + 16;
+    Y0[y - y_beg] = (int)__double2ll_rn(dm(da(dm(fit.iM[4], (double)y), fit.iM[5]), AB)) + 16;
   }
   __syncthreads();
 
@@ -146,11 +151,12 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
     // C == 3, out_w % 4 == 0: 4 pixels (12 bytes) per thread per step
     const uint8_t* safe_end = frames + (size_t)F * H * W * 3 - 16;  // last address load6 may start from
     const int groups_per_row = out_w >> 2;
-    const int n_groups = out_h * groups_per_row;
+    const int n_groups = (y_end - y_beg) * groups_per_row;
     for (int g = tid; g < n_groups; g += kAlignThreads) {
-      const int y = g / groups_per_row;
-      const int xg = (g - y * groups_per_row) << 2;
-      const int bx = X0[y], by = Y0[y];
+      const int yl = g / groups_per_row;
+      const int y = y_beg + yl;
+      const int xg = (g - yl * groups_per_row) << 2;
+      const int bx = X0[yl], by = Y0[yl];
       uint32_t outw[3] = {0u, 0u, 0u};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -204,11 +210,11 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
       dst[0] = outw[0]; dst[1] = outw[1]; dst[2] = outw[2];
     }
   } else {
-    const int n_px = out_h * out_w;
+    const int n_px = (y_end - y_beg) * out_w;
     for (int i = tid; i < n_px; i += kAlignThreads) {
-      const int y = i / out_w, x = i - y * out_w;
-      const int X = (X0[y] + adelta[x]) >> 5;
-      const int Y = (Y0[y] + bdelta[x]) >> 5;
+      const int yl = i / out_w, x = i - yl * out_w;
+      const int X = (X0[yl] + adelta[x]) >> 5;
+      const int Y = (Y0[yl] + bdelta[x]) >> 5;
       const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
       const int fx = X & 31, fy = Y & 31;
       const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32;
@@ -221,7 +227,7 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
         const int p01 = (y0in && x1in) ? frame[o + nc] : 0;
         const int p10 = (y1in && x0in) ? frame[o + (ptrdiff_t)row] : 0;
         const int p11 = (y1in && x1in) ? frame[o + (ptrdiff_t)row + nc] : 0;
-        crop[(size_t)i * nc + ch] = (uint8_t)((w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11 + 16384) >> 15);
+        crop[((size_t)(y_beg + yl) * out_w + x) * nc + ch] = (uint8_t)((w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11 + 16384) >> 15);
       }
     }
   }
@@ -242,15 +248,20 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
     else FLD_REQUIRE(N == Nt && N >= 2, "fld_align: N (%d) must equal Nt (%d) and be >= 2", N, Nt);
   }
   if (B == 0) return FLD_OK;
-  const size_t smem = (size_t)(2 * out_w + 2 * out_h) * sizeof(int);
+  // small batches: split each face over several CTAs (row blocks) so that the grid covers the machine
+  int rb = 1;
+  while (rb < 8 && (long long)B * rb < 4ll * h->sm_count && out_h / (rb * 2) >= 8) rb *= 2;
+  const int rows_per = fld_div_up(out_h, rb);
+  const dim3 grid(B, fld_div_up(out_h, rows_per));
+  const size_t smem = (size_t)(2 * out_w + 2 * rows_per) * sizeof(int);
   const bool fast = (C == 3) && (out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(crops) & 3) == 0) &&
                     ((size_t)F * H * W * 3 >= 32);
   if (fast) {
-    align_warp_kernel<3, true><<<B, kAlignThreads, smem, st>>>(frames, F, H, W, face2frame, marks, N, tmpl, Nt, five_point,
-                                                               M_in, M_out, crops, out_h, out_w, 3);
+    align_warp_kernel<3, true><<<grid, kAlignThreads, smem, st>>>(frames, F, H, W, face2frame, marks, N, tmpl, Nt, five_point,
+                                                               M_in, M_out, crops, out_h, out_w, 3, rows_per);
   } else {
-    align_warp_kernel<1, false><<<B, kAlignThreads, smem, st>>>(frames, F, H, W, face2frame, marks, N, tmpl, Nt, five_point,
-                                                                M_in, M_out, crops, out_h, out_w, C);
+    align_warp_kernel<1, false><<<grid, kAlignThreads, smem, st>>>(frames, F, H, W, face2frame, marks, N, tmpl, Nt, five_point,
+                                                                M_in, M_out, crops, out_h, out_w, C, rows_per);
   }
   FLD_LAUNCHED();
   return FLD_OK;

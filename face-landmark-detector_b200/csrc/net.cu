@@ -219,12 +219,26 @@ extern "C" int fld_net_set_weights(fld_net* net, int layer, const float* kernel_
       for (int o = 0; o < Cout; ++o) L.w_host[k * Cout + o] = (float)((double)kernel_h[k * Cout + o] * scale[o] * isc);
   } else if (d.op == FLD_OP_DECONV) {
     FLD_REQUIRE(!bn_h && !bias_h, "fld_net_set_weights: Conv2DTranspose layers carry no bias/BN in the reference graphs");
-    const int k = d.kh, Cin = a.c;
+    const int k = d.kh, Cin = a.c, st = d.stride;
     L.w_host.resize((size_t)k * k * Cin * Cout);
-    for (int t = 0; t < k * k; ++t)
-      for (int o = 0; o < Cout; ++o)
-        for (int c = 0; c < Cin; ++c)
-          L.w_host[((size_t)t * Cin + c) * Cout + o] = kernel_h[((size_t)t * Cout + o) * Cin + c];
+    if (k == 2 * st) {
+      // phase layout for simt_deconv_phase: [a*s+b][u][v][Cin][Cout] = W[a + s(1-u)][b + s(1-v)][o][c]
+      for (int pa = 0; pa < st; ++pa)
+        for (int pb = 0; pb < st; ++pb)
+          for (int u = 0; u < 2; ++u)
+            for (int v = 0; v < 2; ++v) {
+              const int ka = pa + st * (1 - u), kb = pb + st * (1 - v);
+              float* dst = &L.w_host[((((size_t)(pa * st + pb) * 2 + u) * 2 + v) * Cin) * Cout];
+              const float* src = kernel_h + ((size_t)(ka * k + kb) * Cout) * Cin;
+              for (int c = 0; c < Cin; ++c)
+                for (int o = 0; o < Cout; ++o) dst[(size_t)c * Cout + o] = src[(size_t)o * Cin + c];
+            }
+    } else {
+      for (int t = 0; t < k * k; ++t)
+        for (int o = 0; o < Cout; ++o)
+          for (int c = 0; c < Cin; ++c)
+            L.w_host[((size_t)t * Cin + c) * Cout + o] = kernel_h[((size_t)t * Cout + o) * Cin + c];
+    }
   } else if (d.op == FLD_OP_DENSE) {
     const size_t In = a.elems();
     L.w_host.resize(In * Cout);
@@ -376,7 +390,8 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
         }
         break;
       case FLD_OP_DECONV:
-        rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
+        if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
+        else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
       case FLD_OP_ADD: {
         const TensorInfo& b2 = net->tensors[d.in1];

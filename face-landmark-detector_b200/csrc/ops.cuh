@@ -16,6 +16,9 @@ int simt_conv(const void* in, int in_dtype, const float* w /*[kh*kw*Cin][Cout]*/
               const ConvGeom& g, int B, cudaStream_t st);
 int simt_deconv(const void* in, int in_dtype, const float* w /*[k][k][Cin][Cout]*/, float* out, int B, int IH, int IW, int Cin,
                 int OH, int OW, int Cout, int k, int s, cudaStream_t st);
+// k == 2*s: stride^2 phase convolutions (simt_deconv.cu); weights [s*s][2][2][Cin][Cout]
+int simt_deconv_phase(const void* in, int in_dtype, const float* w_phase, float* out, int B, int IH, int IW, int Cin, int Cout, int s,
+                      cudaStream_t st);
 int simt_add_crop(const float* a, int AH, int AW, const float* b, int BH, int BW, float* out, int B, int OH, int OW, int C,
                   cudaStream_t st);
 int simt_softmax(const float* in, float* out, long long n_px, int C, cudaStream_t st);
