@@ -71,17 +71,22 @@ __global__ void topn_partial_kernel(const float* __restrict__ hm, int HW, int L,
   const int per = (HW + S - 1) / S;
   const int p0 = s * per, p1 = min(HW, p0 + per);
   const float* base = hm + (size_t)b * HW * L;
-  for (int p = p0 + r; p < p1; p += R) {
-    const float v = base[(size_t)p * L + l];
+  auto consider = [&](float v, int p) {
     if (better(v, p, top[mn].v, top[mn].idx)) {
 #pragma unroll
       for (int k = 0; k < NMAX; ++k) if (k == mn) { top[k].v = v; top[k].idx = p; }
-      // rescan for the worst
-      mn = 0;
+      mn = 0;  // rescan for the worst
 #pragma unroll
       for (int k = 1; k < NMAX; ++k) if (k < n && better(top[mn].v, top[mn].idx, top[k].v, top[k].idx)) mn = k;
     }
+  };
+  int p = p0 + r;
+  for (; p + 3 * R < p1; p += 4 * R) {  // four independent loads in flight per thread
+    const float v0 = __ldg(base + (size_t)p * L + l), v1 = __ldg(base + (size_t)(p + R) * L + l);
+    const float v2 = __ldg(base + (size_t)(p + 2 * R) * L + l), v3 = __ldg(base + (size_t)(p + 3 * R) * L + l);
+    consider(v0, p); consider(v1, p + R); consider(v2, p + 2 * R); consider(v3, p + 3 * R);
   }
+  for (; p < p1; p += R) consider(__ldg(base + (size_t)p * L + l), p);
   // every (slab, r) lane writes its n candidates; merge kernel selects among S*R*n
   Cand* dst = partial + ((((size_t)b * S + s) * R + r) * L + l) * n;
   for (int k = 0; k < n; ++k) dst[k] = top[k];
@@ -135,8 +140,19 @@ __global__ void soft_partial_kernel(const float* __restrict__ hm, int HW, int W,
   const int p0 = s * per, p1 = min(HW, p0 + per);
   const float* base = hm + (size_t)b * HW * L;
   double sh = 0, sx = 0, sy = 0;
-  for (int p = p0 + r; p < p1; p += R) {
-    const double v = (double)base[(size_t)p * L + l];
+  int p = p0 + r;
+  for (; p + 3 * R < p1; p += 4 * R) {  // four independent loads in flight per thread
+    const float v[4] = {__ldg(base + (size_t)p * L + l), __ldg(base + (size_t)(p + R) * L + l),
+                        __ldg(base + (size_t)(p + 2 * R) * L + l), __ldg(base + (size_t)(p + 3 * R) * L + l)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pp = p + q * R;
+      const int row = pp / W, col = pp - row * W;
+      sh += (double)v[q]; sx += (double)v[q] * col; sy += (double)v[q] * row;
+    }
+  }
+  for (; p < p1; p += R) {
+    const double v = (double)__ldg(base + (size_t)p * L + l);
     const int row = p / W, col = p - row * W;
     sh += v; sx += v * col; sy += v * row;
   }
@@ -205,9 +221,10 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
   const int HW = H * W;
   const int R = (L >= 256) ? 1 : fld_div_up(256, L);  // pixel lanes per CTA
   const int threads = R * L;
-  // slabs: enough CTAs to cover the machine ~2x, at least 256 pixels per lane
-  int S = fld_div_up(2 * h->sm_count, B);
-  S = max(1, min(S, HW / (256 * R) > 0 ? HW / (256 * R) : 1));
+  // slabs: enough CTAs to cover the machine ~8x (the kernels are latency-bound: one strided stream per thread),
+  // at least 64 pixels per lane
+  int S = fld_div_up(8 * h->sm_count, B);
+  S = max(1, min(S, HW / (64 * R) > 0 ? HW / (64 * R) : 1));
   S = min(S, 65535);
   dim3 grid(B, S);
   const int nBL = B * L;

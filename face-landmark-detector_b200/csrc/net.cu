@@ -21,7 +21,7 @@ struct TensorInfo {
 
 enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 
-struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
+struct PlanEntry { int B; const void* in; TcConvPlan* plan; int fuse = 0; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
 
 struct LayerRt {
@@ -29,6 +29,9 @@ struct LayerRt {
   ConvGeom g{};
   int path = PATH_SIMT;
   int cout_pad = 0;
+  int dc_cpad = 0, dc_cpp = 0;  // tensor-core transposed conv: padded input channels, padded channels per phase
+  bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
+  bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
   bool needs_weights = false, has_weights = false;
   std::vector<float> w_host;  // folded fp32: conv [K][Cout]; deconv [k][k][Cin][Cout]; dense [In][Out]
   std::vector<float> b_host;  // folded bias [Cout] (empty = none)
@@ -126,6 +129,13 @@ int infer_shapes(fld_net* net) {
       LayerRt& L = net->layers[i];
       TensorInfo& o = net->tensors[i + 1];
       const TensorInfo& a = net->tensors[L.d.in0];
+      if (L.d.op == FLD_OP_DECONV && L.d.kh == 2 * L.d.stride && L.d.stride >= 4 && L.d.stride <= 8 && a.c <= 128 && L.d.cout <= 96 &&
+          a.dtype == FLD_F32 && !getenv("FLD_TC_DECONV_OFF")) {
+        // stride^2 phase convolutions on the tensor cores (tc_conv.cu depth-to-space mode)
+        L.path = PATH_TC_TMA;
+        L.dc_cpad = (int)align_up(a.c, 64);
+        L.dc_cpp = (int)align_up(L.d.cout, 32);
+      }
       if (L.d.op != FLD_OP_CONV) { o.dtype = FLD_F32; continue; }
       const bool want_f32 = f32_needed[i + 1] != 0;
       const bool in_ok_first = (a.dtype == FLD_U8 || a.dtype == FLD_F32) && tc_conv_first_supported(L.g);
@@ -134,6 +144,17 @@ int infer_shapes(fld_net* net) {
       else if (in_ok_tma && !(want_f32 && L.g.pool)) { L.path = PATH_TC_TMA; o.dtype = want_f32 ? FLD_F32 : FLD_BF16; }
       else { L.path = PATH_SIMT; o.dtype = want_f32 ? FLD_F32 : FLD_BF16; }
       if (L.path == PATH_TC_TMA) L.cout_pad = (int)align_up(L.g.Cout, L.g.Cout > 256 ? 128 : 16);
+    }
+    // DECONV (tensor cores) immediately followed by the final SOFTMAX over its channels: fuse the softmax into the epilogue
+    for (int i = 0; i + 1 < nL; ++i) {
+      LayerRt& L = net->layers[i];
+      LayerRt& N2 = net->layers[i + 1];
+      if (L.d.op != FLD_OP_DECONV || L.path != PATH_TC_TMA || N2.d.op != FLD_OP_SOFTMAX || N2.d.in0 != i + 1) continue;
+      bool other_use = false;
+      for (int j = i + 2; j < nL; ++j) other_use |= (net->layers[j].d.in0 == i + 1 || net->layers[j].d.in1 == i + 1);
+      if (other_use || L.dc_cpp > 96 || (L.d.stride * L.d.stride) % 2 != 0 || getenv("FLD_TC_FUSE_OFF")) continue;
+      L.dc_fuse_softmax = true;
+      N2.skip = true;
     }
   }
   return FLD_OK;
@@ -274,7 +295,18 @@ extern "C" int fld_net_finalize(fld_net* net) {
       FLD_CUDA(cudaMalloc(&L.d_bias, nb * sizeof(float)));
       FLD_CUDA(cudaMemcpy(L.d_bias, b.data(), nb * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (L.path == PATH_SIMT) {
+    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) {
+      // [tap = u*2+v][phase*cpp + o][cpad]  <-  phase layout [phase][u][v][Cin][Cout] (set_weights)
+      const int st = L.d.stride, Cin = a.c, cp = L.dc_cpad, cpp = L.dc_cpp, nph = st * st;
+      std::vector<uint16_t> pk((size_t)4 * nph * cpp * cp, 0);
+      for (int ph = 0; ph < nph; ++ph)
+        for (int t = 0; t < 4; ++t)
+          for (int c = 0; c < Cin; ++c)
+            for (int o = 0; o < Cout; ++o)
+              pk[(((size_t)t * nph + ph) * cpp + o) * cp + c] = f2bf(L.w_host[(((size_t)ph * 4 + t) * Cin + c) * Cout + o]);
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (L.path == PATH_SIMT) {
       FLD_CUDA(cudaMalloc(&L.d_w, L.w_host.size() * sizeof(float)));
       FLD_CUDA(cudaMemcpy(L.d_w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
@@ -301,8 +333,12 @@ extern "C" int fld_net_finalize(fld_net* net) {
 static size_t dense_scratch_bytes(const fld_net* net, int B) {
   size_t m = 0;
   for (size_t i = 0; i < net->layers.size(); ++i)
-    if (net->layers[i].d.op == FLD_OP_DENSE)
-      m = std::max(m, simt_dense_scratch_bytes(B, (int)net->tensors[net->layers[i].d.in0].elems(), net->layers[i].d.cout));
+  {
+    const LayerRt& L = net->layers[i];
+    const TensorInfo& a = net->tensors[L.d.in0];
+    if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
+    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) m = std::max(m, (size_t)B * a.h * a.w * L.dc_cpad * 2);
+  }
   return m;
 }
 
@@ -327,7 +363,9 @@ extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
   return off + align_up(dense_scratch_bytes(net, B), 1024) + 1024;
 }
 
-extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {
+extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, int hw, int L, int64_t* class_map, fld_stream stream);
+
+static int net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, int64_t* cmap_out, fld_stream stream) {
   FLD_REQUIRE(net, "fld_net_forward: null net");
   int rc = fld_enter(net->h);
   if (rc) return rc;
@@ -344,6 +382,7 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
   std::vector<void*> ptr(nT);
   ptr[0] = const_cast<void*>(in);
   float* dense_scratch = nullptr;
+  bool cmap_done = false;
   {
     size_t off = 0;
     for (int t = 1; t < nT; ++t) {
@@ -390,7 +429,28 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
         }
         break;
       case FLD_OP_DECONV:
-        if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
+        if (L.path == PATH_TC_TMA) {
+          rc = simt_pad_cvt_bf16((const float*)pin, dense_scratch, (long long)B * a.h * a.w, a.c, L.dc_cpad, st);
+          if (rc) return rc;
+          // fused decode: 1 = softmax written into the (skipped) SOFTMAX layer's tensor, 2 = int64 class map to the caller
+          const bool last_pair = L.dc_fuse_softmax && (int)i + 2 == (int)net->layers.size();
+          const int fuse = L.dc_fuse_softmax ? ((cmap_out && last_pair) ? 2 : 1) : 0;
+          void* dst = fuse == 2 ? (void*)cmap_out : (fuse == 1 ? ptr[i + 2] : pout);
+          TcConvPlan* plan = nullptr;
+          for (auto& pe : L.plans) if (pe.B == B && pe.in == (const void*)dense_scratch && pe.fuse == fuse) { plan = pe.plan; break; }
+          if (!plan) {
+            ConvGeom g{};
+            g.IH = a.h; g.IW = a.w; g.Cin = L.dc_cpad; g.OH = a.h + 1; g.OW = a.w + 1; g.Cout = d.cout;
+            g.kh = 2; g.kw = 2; g.stride = 1; g.pad_t = 1; g.pad_l = 1; g.act = FLD_ACT_NONE; g.pool = 0;
+            rc = tc_conv_plan_create(net->h, dense_scratch, L.d_wbf, d.stride * d.stride * L.dc_cpp, g, B, &plan, d.stride, L.dc_cpp, fuse);
+            if (rc) return rc;
+            if (L.plans.size() >= 8) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
+            PlanEntry pe; pe.B = B; pe.in = (const void*)dense_scratch; pe.plan = plan; pe.fuse = fuse;
+            L.plans.push_back(pe);
+          }
+          rc = tc_conv_run(plan, L.d_bias, dst, FLD_F32, st);
+          if (fuse == 2) cmap_done = true;
+        } else if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
         else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
       case FLD_OP_ADD: {
@@ -404,6 +464,7 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
                         st);
         break;
       case FLD_OP_SOFTMAX:
+        if (L.skip) break;  // computed by the preceding transposed conv's epilogue
         FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: SOFTMAX input must be fp32", i);
         rc = simt_softmax((const float*)pin, (float*)pout, (long long)B * a.h * a.w, a.c, st);
         break;
@@ -427,6 +488,12 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
     if (net->profiling) FLD_CUDA(cudaEventRecord(net->events[i + 1], st));
   }
   if (net->profiling) net->profiled_once = true;
+  if (cmap_out && !cmap_done) {  // no fused argmax available: class map from the final tensor
+    const TensorInfo& o = net->tensors[nT - 1];
+    FLD_REQUIRE(o.dtype == FLD_F32, "fld_net_forward_classmap: final tensor must be fp32");
+    rc = fld_decode_classmap(net->h, (const float*)ptr[nT - 1], B, o.h * o.w, o.c, cmap_out, stream);
+    if (rc) return rc;
+  }
   if (out) {
     const TensorInfo& o = net->tensors[nT - 1];
     const size_t n = o.elems() * (size_t)B;
@@ -434,6 +501,16 @@ extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* worksp
     else { rc = simt_cvt_bf16_f32(ptr[nT - 1], out, (long long)n, st); if (rc) return rc; }
   }
   return FLD_OK;
+}
+
+extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {
+  return net_forward(net, in, B, workspace, ws_bytes, out, nullptr, stream);
+}
+
+extern "C" int fld_net_forward_classmap(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int64_t* class_map,
+                                        fld_stream stream) {
+  if (!class_map) { fld_set_error("fld_net_forward_classmap: null class_map"); return FLD_ERR_INVALID; }
+  return net_forward(net, in, B, workspace, ws_bytes, nullptr, class_map, stream);
 }
 
 extern "C" int fld_net_set_profiling(fld_net* net, int enable) {

@@ -39,6 +39,9 @@ struct TmaConvParams {
   int tiles_x, tiles_y, tiles_b, total_tiles;
   int stages;
   int act, pool;
+  int d2s_fuse;        // 0: write logits; 1: fused softmax over the Cout channels (probabilities); 2: fused argmax -> int64 class map
+  int d2s, d2s_cpp;    // depth-to-space mode (transposed conv as stride^2 phase convs): stride, padded channels per phase;
+                       // N tile = BN / d2s_cpp phases, output pixel (d2s*oy + a, d2s*ox + b) of a [B, d2s*OH, d2s*OW, Cout] fp32 map
   unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
   int dbg;             // FLD_TC_DBG bisect switches (results are garbage when set): 1 skip epilogue math/stores,
                        // 2 skip TMEM loads too, 4 skip the A-operand TMA, 8 skip the B-operand TMA, 16 skip the MMAs
@@ -201,6 +204,68 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       if (tr) TRACE(2, ti, 1);
       tc_fence_after();
+      if (OUT_F32 && p.d2s && p.d2s_fuse) {
+        // Fused decode (reference networks/utils.py:28-30 softmax / prediction.py:209 argmax): this warp takes phase
+        // `half` of the N tile, so each thread holds ALL Cout logits of one output pixel (<= 3 chunks of 32 columns).
+        const int nch = p.d2s_cpp >> 5;
+        uint32_t rg[3][32];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < nch) tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 256 + half * p.d2s_cpp + k * 32, rg[k]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator drained into registers: MMAs of the next tile may start
+        const int phase = nt * 2 + half;
+        const int a = phase / p.d2s, bq = phase - a * p.d2s;
+        const size_t opix = ((size_t)b * (p.OH * p.d2s) + (size_t)oy * p.d2s + a) * (size_t)(p.OW * p.d2s) + (size_t)ox * p.d2s + bq;
+        float mx = -INFINITY;
+        int amax = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k < nch && k * 32 + j < p.Cout) {
+              const float v = __uint_as_float(rg[k][j]);
+              if (v > mx) { mx = v; amax = k * 32 + j; }   // first maximum wins (numpy argmax)
+            }
+        if (eo.valid) {
+          if (p.d2s_fuse == 2) {
+            reinterpret_cast<long long*>(p.out)[opix] = amax;
+          } else {
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (k < nch && k * 32 + j < p.Cout) {
+                  const float e = expf(__uint_as_float(rg[k][j]) - mx);
+                  rg[k][j] = __float_as_uint(e);
+                  sum += e;
+                }
+            const float inv = 1.0f / sum;
+            float* o = reinterpret_cast<float*>(p.out) + opix * p.Cout;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int c = k * 32 + 4 * q;
+                if (k < nch && c + 4 <= p.Cout && (p.Cout & 3) == 0) {
+                  *reinterpret_cast<float4*>(o + c) = make_float4(__uint_as_float(rg[k][4 * q]) * inv, __uint_as_float(rg[k][4 * q + 1]) * inv,
+                                                                  __uint_as_float(rg[k][4 * q + 2]) * inv, __uint_as_float(rg[k][4 * q + 3]) * inv);
+                } else if (k < nch) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (c + e < p.Cout) o[c + e] = __uint_as_float(rg[k][4 * q + e]) * inv;
+                }
+              }
+          }
+        }
+        if (tr) TRACE(2, ti, 2);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       for (int ch = half * 32; ch < p.BN; ch += 64) {
         if (p.dbg & 2) break;
         uint32_t regs[32];
@@ -208,6 +273,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
         if (p.dbg & 1) { if ((regs[0] ^ regs[31]) == 0x7fc12345u) eo.valid = false; continue; }
         EpiOut e2 = eo;
+        if (OUT_F32 && p.d2s) {
+          // phase (a, bq) of the transposed conv owns columns [pl*d2s_cpp, (pl+1)*d2s_cpp) of this N tile
+          const int pl = ch / p.d2s_cpp, cb = ch - pl * p.d2s_cpp;
+          const int phase = nt * (p.BN / p.d2s_cpp) + pl;
+          const int a = phase / p.d2s, bq = phase - a * p.d2s;
+          const size_t opix = ((size_t)b * (p.OH * p.d2s) + (size_t)oy * p.d2s + a) * (size_t)(p.OW * p.d2s) + (size_t)ox * p.d2s + bq;
+          e2.c_left = p.Cout - cb;
+          e2.ptr = reinterpret_cast<float*>(p.out) + opix * p.Cout + cb;
+          epilogue_chunk<false, true, false>(regs, p.bias, p.act, lane, p.TW, e2);
+          continue;
+        }
         e2.c_left = p.Cout - n0 - ch;
         if (OUT_F32) e2.ptr = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0 + ch;
         else e2.ptr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0 + ch;
@@ -249,7 +325,7 @@ bool tc_conv_supported(const ConvGeom& g) {
 }
 
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcConvPlan** out) {
+                        TcConvPlan** out, int d2s, int d2s_cpp, int d2s_fuse) {
   if (!h->encode_tiled) { fld_set_error("cuTensorMapEncodeTiled entry point not available"); return FLD_ERR_CUDA; }
   EncodeTiledFn enc = (EncodeTiledFn)h->encode_tiled;
   TcConvPlan* pl = new TcConvPlan();
@@ -260,6 +336,7 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.act = g.act; p.pool = g.pool;
   { const char* e = getenv("FLD_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.trace = nullptr;
+  p.d2s = d2s; p.d2s_cpp = d2s_cpp; p.d2s_fuse = d2s_fuse;
   // M-tile geometry: TW*TH*NB = 128 pixels, TW in {4, 8}: the pool partners are lane^1 and lane^TW
   const int TW = g.OW > 4 ? 8 : 4;
   int TH = 2;
@@ -267,9 +344,13 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   const int NB = 128 / (TW * TH);
   p.TW = TW; p.TH = TH; p.NB = NB;
   // N tile
-  const int BN = cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128);
+  const int BN = d2s ? (d2s_cpp <= 128 && (cout_pad / d2s_cpp) % 2 == 0 ? 2 * d2s_cpp : d2s_cpp)
+                     : (cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128));
   if (cout_pad % BN != 0 || BN % 16 != 0) { delete pl; fld_set_error("tc_conv: bad cout_pad %d", cout_pad); return FLD_ERR_INVALID; }
   p.BN = BN; p.cout_pad = cout_pad; p.n_ntiles = cout_pad / BN;
+  if (d2s_fuse && (BN != 2 * d2s_cpp || d2s_cpp > 96 || d2s_cpp % 32 != 0)) {
+    delete pl; fld_set_error("tc_conv: fused decode needs two phases of <= 96 channels per N tile"); return FLD_ERR_INVALID;
+  }
   p.tiles_x = fld_div_up(g.OW, TW); p.tiles_y = fld_div_up(g.OH, TH); p.tiles_b = fld_div_up(B, NB);
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_ntiles;
   const size_t stage_bytes = 128 * 128 + (size_t)BN * 128;

@@ -271,6 +271,31 @@ class Model:
             return out, ws, al
         return out
 
+    def forward_classmap_device(self, x, dtype=None):
+        """Segmentation models: forward + per-pixel argmax over classes (reference prediction.py:208-209) in one call ->
+        int64 CUDA [B, oh, ow].  In bfloat16 mode fcn_8's argmax runs inside the last transposed conv's epilogue, so neither
+        logits nor probabilities are written to HBM."""
+        assert self.kind == "segmentation"
+        lib = N.load_library()
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != self.graph.input_shape:
+            raise ValueError("input shape %s != model input %s" % (tuple(x.shape[1:]), self.graph.input_shape))
+        dev = x.device.index
+        with torch.cuda.device(dev):
+            net = self.compiled(dev, dtype)
+            comp = self._compute_code(dtype)
+            need = lib.fld_net_workspace_bytes(net, B)
+            ws = self._ws.get((dev, comp))
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+                self._ws[(dev, comp)] = ws
+            base = ws.data_ptr()
+            al = (-base) % 1024
+            cmap = torch.empty((B, self.output_height, self.output_width), dtype=torch.int64, device=x.device)
+            N.check(lib.fld_net_forward_classmap(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(cmap), N.stream_ptr(dev)))
+        return cmap
+
     def intermediate(self, x, tensor, dtype=None):
         """Run forward and return intermediate tensor `tensor` ([B,h,w,c] float32 CUDA) — parity checks of the levels."""
         out, ws, al = self.forward_device(x, dtype, return_workspace=True)

@@ -313,8 +313,7 @@ def _prediction(
     if hasattr(model, "forward_device"):
         x = get_image_array(inp, input_width, input_height, ordering=IMAGE_ORDERING, as_tensor=True)
         with torch.cuda.device(dev):
-            probs = model.forward_device(x[None].contiguous())
-            pr = class_map_device(probs, output_height, output_width)[0].cpu().numpy()
+            pr = model.forward_classmap_device(x[None].contiguous())[0].cpu().numpy()
     else:  # foreign model object with a Keras-style predict()
         x = get_image_array(inp, input_width, input_height, ordering=IMAGE_ORDERING)
         pr = model.predict(np.array([x]))[0]

@@ -130,6 +130,12 @@ FLD_API int64_t fld_net_tensor_offset(const fld_net* net, int tensor, int B);
  * bf16 in FLD_BF16 mode), may be NULL when only the workspace copy is wanted. */
 FLD_API int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream);
 
+/* Forward of a segmentation graph followed by prediction.py:209 (argmax over classes, first max wins): class_map int64
+ * [B, oh, ow].  In FLD_BF16 mode, when the graph ends in Conv2DTranspose(k = 2*stride) + softmax (fcn_8), the argmax runs
+ * in the transposed conv's epilogue and neither logits nor probabilities are written to HBM. */
+FLD_API int fld_net_forward_classmap(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int64_t* class_map,
+                                     fld_stream stream);
+
 /* Per-layer device timing (bench.py's live roofline measurement): when enabled, fld_net_forward brackets
  * every layer with CUDA events on the launching stream; fld_net_layer_times waits for the last profiled
  * forward and writes one duration (ms) per layer, returning the layer count. */

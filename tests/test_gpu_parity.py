@@ -335,6 +335,28 @@ def test_fcn8_bf16(dev):
     assert (probs.reshape(2, 72, 104, 68).argmax(-1) == ref).mean() > 0.97
 
 
+def test_fcn8_fused_classmap(dev):
+    """fld_net_forward_classmap: argmax fused into the tensor-core up8 epilogue (bf16) / classmap kernel (fp32) must equal
+    argmax over the same mode's materialised probabilities, and agree with the oracle."""
+    from keypoints_detector import prediction
+    from keypoints_detector.networks.fcn import fcn_8
+    from keypoints_detector.data.generator import get_image_array
+    from oracle import cnn as o_cnn
+    m = fcn_8(68, input_height=64, input_width=96).init_weights(5)
+    imgs = [gi.image(90 + i, 120, 160) for i in range(3)]
+    x = np.stack([get_image_array(im, 96, 64, ordering="channels_last") for im in imgs])
+    ref = o_cnn.fcn_forward(x.astype(np.float64), m.weights, "fcn_8", torch.float64).reshape(3, 72, 104, 68).argmax(-1)
+    for dtype, rate in (("float32", 0.999), ("bfloat16", 0.97)):
+        xt = T(x, dev)
+        cm = m.forward_classmap_device(xt, dtype)
+        assert cm.dtype == torch.int64 and tuple(cm.shape) == (3, 72, 104)
+        probs = m.forward_device(xt, dtype)
+        same_mode = prediction.class_map_device(probs, 72, 104)
+        assert (cm == same_mode).float().mean().item() > 0.9995          # identical up to exact ties in rounded probabilities
+        np.testing.assert_allclose(probs.sum(-1).cpu().numpy(), 1.0, atol=1e-4)
+        assert (cm.cpu().numpy() == ref).mean() > rate
+
+
 def test_prediction_dropin_fcn(dev, tmp_path):
     """keypts_predict / _prediction / model_from_checkpoint_path round trip (reference prediction.py:116-222)."""
     from keypoints_detector import prediction
