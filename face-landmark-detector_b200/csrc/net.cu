@@ -108,6 +108,14 @@ int infer_shapes(fld_net* net) {
         FLD_REQUIRE(d.kh > 0 && d.stride > 0, "layer %d: bad pool parameters", i);
         o.h = (a.h - d.kh) / d.stride + 1; o.w = (a.w - d.kh) / d.stride + 1; o.c = a.c;
         break;
+      case FLD_OP_DWCONV:
+        FLD_REQUIRE(d.kh > 0 && d.kw > 0 && d.stride > 0, "layer %d: bad depthwise conv parameters", i);
+        FLD_REQUIRE(d.cout == 0 || d.cout == a.c, "layer %d: depthwise conv keeps the channel count (%d), got cout=%d", i, a.c, d.cout);
+        L.d.cout = a.c;  // depth_multiplier 1 (mobilenet.py:37)
+        o.h = (a.h + d.pad_t + d.pad_b - d.kh) / d.stride + 1; o.w = (a.w + d.pad_l + d.pad_r - d.kw) / d.stride + 1; o.c = a.c;
+        FLD_REQUIRE(o.h > 0 && o.w > 0, "layer %d: depthwise conv output is empty", i);
+        L.needs_weights = true;
+        break;
       default:
         fld_set_error("layer %d: op %d not implemented", i, d.op);
         return FLD_ERR_INVALID;
@@ -121,9 +129,10 @@ int infer_shapes(fld_net* net) {
     f32_needed.back() = 1;  // final tensor is handed out as fp32
     for (int i = 0; i < nL; ++i) {
       const fld_layer_desc& d = net->layers[i].d;
-      if (d.op == FLD_OP_ADD) { f32_needed[d.in0] = 1; f32_needed[d.in1] = 1; }
+      // FCN skip adds work on fp32 logits; residual adds (add -> ReLU, resnet50.py:68-69) take the trunk's bf16 tensors
+      if (d.op == FLD_OP_ADD && d.act == FLD_ACT_NONE) { f32_needed[d.in0] = 1; f32_needed[d.in1] = 1; }
       // logits feeding transposed convs / softmax stay fp32 (they are tiny; bf16 there only costs accuracy)
-      if (d.op == FLD_OP_SOFTMAX || d.op == FLD_OP_MAXPOOL || d.op == FLD_OP_DECONV) f32_needed[d.in0] = 1;
+      if (d.op == FLD_OP_SOFTMAX || d.op == FLD_OP_DECONV) f32_needed[d.in0] = 1;
     }
     for (int i = 0; i < nL; ++i) {
       LayerRt& L = net->layers[i];
@@ -136,8 +145,9 @@ int infer_shapes(fld_net* net) {
         L.dc_cpad = (int)align_up(a.c, 64);
         L.dc_cpp = (int)align_up(L.d.cout, 32);
       }
-      if (L.d.op != FLD_OP_CONV) { o.dtype = FLD_F32; continue; }
       const bool want_f32 = f32_needed[i + 1] != 0;
+      if (L.d.op == FLD_OP_DWCONV || L.d.op == FLD_OP_MAXPOOL || L.d.op == FLD_OP_ADD) { o.dtype = want_f32 ? FLD_F32 : FLD_BF16; continue; }
+      if (L.d.op != FLD_OP_CONV) { o.dtype = FLD_F32; continue; }
       const bool in_ok_first = (a.dtype == FLD_U8 || a.dtype == FLD_F32) && tc_conv_first_supported(L.g);
       const bool in_ok_tma = (a.dtype == FLD_BF16) && tc_conv_supported(L.g);
       if (in_ok_first && !want_f32) { L.path = PATH_TC_FIRST; o.dtype = FLD_BF16; }
@@ -260,6 +270,12 @@ extern "C" int fld_net_set_weights(fld_net* net, int layer, const float* kernel_
           for (int c = 0; c < Cin; ++c)
             L.w_host[((size_t)t * Cin + c) * Cout + o] = kernel_h[((size_t)t * Cout + o) * Cin + c];
     }
+  } else if (d.op == FLD_OP_DWCONV) {
+    // Keras depthwise kernel [kh][kw][C][1] -> [tap][C], BN scale folded per channel
+    const size_t T = (size_t)d.kh * d.kw;
+    L.w_host.resize(T * Cout);
+    for (size_t t = 0; t < T; ++t)
+      for (int o = 0; o < Cout; ++o) L.w_host[t * Cout + o] = (float)((double)kernel_h[t * Cout + o] * scale[o]);
   } else if (d.op == FLD_OP_DENSE) {
     const size_t In = a.elems();
     L.w_host.resize(In * Cout);
@@ -455,8 +471,10 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         break;
       case FLD_OP_ADD: {
         const TensorInfo& b2 = net->tensors[d.in1];
-        FLD_REQUIRE(a.dtype == FLD_F32 && b2.dtype == FLD_F32, "layer %zu: ADD inputs must be fp32", i);
-        rc = simt_add_crop((const float*)pin, a.h, a.w, (const float*)ptr[d.in1], b2.h, b2.w, (float*)pout, B, o.h, o.w, o.c, st);
+        if (a.dtype == FLD_F32 && b2.dtype == FLD_F32 && o.dtype == FLD_F32 && d.act == FLD_ACT_NONE)
+          rc = simt_add_crop((const float*)pin, a.h, a.w, (const float*)ptr[d.in1], b2.h, b2.w, (float*)pout, B, o.h, o.w, o.c, st);
+        else
+          rc = simt_add_act(pin, a.dtype, a.h, a.w, ptr[d.in1], b2.dtype, b2.h, b2.w, pout, o.dtype, B, o.h, o.w, o.c, d.act, st);
         break;
       }
       case FLD_OP_DENSE:
@@ -469,8 +487,12 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         rc = simt_softmax((const float*)pin, (float*)pout, (long long)B * a.h * a.w, a.c, st);
         break;
       case FLD_OP_MAXPOOL:
-        FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: MAXPOOL input must be fp32", i);
-        rc = simt_maxpool((const float*)pin, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, d.kh, d.stride, st);
+        if (a.dtype == FLD_F32 && o.dtype == FLD_F32) rc = simt_maxpool((const float*)pin, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, d.kh, d.stride, st);
+        else rc = simt_maxpool2d(pin, a.dtype, pout, o.dtype, B, a.h, a.w, a.c, o.h, o.w, d.kh, d.stride, st);
+        break;
+      case FLD_OP_DWCONV:
+        rc = simt_dwconv(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, pout, o.dtype, B, a.h, a.w, a.c, o.h, o.w, d.kh, d.kw,
+                         d.stride, d.pad_t, d.pad_l, d.act, st);
         break;
       default:
         fld_set_error("layer %zu: op %d not implemented", i, d.op);

@@ -52,3 +52,11 @@ int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
                         TcHaloPlan** out);
 void tc_halo_plan_destroy(TcHaloPlan* p);
 int tc_halo_run(const TcHaloPlan* p, const float* bias, void* out, cudaStream_t st);
+
+// ---- encoder extras (simt_extra.cu): depthwise conv, k/s max-pool, add(+act); f32 or bf16 NHWC on either side
+int simt_dwconv(const void* in, int in_dtype, const float* w /*[kh*kw][C]*/, const float* bias, void* out, int out_dtype, int B, int IH,
+                int IW, int C, int OH, int OW, int kh, int kw, int stride, int pad_t, int pad_l, int act, cudaStream_t st);
+int simt_maxpool2d(const void* in, int in_dtype, void* out, int out_dtype, int B, int IH, int IW, int C, int OH, int OW, int k, int s,
+                   cudaStream_t st);
+int simt_add_act(const void* a, int a_dtype, int AH, int AW, const void* b, int b_dtype, int BH, int BW, void* out, int out_dtype, int B,
+                 int OH, int OW, int C, int act, cudaStream_t st);

@@ -5,7 +5,8 @@ kernel size :32, Reshape/transpose-conv size mismatch :45-50) and lacks the attr
 (SURVEY App. A end); the key is kept and mapped to fcn_8 over the vanilla encoder.  'landmark_regressor' and
 'fcn_8_vanilla' / 'fcn_32_vanilla' are additions.
 """
-from .fcn import fcn_8, fcn_32, fcn_8_resnet50, fcn_8_mobilenet, fcn_8_vgg, fcn_8_vanilla, vanilla_encoder
+from .fcn import (fcn_8, fcn_32, fcn_8_resnet50, fcn_8_mobilenet, fcn_8_vgg, fcn_8_vanilla, fcn_32_vgg, fcn_32_resnet50,
+                  fcn_32_mobilenet, vanilla_encoder)
 from .regression import landmark_regressor
 
 
@@ -29,4 +30,7 @@ LANDMARKS_MODELS = {
     # additions of this build
     'fcn_8_vanilla': fcn_8_vanilla,
     'fcn_32_vanilla': fcn_32_vanilla,
+    'fcn_32_vgg': fcn_32_vgg,
+    'fcn_32_resnet50': fcn_32_resnet50,
+    'fcn_32_mobilenet': fcn_32_mobilenet,
 }

@@ -30,6 +30,19 @@ def canonical_face68():
     return pts
 
 
+def _bn_stats(rng, w, bn, c, nontrivial_bn):
+    if nontrivial_bn:
+        w[bn + "/gamma"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+        w[bn + "/beta"] = rng.normal(0, 0.1, c).astype(np.float32)
+        w[bn + "/moving_mean"] = rng.normal(0, 0.1, c).astype(np.float32)
+        w[bn + "/moving_variance"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    else:  # fresh Keras BN: gamma 1, beta 0, mean 0, var 1  (y = x / sqrt(1.001), not identity)
+        w[bn + "/gamma"] = np.ones(c, np.float32)
+        w[bn + "/beta"] = np.zeros(c, np.float32)
+        w[bn + "/moving_mean"] = np.zeros(c, np.float32)
+        w[bn + "/moving_variance"] = np.ones(c, np.float32)
+
+
 def random_weights(model, seed=0, nontrivial_bn=True):
     rng = np.random.default_rng(seed)
     g = model.graph
@@ -45,23 +58,24 @@ def random_weights(model, seed=0, nontrivial_bn=True):
             else:
                 lim = np.sqrt(6.0 / (fan_in + fan_out))
                 k = rng.uniform(-lim, lim, (kh, kw, cin, cout))                             # glorot_uniform
-                if L["act"] == N.ACT_RELU:
+                if L["act"] != N.ACT_NONE:
                     k *= 1.6  # keep activation scale roughly constant through the ReLU/pool stages
             w[n + "/kernel"] = k.astype(np.float32)
             if L["has_bias"]:
                 w[n + "/bias"] = rng.normal(0, 0.05, cout).astype(np.float32)
             if L["has_bn"]:
-                bn = L["bn_name"]
-                if nontrivial_bn:
-                    w[bn + "/gamma"] = rng.uniform(0.5, 1.5, cout).astype(np.float32)
-                    w[bn + "/beta"] = rng.normal(0, 0.1, cout).astype(np.float32)
-                    w[bn + "/moving_mean"] = rng.normal(0, 0.1, cout).astype(np.float32)
-                    w[bn + "/moving_variance"] = rng.uniform(0.5, 1.5, cout).astype(np.float32)
-                else:  # fresh Keras BN: gamma 1, beta 0, mean 0, var 1  (y = x / sqrt(1.001), not identity)
-                    w[bn + "/gamma"] = np.ones(cout, np.float32)
-                    w[bn + "/beta"] = np.zeros(cout, np.float32)
-                    w[bn + "/moving_mean"] = np.zeros(cout, np.float32)
-                    w[bn + "/moving_variance"] = np.ones(cout, np.float32)
+                _bn_stats(rng, w, L["bn_name"], cout, nontrivial_bn)
+        elif L["op"] == N.OP_DWCONV:
+            kh, kw = L["kh"], L["kw"]
+            lim = np.sqrt(6.0 / (2 * kh * kw))
+            k = rng.uniform(-lim, lim, (kh, kw, cin, 1))
+            if L["act"] != N.ACT_NONE:
+                k *= 1.6
+            w[n + "/depthwise_kernel"] = k.astype(np.float32)
+            if L["has_bias"]:
+                w[n + "/bias"] = rng.normal(0, 0.05, cin).astype(np.float32)
+            if L["has_bn"]:
+                _bn_stats(rng, w, L["bn_name"], cin, nontrivial_bn)
         elif L["op"] == N.OP_DECONV:
             k, cout = L["kh"], L["cout"]
             lim = np.sqrt(6.0 / (k * k * cin + k * k * cout))

@@ -52,12 +52,29 @@ class Graph:
         return self._add(name=name, op=N.OP_DECONV, in0=x, in1=-1, kh=k, kw=k, stride=stride, pad=(0, 0, 0, 0), cout=cout,
                          act=0, pool=0, has_bias=False, has_bn=False, in_scale=1.0)
 
-    def add(self, a, b, name):
+    def add(self, a, b, name, act=N.ACT_NONE):
+        """crop-to-smaller + Add (fcn.py:55-86); act=ACT_RELU is the residual add -> ReLU of resnet50.py:68-69."""
         ha, wa, c = self.shapes[a]
         hb, wb, _ = self.shapes[b]
         self.shapes.append((min(ha, hb), min(wa, wb), c))
-        return self._add(name=name, op=N.OP_ADD, in0=a, in1=b, kh=0, kw=0, stride=1, pad=(0, 0, 0, 0), cout=c, act=0, pool=0,
+        return self._add(name=name, op=N.OP_ADD, in0=a, in1=b, kh=0, kw=0, stride=1, pad=(0, 0, 0, 0), cout=c, act=act, pool=0,
                          has_bias=False, has_bn=False, in_scale=1.0)
+
+    def dwconv(self, x, name, k=3, pad=(1, 1, 1, 1), stride=1, act=N.ACT_NONE, bias=False, bn=True, bn_name=None):
+        """ZeroPadding2D + DepthwiseConv2D(depth_multiplier=1) [+BN folded] [+ReLU6] (mobilenet.py:37-47)."""
+        h, w, c = self.shapes[x]
+        oh = (h + pad[0] + pad[1] - k) // stride + 1
+        ow = (w + pad[2] + pad[3] - k) // stride + 1
+        self.shapes.append((oh, ow, c))
+        return self._add(name=name, op=N.OP_DWCONV, in0=x, in1=-1, kh=k, kw=k, stride=stride, pad=tuple(pad), cout=c, act=act,
+                         pool=0, has_bias=bias, has_bn=bn, in_scale=1.0, bn_name=bn_name or name + "_bn")
+
+    def maxpool(self, x, name, k, stride):
+        """MaxPooling2D((k,k), strides) padding='valid' (resnet50.py:149)."""
+        h, w, c = self.shapes[x]
+        self.shapes.append(((h - k) // stride + 1, (w - k) // stride + 1, c))
+        return self._add(name=name, op=N.OP_MAXPOOL, in0=x, in1=-1, kh=k, kw=k, stride=stride, pad=(0, 0, 0, 0), cout=c, act=0,
+                         pool=0, has_bias=False, has_bn=False, in_scale=1.0)
 
     def dense(self, x, name, units, act=N.ACT_NONE):
         self.shapes.append((1, 1, units))
@@ -84,6 +101,13 @@ def weight_specs(graph):
                 bn = L["bn_name"]
                 for s in ("gamma", "beta", "moving_mean", "moving_variance"):
                     specs[bn + "/" + s] = (L["cout"],)
+        elif L["op"] == N.OP_DWCONV:
+            specs[n + "/depthwise_kernel"] = (L["kh"], L["kw"], cin, 1)
+            if L["has_bias"]:
+                specs[n + "/bias"] = (cin,)
+            if L["has_bn"]:
+                for s in ("gamma", "beta", "moving_mean", "moving_variance"):
+                    specs[L["bn_name"] + "/" + s] = (cin,)
         elif L["op"] == N.OP_DECONV:
             specs[n + "/kernel"] = (L["kh"], L["kw"], L["cout"], cin)
         elif L["op"] == N.OP_DENSE:
@@ -207,9 +231,9 @@ class Model:
                                        comp, ctypes.byref(net)))
             for i, L in enumerate(g.layers):
                 n = L["name"]
-                if L["op"] not in (N.OP_CONV, N.OP_DECONV, N.OP_DENSE):
+                if L["op"] not in (N.OP_CONV, N.OP_DECONV, N.OP_DENSE, N.OP_DWCONV):
                     continue
-                k = self.weights[n + "/kernel"]
+                k = self.weights[n + ("/depthwise_kernel" if L["op"] == N.OP_DWCONV else "/kernel")]
                 b = self.weights.get(n + "/bias") if L["has_bias"] else None
                 bn = None
                 if L["has_bn"]:

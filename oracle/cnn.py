@@ -218,3 +218,74 @@ def softmax_np(logits_nhwc):
     z = z - z.max(axis=-1, keepdims=True)
     e = np.exp(z)
     return e / e.sum(axis=-1, keepdims=True)
+
+
+# ----------------------------------------------------------------------------- MobileNet-v1 / ResNet50 encoders
+def relu6_t(x):
+    """mobilenet.py:12-13: K.relu(x, max_value=6)."""
+    return torch.clamp(x, 0.0, 6.0)
+
+
+def mobilenet_encoder_t(x, w):
+    """mobilenet.py:59-104 (alpha = 1, depth_multiplier = 1).  x NCHW.  Layer names as in the reference:
+    conv1 / conv1_bn, conv_dw_%d / conv_dw_%d_bn, conv_pw_%d / conv_pw_%d_bn.  Returns [f1..f5]."""
+    # _conv_block (:16-28): ZeroPadding2D((1,1)) (symmetric!) -> Conv 3x3 valid stride 2 no-bias -> BN -> relu6
+    x = conv2d_t(x, w["conv1/kernel"], None, stride=2, pad=(1, 1, 1, 1))
+    x = relu6_t(bn_t(x, w, "conv1_bn"))
+    cfg = [(64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1), (512, 1), (512, 1), (512, 1), (512, 1),
+           (1024, 2), (1024, 1)]
+    levels = []
+    for i, (f, s) in enumerate(cfg, start=1):
+        # _depthwise_conv_block (:31-56): ZeroPad(1,1) -> DepthwiseConv 3x3 valid stride s no-bias -> BN -> relu6
+        #                                 -> Conv 1x1 same no-bias -> BN -> relu6
+        k = w["conv_dw_%d/depthwise_kernel" % i]                     # [3,3,C,1]
+        C = k.shape[2]
+        wt = k.permute(2, 3, 0, 1).contiguous()              # [C,1,3,3]
+        x = F.conv2d(F.pad(x, (1, 1, 1, 1)), wt, None, stride=s, groups=C)
+        x = relu6_t(bn_t(x, w, "conv_dw_%d_bn" % i))
+        x = conv2d_t(x, w["conv_pw_%d/kernel" % i], None)
+        x = relu6_t(bn_t(x, w, "conv_pw_%d_bn" % i))
+        if i in (1, 3, 5, 11, 13):
+            levels.append(x)
+    return levels
+
+
+def _res_block_t(x, w, stage, block, stride, with_shortcut):
+    """resnet50.py:32-119 identity_block / conv_block (all convs have bias; BN after every conv)."""
+    cb = "res%d%s_branch" % (stage, block)
+    bb = "bn%d%s_branch" % (stage, block)
+    y = F.relu(bn_t(conv2d_t(x, w[cb + "2a/kernel"], w[cb + "2a/bias"], stride=stride), w, bb + "2a"))
+    y = F.relu(bn_t(conv2d_t(y, w[cb + "2b/kernel"], w[cb + "2b/bias"], pad=same_pad(3)), w, bb + "2b"))
+    y = bn_t(conv2d_t(y, w[cb + "2c/kernel"], w[cb + "2c/bias"]), w, bb + "2c")
+    sc = x
+    if with_shortcut:
+        sc = bn_t(conv2d_t(x, w[cb + "1/kernel"], w[cb + "1/bias"], stride=stride), w, bb + "1")
+    return F.relu(y + sc)
+
+
+def resnet50_encoder_t(x, w):
+    """resnet50.py:122-173.  Returns [f1 (conv1 output BEFORE BN/ReLU), f2 (one_side_pad), f3, f4, f5]."""
+    x = conv2d_t(x, w["conv1/kernel"], w["conv1/bias"], stride=2, pad=(3, 3, 3, 3))
+    f1 = x
+    x = F.relu(bn_t(x, w, "bn_conv1"))
+    x = F.max_pool2d(x, 3, 2)
+    levels = [f1]
+    for stage, blocks, stride in ((2, "abc", 1), (3, "abcd", 2), (4, "abcdef", 2), (5, "abc", 2)):
+        for bi, b in enumerate(blocks):
+            x = _res_block_t(x, w, stage, b, stride if bi == 0 else 1, bi == 0)
+        if stage == 2:
+            levels.append(F.pad(x, (1, 0, 1, 0)))   # one_side_pad (:23-29): pad 1 all round, drop last row/col = pad top/left
+        else:
+            levels.append(x)
+    return levels
+
+
+def fcn_forward_encoder(x_nhwc, weights, encoder="mobilenet", dtype=torch.float64, return_levels=False):
+    """fcn_8 over the MobileNet / ResNet50 encoder: float NHWC -> probs [B, oh*ow, n]."""
+    w = _prep(weights, dtype)
+    x = _t(x_nhwc, dtype).permute(0, 3, 1, 2)
+    levels = mobilenet_encoder_t(x, w) if encoder == "mobilenet" else resnet50_encoder_t(x, w)
+    probs = segmentation_probs_t(fcn_8_logits_t(levels, w)).numpy()
+    if return_levels:
+        return probs, [l.permute(0, 2, 3, 1).contiguous().numpy() for l in levels]
+    return probs

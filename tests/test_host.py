@@ -170,3 +170,26 @@ dist.destroy_process_group()
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("OK") == 2
+
+
+def test_encoder_graphs_match_oracle_shapes():
+    """Every LANDMARKS_MODELS entry builds (rows a5 / f3); the encoder graphs' level shapes and layer names agree with
+    the oracle restatement of reference networks/mobilenet.py / resnet50.py (the oracle consumes the builder's weights)."""
+    import torch
+    from keypoints_detector.networks import mobilenet, resnet50
+    from keypoints_detector.networks.basic_models import LANDMARKS_MODELS
+    from oracle import cnn as o_cnn
+    for name, build in LANDMARKS_MODELS.items():
+        m = build(5, input_height=32, input_width=64)
+        assert m.n_classes == 5 and m.output_height > 0 and m.weight_specs()
+    x = torch.zeros(1, 3, 32, 64, dtype=torch.float32)
+    for getter, enc_t in ((mobilenet.get_mobilenet_encoder, o_cnn.mobilenet_encoder_t),
+                          (resnet50.get_resnet50_encoder, o_cnn.resnet50_encoder_t)):
+        g, levels = getter(32, 64)
+        from keypoints_detector.networks.model import Model
+        w = o_cnn._prep(Model(g, "segmentation").init_weights(0).weights, torch.float32)
+        ref = enc_t(x, w)
+        for tid, r in list(zip(levels, ref))[2:]:
+            assert g.shapes[tid] == (r.shape[2], r.shape[3], r.shape[1])
+    with pytest.raises(ValueError):
+        mobilenet.get_mobilenet_encoder(pretrained="imagenet")
