@@ -61,13 +61,29 @@ def decode_regress_device(out136, faceboxes, want_uint=True):
     return marks, marks_u
 
 
+_TEMPLATE_CACHE = {}
+
+
+def _template_device(template, device):
+    """fp64 template resident on `device`, uploaded once: a per-call pageable H2D copy would synchronise the stream and
+    serialise the whole pipeline behind it."""
+    tmpl = TEMPLATE_112 if template is None else np.ascontiguousarray(template, dtype=np.float64)
+    key = (device.index, tmpl.shape, tmpl.tobytes())
+    t = _TEMPLATE_CACHE.get(key)
+    if t is None:
+        if len(_TEMPLATE_CACHE) > 64:
+            _TEMPLATE_CACHE.clear()
+        t = torch.from_numpy(np.array(tmpl, dtype=np.float64)).to(device)
+        _TEMPLATE_CACHE[key] = t
+    return t
+
+
 def align_device(frames, face2frame, marks, template=None, out_size=(112, 112), five_point=True, return_matrix=True):
     """Umeyama fit + cv2.warpAffine-exact warp on device.  marks float32 CUDA [B,N,2] in frame pixels."""
     lib = N.load_library()
     F, H, W, C = frames.shape
     B, Np = marks.shape[0], marks.shape[1]
-    tmpl = TEMPLATE_112 if template is None else np.asarray(template, dtype=np.float64)
-    t = torch.from_numpy(np.ascontiguousarray(tmpl, dtype=np.float64)).to(frames.device)
+    t = _template_device(template, frames.device)
     oh, ow = out_size
     crops = torch.empty((B, oh, ow, C), dtype=torch.uint8, device=frames.device)
     M = torch.empty((B, 2, 3), dtype=torch.float64, device=frames.device) if return_matrix else None
