@@ -21,15 +21,15 @@ struct TensorInfo {
 
 enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 
-struct PlanEntry { int B; const void* in; TcConvPlan* plan; int fuse = 0; };
+struct PlanEntry { int B; const void* in; TcConvPlan* plan; int fuse = 0; const void* out = nullptr; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
+struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; };
 
 struct LayerRt {
   fld_layer_desc d;
   ConvGeom g{};
   int path = PATH_SIMT;
   int cout_pad = 0;
-  int dc_cpad = 0, dc_cpp = 0;  // tensor-core transposed conv: padded input channels, padded channels per phase
   bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
   bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
   bool needs_weights = false, has_weights = false;
@@ -40,6 +40,7 @@ struct LayerRt {
   __nv_bfloat16* d_wbf = nullptr;
   std::vector<PlanEntry> plans;
   std::vector<HaloPlanEntry> hplans;
+  std::vector<DeconvPlanEntry> dplans;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -138,12 +139,9 @@ int infer_shapes(fld_net* net) {
       LayerRt& L = net->layers[i];
       TensorInfo& o = net->tensors[i + 1];
       const TensorInfo& a = net->tensors[L.d.in0];
-      if (L.d.op == FLD_OP_DECONV && L.d.kh == 2 * L.d.stride && L.d.stride >= 4 && L.d.stride <= 8 && a.c <= 128 && L.d.cout <= 96 &&
-          a.dtype == FLD_F32 && !getenv("FLD_TC_DECONV_OFF")) {
-        // stride^2 phase convolutions on the tensor cores (tc_conv.cu depth-to-space mode)
-        L.path = PATH_TC_TMA;
-        L.dc_cpad = (int)align_up(a.c, 64);
-        L.dc_cpp = (int)align_up(L.d.cout, 32);
+      if (L.d.op == FLD_OP_DECONV && L.d.kh == L.d.kw && tc_deconv_supported(L.d.kh, L.d.stride, a.c, L.d.cout) && a.dtype == FLD_F32 &&
+          !getenv("FLD_TC_DECONV_OFF")) {
+        L.path = PATH_TC_TMA;  // the stride^2 phase convolutions as one tensor-core GEMM (tc_deconv.cu)
       }
       const bool want_f32 = f32_needed[i + 1] != 0;
       if (L.d.op == FLD_OP_DWCONV || L.d.op == FLD_OP_MAXPOOL || L.d.op == FLD_OP_ADD) { o.dtype = want_f32 ? FLD_F32 : FLD_BF16; continue; }
@@ -162,7 +160,7 @@ int infer_shapes(fld_net* net) {
       if (L.d.op != FLD_OP_DECONV || L.path != PATH_TC_TMA || N2.d.op != FLD_OP_SOFTMAX || N2.d.in0 != i + 1) continue;
       bool other_use = false;
       for (int j = i + 2; j < nL; ++j) other_use |= (net->layers[j].d.in0 == i + 1 || net->layers[j].d.in1 == i + 1);
-      if (other_use || L.dc_cpp > 96 || (L.d.stride * L.d.stride) % 2 != 0 || getenv("FLD_TC_FUSE_OFF")) continue;
+      if (other_use || getenv("FLD_TC_FUSE_OFF")) continue;
       L.dc_fuse_softmax = true;
       N2.skip = true;
     }
@@ -177,6 +175,8 @@ void free_layer(LayerRt& L) {
   for (auto& pe : L.plans) tc_conv_plan_destroy(pe.plan);
   for (auto& pe : L.hplans) tc_halo_plan_destroy(pe.plan);
   L.hplans.clear();
+  for (auto& pe : L.dplans) tc_deconv_plan_destroy(pe.plan);
+  L.dplans.clear();
   L.d_w = nullptr; L.d_bias = nullptr; L.d_wbf = nullptr; L.plans.clear();
 }
 
@@ -312,14 +312,8 @@ extern "C" int fld_net_finalize(fld_net* net) {
       FLD_CUDA(cudaMemcpy(L.d_bias, b.data(), nb * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) {
-      // [tap = u*2+v][phase*cpp + o][cpad]  <-  phase layout [phase][u][v][Cin][Cout] (set_weights)
-      const int st = L.d.stride, Cin = a.c, cp = L.dc_cpad, cpp = L.dc_cpp, nph = st * st;
-      std::vector<uint16_t> pk((size_t)4 * nph * cpp * cp, 0);
-      for (int ph = 0; ph < nph; ++ph)
-        for (int t = 0; t < 4; ++t)
-          for (int c = 0; c < Cin; ++c)
-            for (int o = 0; o < Cout; ++o)
-              pk[(((size_t)t * nph + ph) * cpp + o) * cp + c] = f2bf(L.w_host[(((size_t)ph * 4 + t) * Cin + c) * Cout + o]);
+      std::vector<uint16_t> pk;
+      tc_deconv_pack_weights(L.w_host.data(), L.d.stride, a.c, Cout, f2bf, pk);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_SIMT) {
@@ -353,7 +347,7 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     const LayerRt& L = net->layers[i];
     const TensorInfo& a = net->tensors[L.d.in0];
     if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
-    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) m = std::max(m, (size_t)B * a.h * a.w * L.dc_cpad * 2);
+    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) m = std::max(m, tc_deconv_scratch_bytes(B, a.h, a.w, a.c));
   }
   return m;
 }
@@ -407,6 +401,9 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
     }
     dense_scratch = (float*)((char*)workspace + off);
   }
+  // the final tensor is produced straight into the caller's buffer (no device-to-device copy of the probabilities)
+  const bool direct_out = out && net->tensors[nT - 1].dtype == FLD_F32;
+  if (direct_out) ptr[nT - 1] = out;
   static const bool debug_sync = getenv("FLD_DEBUG_SYNC") != nullptr;
   if (net->profiling) FLD_CUDA(cudaEventRecord(net->events[0], st));
   for (size_t i = 0; i < net->layers.size(); ++i) {
@@ -446,26 +443,20 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         break;
       case FLD_OP_DECONV:
         if (L.path == PATH_TC_TMA) {
-          rc = simt_pad_cvt_bf16((const float*)pin, dense_scratch, (long long)B * a.h * a.w, a.c, L.dc_cpad, st);
-          if (rc) return rc;
           // fused decode: 1 = softmax written into the (skipped) SOFTMAX layer's tensor, 2 = int64 class map to the caller
           const bool last_pair = L.dc_fuse_softmax && (int)i + 2 == (int)net->layers.size();
-          const int fuse = L.dc_fuse_softmax ? ((cmap_out && last_pair) ? 2 : 1) : 0;
-          void* dst = fuse == 2 ? (void*)cmap_out : (fuse == 1 ? ptr[i + 2] : pout);
-          TcConvPlan* plan = nullptr;
-          for (auto& pe : L.plans) if (pe.B == B && pe.in == (const void*)dense_scratch && pe.fuse == fuse) { plan = pe.plan; break; }
+          const int mode = L.dc_fuse_softmax ? ((cmap_out && last_pair) ? 2 : 1) : 0;
+          void* dst = mode == 2 ? (void*)cmap_out : (mode == 1 ? ptr[i + 2] : pout);
+          TcDeconvPlan* plan = nullptr;
+          for (auto& pe : L.dplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
           if (!plan) {
-            ConvGeom g{};
-            g.IH = a.h; g.IW = a.w; g.Cin = L.dc_cpad; g.OH = a.h + 1; g.OW = a.w + 1; g.Cout = d.cout;
-            g.kh = 2; g.kw = 2; g.stride = 1; g.pad_t = 1; g.pad_l = 1; g.act = FLD_ACT_NONE; g.pool = 0;
-            rc = tc_conv_plan_create(net->h, dense_scratch, L.d_wbf, d.stride * d.stride * L.dc_cpp, g, B, &plan, d.stride, L.dc_cpp, fuse);
+            rc = tc_deconv_plan_create(net->h, dense_scratch, L.d_wbf, B, a.h, a.w, a.c, d.cout, d.stride, &plan);
             if (rc) return rc;
-            if (L.plans.size() >= 8) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
-            PlanEntry pe; pe.B = B; pe.in = (const void*)dense_scratch; pe.plan = plan; pe.fuse = fuse;
-            L.plans.push_back(pe);
+            if (L.dplans.size() >= 8) { tc_deconv_plan_destroy(L.dplans.front().plan); L.dplans.erase(L.dplans.begin()); }
+            L.dplans.push_back({B, (const void*)dense_scratch, plan});
           }
-          rc = tc_conv_run(plan, L.d_bias, dst, FLD_F32, st);
-          if (fuse == 2) cmap_done = true;
+          rc = tc_deconv_run(plan, (const float*)pin, dst, mode, st);
+          if (mode == 2) cmap_done = true;
         } else if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
         else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
@@ -516,7 +507,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
     rc = fld_decode_classmap(net->h, (const float*)ptr[nT - 1], B, o.h * o.w, o.c, cmap_out, stream);
     if (rc) return rc;
   }
-  if (out) {
+  if (out && !direct_out) {
     const TensorInfo& o = net->tensors[nT - 1];
     const size_t n = o.elems() * (size_t)B;
     if (o.dtype == FLD_F32) FLD_CUDA(cudaMemcpyAsync(out, ptr[nT - 1], n * 4, cudaMemcpyDeviceToDevice, st));

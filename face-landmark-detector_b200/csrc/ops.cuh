@@ -1,6 +1,7 @@
 // ops.cuh — internal layer-op entry points shared by net.cu / simt_ops.cu / tc_conv.cu
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 struct ConvGeom {
   int IH, IW, Cin;      // input (un-padded)
@@ -40,7 +41,7 @@ void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_ho
 bool tc_conv_supported(const ConvGeom& g);
 // d2s > 0: transposed-conv phase mode (see tc_conv.cu): cout_pad = stride^2 * d2s_cpp rows per tap, fp32 depth-to-space output
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcConvPlan** out, int d2s = 0, int d2s_cpp = 0, int d2s_fuse = 0);
+                        TcConvPlan** out, int d2s = 0, int d2s_cpp = 0, int d2s_fuse = 0, void* d2s_out = nullptr);
 int simt_pad_cvt_bf16(const float* in, void* out_bf16, long long n_px, int C, int Cpad, cudaStream_t st);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype, cudaStream_t st);
@@ -60,3 +61,17 @@ int simt_maxpool2d(const void* in, int in_dtype, void* out, int out_dtype, int B
                    cudaStream_t st);
 int simt_add_act(const void* a, int a_dtype, int AH, int AW, const void* b, int b_dtype, int BH, int BW, void* out, int out_dtype, int B,
                  int OH, int OW, int C, int act, cudaStream_t st);
+
+// ---- transposed conv (k = 2*stride) as one flat GEMM on the tensor cores with fused softmax / argmax (tc_deconv.cu)
+struct TcDeconvPlan;
+bool tc_deconv_supported(int k, int s, int Cin, int Cout);
+int tc_deconv_kp(int Cin);    // packed K: 4 taps x Cin, padded to 64
+int tc_deconv_cpp(int Cout);  // channels per phase, padded to 8
+size_t tc_deconv_scratch_bytes(int B, int IH, int IW, int Cin);  // bf16 im2col matrix
+void tc_deconv_pack_weights(const float* w_phase /*[s*s][2][2][Cin][Cout]*/, int s, int Cin, int Cout, uint16_t (*f2bf)(float),
+                            std::vector<uint16_t>& out /*[s*s*cpp][Kp]*/);
+int tc_deconv_plan_create(const fld_handle* h, void* scratch, const __nv_bfloat16* w_packed, int B, int IH, int IW, int Cin, int Cout,
+                          int s, TcDeconvPlan** out);
+void tc_deconv_plan_destroy(TcDeconvPlan* p);
+// mode 0: fp32 logits, 1: softmax probabilities, 2: int64 argmax class map
+int tc_deconv_run(const TcDeconvPlan* p, const float* in, void* out, int mode, cudaStream_t st);

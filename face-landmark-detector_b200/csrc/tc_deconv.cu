@@ -1,0 +1,449 @@
+// tc_deconv.cu — Conv2DTranspose(k = 2*stride, 'valid', no bias) on the tcgen05 tensor cores, with the per-pixel decode
+// of the segmentation head fused into the epilogue.
+//
+//   reference: networks/fcn.py:104,114,121 (4x4 s2, 4x4 s2, 16x16 s8 transposed convs), networks/utils.py:28-30 (softmax
+//   over the classes), prediction.py:209 (argmax class map).
+//
+// A transposed conv with k = 2s is s*s independent 2x2 "phase" convolutions over the (h+1) x (w+1) grid of input
+// neighbourhoods:
+//   out[b, oy*s + a, ox*s + bq, o] = sum_{u,v in {0,1}} sum_c in[b, oy-1+u, ox-1+v, c] * W[a + s(1-u), bq + s(1-v), o, c]
+// so the whole layer is ONE GEMM   D[M, N] = A[M, K] * Bw[N, K]^T   with
+//   M = B*(h+1)*(w+1) neighbourhoods (flat, no per-image tile padding), K = 4*C (taps packed densely, padded to 64),
+//   N = s*s phases x cpp (Cout padded to 8).
+// A is materialised once by a small im2col kernel (bf16, <= 0.6 MB per image for up8 — 4 % of the output bytes).
+//
+// Kernel structure (one persistent CTA per SM, 320 threads):
+//   warp 0   TMA producer: the M tile's whole A block (all K, 80 KB for up8) is loaded ONCE and stays resident while the CTA
+//            walks a run of N tiles (phase pairs) whose weight slabs stream through a ring (L2-resident, 92 KB per tile).
+//            Operand fill, not the tensor pipe, bounded the earlier tap-by-tap version (320 KB of smem fill per tile).
+//            N is the fast index on purpose: all s*s phases of a pixel block are written within microseconds of each
+//            other, so L2 merges the interleaved Cout*4-byte runs into whole output rows before they reach HBM (with N
+//            slow, HBM saw isolated 544-byte runs at a 2176-byte pitch and delivered 1.4 TB/s).
+//   warp 1   MMA issuer: tcgen05.mma M=128, N=2*cpp, fp32 accumulators in TMEM, two accumulator buffers.
+//   warps 2-9 epilogue: each half (4 warps = 128 TMEM lanes) owns one phase of the N tile, so a thread holds ALL Cout
+//            logits of one output pixel: softmax / argmax need no cross-thread traffic.  Values leave through a shared
+//            memory transpose so that global stores are contiguous Cout*4-byte runs (272 B for 68 classes).
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+using namespace tc;
+
+struct DeconvParams {
+  void* out;
+  long long M;          // rows = B * GH * GW
+  int GH, GW;           // neighbourhood grid = (h+1, w+1)
+  int s, Cout, cpp;     // stride, real / padded channels per phase
+  int BN;               // 2 * cpp
+  int kblocks;          // Kp / 64
+  int n_ntiles, mtiles, total_tiles;
+  int nsplit, cn, units;  // work unit = (M tile, run of cn consecutive N tiles); units = mtiles * nsplit
+  int stages;
+  int mode;             // 0 logits, 1 softmax probabilities, 2 int64 argmax class map
+};
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxStages = 8;
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DeconvParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], afull_bar, afree_bar;
+  __shared__ long long goff[2][128];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
+  const uint32_t smem_a = smem_base;                                   // stationary A block: kblocks slabs [128][64] (SW128)
+  const uint32_t smem_b = smem_a + (uint32_t)p.kblocks * a_bytes;      // weight ring: slabs [BN][64] (b_bytes multiple of 1024)
+  const uint32_t smem_stg = smem_b + (uint32_t)p.stages * b_bytes;     // 2 x [128][Cout] fp32 staging
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+  const uint32_t afull = smem_u32(&afull_bar), afree = smem_u32(&afree_bar);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiWarps); }
+    mbar_init(afull, 1);
+    mbar_init(afree, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0, afree_phase = 0;
+      bool first = true;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int mt = u / p.nsplit, nc = u - mt * p.nsplit;
+        if (!first) { mbar_wait(afree, afree_phase); afree_phase ^= 1; }          // MMAs reading the previous A block are done
+        first = false;
+        mbar_arrive_expect_tx(afull, (uint32_t)p.kblocks * a_bytes);
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(smem_a + kb * a_bytes, &tmA, afull, kb * 64, mt * 128);  // rows past M: zero fill
+        for (int nt = nc * p.cn; nt < (nc + 1) * p.cn; ++nt)
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_arrive_expect_tx(fb, b_bytes);
+            tma_load_2d(smem_b + stage * b_bytes, &tmB, fb, kb * 64, nt * p.BN);
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+      const uint64_t adesc0 = umma_desc(smem_a, 16, 1024, 2);
+      const uint64_t bdesc0 = umma_desc(smem_b, 16, 1024, 2);
+      const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, aphase = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        mbar_wait(afull, aphase);
+        aphase ^= 1;
+        for (int t = 0; t < p.cn; ++t) {
+          mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * 256;
+          uint32_t accum = 0;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t ad = adesc0 + (uint64_t)(kb * a_step);
+            const uint64_t bd = bdesc0 + (uint64_t)(stage * b_step);
+            umma_bf16(d, ad, bd, idesc, accum);
+            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+            umma_commit(empty0 + 8 * stage);
+            if (kb == p.kblocks - 1) {
+              umma_commit(tfull0 + 8 * acc);
+              if (t == p.cn - 1) umma_commit(afree);
+            }
+            accum = 1u;
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    // COUT > 0: the channel count is a compile-time constant (68 = the reference's n_classes), so none of the unrolled
+    // per-channel loops carries a predicate; COUT == 0 is the generic runtime-count variant.
+    const int Cout = COUT ? COUT : p.Cout;
+    const int ew = warp - 2;
+    const int sub = warp & 3;              // TMEM lane quadrant (hardware rule: warp id % 4)
+    const int half = ew >> 2;              // phase of the N tile this warp group owns
+    const int r = sub * 32 + lane;         // tile row
+    const int gt = (ew & 3) * 32 + lane;   // thread index inside the 128-thread group (copy-out role)
+    const int n32 = Cout >> 5;             // full 32-column chunks
+    const int tail8 = ((Cout & 31) + 7) >> 3;
+    const bool vec = (Cout & 3) == 0;
+    const uint32_t stg = smem_stg + (uint32_t)half * (uint32_t)(128 * Cout * 4);
+    const uint32_t row = stg + (uint32_t)r * (uint32_t)(Cout * 4);
+    const int OWs = p.GW * p.s;
+    const long long OHs = (long long)p.GH * p.s;
+    // copy-out role: piece i = gt + 128*j of the [128 px][nper pieces] staging block; (px, q) advance incrementally
+    const int nper = vec ? (Cout >> 2) : Cout;
+    const int px0 = gt / nper, q0 = gt - px0 * nper, px_step = 128 / nper, q_step = 128 - px_step * nper;
+    float* const outp = reinterpret_cast<float*>(p.out);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x)
+    for (int t = 0; t < p.cn; ++t) {
+      const int mt = u / p.nsplit, nt = (u - mt * p.nsplit) * p.cn + t;
+      const long long g = (long long)mt * 128 + r;
+      const bool valid = g < p.M;
+      const long long b = g / (p.GH * p.GW);
+      const int rem = (int)(g - b * (p.GH * p.GW));
+      const int oy = rem / p.GW, ox = rem - oy * p.GW;
+      const int ph = nt * 2 + half;
+      const int a = ph / p.s, bq = ph - a * p.s;
+      const long long opix = (b * OHs + (long long)oy * p.s + a) * OWs + (long long)ox * p.s + bq;
+
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      uint32_t rg[3][32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 256 + half * p.cpp;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k < n32) tmem_ld32(tbase + k * 32, rg[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k == n32) {
+#pragma unroll
+          for (int t8 = 0; t8 < 4; ++t8)
+            if (t8 < tail8) tmem_ld8(tbase + k * 32 + t8 * 8, &rg[k][t8 * 8]);
+        }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator is in registers: the MMAs of the tile after next may start
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+
+      if (p.mode == 2) {
+        float mx = -INFINITY;
+        int amax = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k * 32 + j < Cout) {
+              const float v = __uint_as_float(rg[k][j]);
+              if (v > mx) { mx = v; amax = k * 32 + j; }   // first maximum wins (numpy argmax, prediction.py:209)
+            }
+        if (valid) reinterpret_cast<long long*>(p.out)[opix] = amax;
+        continue;
+      }
+
+      float inv = 1.0f;
+      if (p.mode == 1) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k * 32 + j < Cout) mx = fmaxf(mx, __uint_as_float(rg[k][j]));
+        // exp(v - mx) = 2^(v*log2e - mx*log2e): one FFMA + one MUFU.EX2 per class (flush-to-zero: terms below 2^-126 add nothing)
+        const float nmx = -mx * 1.4426950408889634f;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k * 32 + j < Cout) {
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(rg[k][j]), 1.4426950408889634f, nmx)));
+              rg[k][j] = __float_as_uint(e);
+              sum += e;
+            }
+        inv = __fdividef(1.0f, sum);
+      }
+      named_bar_sync(1 + half, 128);                   // previous tile's copy-out has drained the staging buffer
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = k * 32 + 4 * q;
+          if (c + 4 <= Cout && vec) {
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + c * 4), "f"(__uint_as_float(rg[k][4 * q]) * inv),
+                         "f"(__uint_as_float(rg[k][4 * q + 1]) * inv), "f"(__uint_as_float(rg[k][4 * q + 2]) * inv),
+                         "f"(__uint_as_float(rg[k][4 * q + 3]) * inv)
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c + e < Cout) asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + (c + e) * 4), "f"(__uint_as_float(rg[k][4 * q + e]) * inv) : "memory");
+          }
+        }
+      goff[half][r] = valid ? opix * Cout : -1;
+      named_bar_sync(1 + half, 128);
+      // copy-out: consecutive threads write consecutive pieces of each pixel's contiguous Cout*4-byte run
+      int px = px0, q = q0;
+      if (COUT && vec) {
+        constexpr int NPER = COUT ? COUT / 4 : 1;
+        float4 v[NPER];
+        long long off[NPER];
+#pragma unroll
+        for (int j = 0; j < NPER; ++j) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                       : "r"(stg + (uint32_t)(gt + 128 * j) * 16u));
+          const long long o = goff[half][px];
+          off[j] = o < 0 ? -1 : o + 4 * q;
+          q += q_step; px += px_step;
+          if (q >= nper) { q -= nper; ++px; }
+        }
+#pragma unroll
+        for (int j = 0; j < NPER; ++j)
+          if (off[j] >= 0) *reinterpret_cast<float4*>(outp + off[j]) = v[j];
+      } else if (vec) {
+        for (int j = 0; j < nper; ++j) {
+          const long long o = goff[half][px];
+          if (o >= 0) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stg + (uint32_t)(gt + 128 * j) * 16u));
+            *reinterpret_cast<float4*>(outp + o + 4 * q) = v;
+          }
+          q += q_step; px += px_step;
+          if (q >= nper) { q -= nper; ++px; }
+        }
+      } else {
+        for (int j = 0; j < nper; ++j) {
+          const long long o = goff[half][px];
+          if (o >= 0) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg + (uint32_t)(gt + 128 * j) * 4u));
+            outp[o + q] = v;
+          }
+          q += q_step; px += px_step;
+          if (q >= nper) { q -= nper; ++px; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// A[g][(u*2+v)*C + c] = in[b][oy-1+u][ox-1+v][c] (zero outside the map / past 4*C), bf16; one thread per two K entries
+__global__ void deconv_im2col_kernel(const float* __restrict__ in, __nv_bfloat162* __restrict__ A, long long M, int h, int w, int C, int Kp) {
+  const int kp2 = Kp >> 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * kp2) return;
+  const long long g = i / kp2;
+  const int k0 = (int)(i - g * kp2) * 2;
+  const int GW = w + 1, GH = h + 1;
+  const long long b = g / (GH * GW);
+  const int rem = (int)(g - b * (GH * GW));
+  const int oy = rem / GW, ox = rem - oy * GW;
+  float v[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + e;
+    const int t = k / C, c = k - t * C;
+    const int iy = oy - 1 + (t >> 1), ix = ox - 1 + (t & 1);
+    v[e] = (t < 4 && iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(in + ((b * h + iy) * w + ix) * C + c) : 0.f;
+  }
+  A[i] = __floats2bfloat162_rn(v[0], v[1]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr size_t kSmemMax = 232448;  // 227 KB dynamic shared memory per CTA
+
+size_t fixed_smem(int Cin, int Cout) {
+  const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);
+  (void)cpp;
+  return (size_t)(Kp / 64) * 16384 + (size_t)2 * 128 * Cout * 4 + 1024;   // stationary A block + staging + alignment slack
+}
+
+}  // namespace
+
+int tc_deconv_kp(int Cin) { return (4 * Cin + 63) / 64 * 64; }
+int tc_deconv_cpp(int Cout) {
+  const char* e = getenv("FLD_TC_DECONV_CPP");   // bring-up switch: 96 reproduces the 32-column-chunk layout
+  const int want = e ? atoi(e) : 0;
+  const int cpp = (Cout + 7) / 8 * 8;
+  return want >= cpp && want % 8 == 0 ? want : cpp;
+}
+
+bool tc_deconv_supported(int k, int s, int Cin, int Cout) {
+  if (k != 2 * s || s < 2 || (s * s) % 2 != 0 || Cout < 1 || Cout > 96 || Cin < 1) return false;
+  if (2 * tc_deconv_cpp(Cout) > 256) return false;
+  return fixed_smem(Cin, Cout) + (size_t)2 * (2 * tc_deconv_cpp(Cout)) * 128 <= kSmemMax;
+}
+
+size_t tc_deconv_scratch_bytes(int B, int IH, int IW, int Cin) { return (size_t)B * (IH + 1) * (IW + 1) * tc_deconv_kp(Cin) * 2; }
+
+// w_phase: [s*s][2][2][Cin][Cout] (net.cu set_weights)  ->  out bf16 [s*s*cpp][Kp], k = (u*2+v)*Cin + c
+void tc_deconv_pack_weights(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), std::vector<uint16_t>& out) {
+  const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout), nph = s * s;
+  out.assign((size_t)nph * cpp * Kp, 0);
+  for (int ph = 0; ph < nph; ++ph)
+    for (int t = 0; t < 4; ++t)
+      for (int c = 0; c < Cin; ++c)
+        for (int o = 0; o < Cout; ++o)
+          out[((size_t)ph * cpp + o) * Kp + (size_t)t * Cin + c] = f2bf(w_phase[(((size_t)ph * 4 + t) * Cin + c) * Cout + o]);
+}
+
+struct TcDeconvPlan {
+  CUtensorMap tmA, tmB;
+  DeconvParams p;
+  int grid;
+  size_t smem;
+  const void* scratch;
+  int B, h, w, C, Kp;
+};
+
+int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat16* w_packed, int B, int IH, int IW, int Cin, int Cout,
+                          int s, TcDeconvPlan** out) {
+  if (!hd->encode_tiled) { fld_set_error("cuTensorMapEncodeTiled entry point not available"); return FLD_ERR_CUDA; }
+  if (!tc_deconv_supported(2 * s, s, Cin, Cout)) { fld_set_error("tc_deconv: unsupported geometry"); return FLD_ERR_INVALID; }
+  EncodeTiledFn enc = (EncodeTiledFn)hd->encode_tiled;
+  TcDeconvPlan* pl = new TcDeconvPlan();
+  DeconvParams& p = pl->p;
+  const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);
+  p.out = nullptr;
+  p.GH = IH + 1; p.GW = IW + 1;
+  p.M = (long long)B * p.GH * p.GW;
+  p.s = s; p.Cout = Cout; p.cpp = cpp; p.BN = 2 * cpp; p.kblocks = Kp / 64;
+  p.n_ntiles = s * s / 2;
+  p.mtiles = (int)((p.M + 127) / 128);
+  p.total_tiles = p.mtiles * p.n_ntiles;
+  const size_t fixed = fixed_smem(Cin, Cout);
+  const size_t b_bytes = (size_t)p.BN * 128;
+  p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
+  p.mode = 0;
+  pl->smem = fixed + (size_t)p.stages * b_bytes;
+  // work units: the smallest split of the N range that still gives every SM a few units
+  p.nsplit = 1;
+  while (p.nsplit < p.n_ntiles && (long long)p.mtiles * p.nsplit < 4LL * hd->sm_count && p.n_ntiles % (p.nsplit * 2) == 0) p.nsplit *= 2;
+  p.cn = p.n_ntiles / p.nsplit;
+  p.units = p.mtiles * p.nsplit;
+  pl->grid = std::min(p.units, hd->sm_count);
+  pl->scratch = scratch; pl->B = B; pl->h = IH; pl->w = IW; pl->C = Cin; pl->Kp = Kp;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)p.M};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scratch, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(deconv A) failed: %d", (int)r); return FLD_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)s * s * cpp};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w_packed), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(deconv B) failed: %d", (int)r); return FLD_ERR_CUDA; }
+  }
+  *out = pl;
+  return FLD_OK;
+}
+
+void tc_deconv_plan_destroy(TcDeconvPlan* p) { delete p; }
+
+// in: fp32 NHWC [B][h][w][C]; out: mode 0/1 fp32 [B][(h+1)s][(w+1)s][Cout], mode 2 int64 [B][(h+1)s][(w+1)s]
+int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st) {
+  if (pl->p.total_tiles == 0) return FLD_OK;
+  {
+    const long long n = pl->p.M * (pl->Kp / 2);
+    deconv_im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat162*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C, pl->Kp);
+    FLD_LAUNCHED();
+  }
+  DeconvParams p = pl->p;
+  p.out = out; p.mode = mode;
+  if (p.Cout == 68) {   // the reference's n_classes (scripts/cli.py:39, training.py:110)
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    deconv_gemm_kernel<68><<<pl->grid, kThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
+  } else {
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    deconv_gemm_kernel<0><<<pl->grid, kThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
+  }
+  FLD_LAUNCHED();
+  return FLD_OK;
+}

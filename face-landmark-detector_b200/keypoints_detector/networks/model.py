@@ -323,6 +323,8 @@ class Model:
     def intermediate(self, x, tensor, dtype=None):
         """Run forward and return intermediate tensor `tensor` ([B,h,w,c] float32 CUDA) — parity checks of the levels."""
         out, ws, al = self.forward_device(x, dtype, return_workspace=True)
+        if tensor == len(self.graph.layers):   # the final tensor is written straight into `out`, not the workspace
+            return out
         lib = N.load_library()
         net = self.compiled(x.device.index, dtype)
         (h, w, c), dt = self.tensor_info(tensor, x.device.index, dtype)

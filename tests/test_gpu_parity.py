@@ -423,3 +423,23 @@ def test_multi_gpu_shards_bit_identical(dev):
         parts.append(prediction.LandmarkPipeline(m, dtype="bfloat16", device=g)(frames, boxes[lo:hi], f2f[lo:hi]))
     for k in ("marks", "aligned"):
         assert np.array_equal(np.concatenate([p[k] for p in parts]), full[k])
+
+
+@pytest.mark.parametrize("n_classes", [12, 21])
+def test_fcn8_other_class_counts_bf16(dev, n_classes):
+    """The tensor-core transposed conv has a compile-time variant for 68 classes; other counts take the generic variant
+    (12: 16-byte vector stores, 21: scalar stores).  Same bars as test_fcn8_bf16 / test_fcn8_fused_classmap."""
+    from keypoints_detector.networks.fcn import fcn_8
+    from oracle import cnn as o_cnn
+    m = fcn_8(n_classes, input_height=64, input_width=96).init_weights(9)
+    x = np.random.default_rng(9).normal(0, 40, (3, 64, 96, 3)).astype(np.float32)
+    probs_ref = o_cnn.fcn_forward(x.astype(np.float64), m.weights, "fcn_8", torch.float64)
+    xt = T(x, dev)
+    probs = m.forward_device(xt, "bfloat16").cpu().numpy()
+    assert probs.shape == probs_ref.shape == (3, 72 * 104, n_classes)
+    np.testing.assert_allclose(probs.sum(-1), 1.0, atol=1e-4)
+    assert np.abs(probs - probs_ref).mean() < 4e-3
+    ref = probs_ref.reshape(3, 72, 104, n_classes).argmax(-1)
+    assert (probs.reshape(3, 72, 104, n_classes).argmax(-1) == ref).mean() > 0.97
+    cm = m.forward_classmap_device(xt, "bfloat16").cpu().numpy()
+    assert (cm == ref).mean() > 0.97

@@ -40,7 +40,7 @@ def main():
     from keypoints_detector.utils import metrics
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    which = sys.argv[1:] or ["align", "decode", "preprocess", "fcn"]
+    which = sys.argv[1:] or ["align", "decode", "preprocess", "fcn", "encoders"]
 
     if "align" in which:
         F, B = 64, 4096
@@ -81,22 +81,39 @@ def main():
             print(json.dumps({"kernel": "heatmap_xy (n_points=%d, C3 shape, B=64)" % n, "ms_median": med, "images_per_s": B / med * 1e3,
                               "algorithmic_bytes": nbytes, "achieved_GBs": nbytes / med / 1e6, "frac_of_measured_hbm": nbytes / med / 1e6 / HBM}))
 
+    def fcn_bench(label, m, dtype, B, H=224, W=224):
+        x = torch.randn((B, H, W, 3), dtype=torch.float32, device=dev) * 50
+        m.forward_device(x, dtype)
+        m.set_profiling(True, dev, dtype)
+        acc = np.zeros(len(m.graph.layers))
+        for _ in range(3):
+            m.forward_device(x, dtype)
+            acc += np.array([t for _, t in m.layer_times(dev, dtype)])
+        m.set_profiling(False, dev, dtype)
+        acc /= 3
+        med_p, _ = timeit(lambda: m.forward_device(x, dtype), reps=5, warm=1)
+        med_c, _ = timeit(lambda: m.forward_classmap_device(x, dtype), reps=5, warm=1)
+        names = [L["name"] for L in m.graph.layers]
+        top = sorted(zip(names, acc), key=lambda t: -t[1])[:12]
+        print(json.dumps({"kernel": label + " forward", "dtype": dtype, "batch": B, "ms_layers_sum": float(acc.sum()),
+                          "ms_forward_probs": med_p, "ms_forward_classmap": med_c, "images_per_s_probs": B / med_p * 1e3,
+                          "images_per_s_classmap": B / med_c * 1e3,
+                          "layer_ms": {n: round(float(t), 4) for n, t in (zip(names, acc) if len(names) <= 20 else top)}}), flush=True)
+        del x
+        m._release()
+        torch.cuda.empty_cache()
+
     if "fcn" in which:
         from keypoints_detector.networks.fcn import fcn_8
         m = fcn_8(68, input_height=224, input_width=224).init_weights(0)
-        for dtype, B in (("bfloat16", 32), ("float32", 4)):
-            x = torch.randn((B, 224, 224, 3), dtype=torch.float32, device=dev) * 50
-            m.forward_device(x, dtype)
-            m.set_profiling(True, dev, dtype)
-            acc = np.zeros(len(m.graph.layers))
-            for _ in range(3):
-                m.forward_device(x, dtype)
-                acc += np.array([t for _, t in m.layer_times(dev, dtype)])
-            m.set_profiling(False, dev, dtype)
-            acc /= 3
-            print(json.dumps({"kernel": "fcn_8/vanilla@224 forward", "dtype": dtype, "batch": B, "ms_total": float(acc.sum()),
-                              "images_per_s": B / acc.sum() * 1e3,
-                              "layer_ms": {L["name"]: round(float(t), 4) for L, t in zip(m.graph.layers, acc)}}))
+        for dtype, B in (("bfloat16", 32), ("bfloat16", 256), ("float32", 4)):
+            fcn_bench("fcn_8/vanilla@224", m, dtype, B)
+
+    if "encoders" in which:
+        from keypoints_detector.networks import fcn
+        for name, build in (("fcn_8_mobilenet", fcn.fcn_8_mobilenet), ("fcn_8_resnet50", fcn.fcn_8_resnet50), ("fcn_8_vgg", fcn.fcn_8_vgg)):
+            m = build(68, 224, 224).init_weights(0)
+            fcn_bench(name + "@224", m, "bfloat16", 32)
 
 
 if __name__ == "__main__":
