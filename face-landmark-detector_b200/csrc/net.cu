@@ -21,7 +21,7 @@ struct TensorInfo {
 
 enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 
-struct PlanEntry { int B; const void* in; TcConvPlan* plan; int fuse = 0; const void* out = nullptr; };
+struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
 struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; };
 

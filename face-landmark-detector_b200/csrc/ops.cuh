@@ -39,9 +39,8 @@ void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_ho
                         uint16_t (*f2bf)(float), uint16_t* out /*[Cout*48]*/);
 // generic: stride 1, Cin % 64 == 0, bf16 NHWC in; weights bf16 [kh*kw][Cout_pad][Cin]; out bf16 or f32 NHWC
 bool tc_conv_supported(const ConvGeom& g);
-// d2s > 0: transposed-conv phase mode (see tc_conv.cu): cout_pad = stride^2 * d2s_cpp rows per tap, fp32 depth-to-space output
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcConvPlan** out, int d2s = 0, int d2s_cpp = 0, int d2s_fuse = 0, void* d2s_out = nullptr);
+                        TcConvPlan** out);
 int simt_pad_cvt_bf16(const float* in, void* out_bf16, long long n_px, int C, int Cpad, cudaStream_t st);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype, cudaStream_t st);

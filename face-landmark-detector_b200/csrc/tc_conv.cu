@@ -39,10 +39,6 @@ struct TmaConvParams {
   int tiles_x, tiles_y, tiles_b, total_tiles;
   int stages;
   int act, pool;
-  int d2s_fuse;        // 0: write logits; 1: fused softmax over the Cout channels (probabilities); 2: fused argmax -> int64 class map
-  int d2s_tma;         // fused softmax: stage each phase's [128 px][Cout] fp32 block in shared memory, write it with one TMA store
-  int d2s, d2s_cpp;    // depth-to-space mode (transposed conv as stride^2 phase convs): stride, padded channels per phase;
-                       // N tile = BN / d2s_cpp phases, output pixel (d2s*oy + a, d2s*ox + b) of a [B, d2s*OH, d2s*OW, Cout] fp32 map
   unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
   int dbg;             // FLD_TC_DBG bisect switches (results are garbage when set): 1 skip epilogue math/stores,
                        // 2 skip TMEM loads too, 4 skip the A-operand TMA, 8 skip the B-operand TMA, 16 skip the MMAs
@@ -60,8 +56,7 @@ constexpr int kTraceN = 2048;
 
 template <bool OUT_F32>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
-                const TmaConvParams p) {
+conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TmaConvParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -206,107 +201,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       if (tr) TRACE(2, ti, 1);
       tc_fence_after();
-      if (OUT_F32 && p.d2s && p.d2s_fuse) {
-        // Fused decode (reference networks/utils.py:28-30 softmax / prediction.py:209 argmax): this warp takes phase
-        // `half` of the N tile, so each thread holds ALL Cout logits of one output pixel (<= 3 chunks of 32 columns).
-        const int nch = p.d2s_cpp >> 5;
-        uint32_t rg[3][32];
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < nch) tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 256 + half * p.d2s_cpp + k * 32, rg[k]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator drained into registers: MMAs of the next tile may start
-        const int phase = nt * 2 + half;
-        const int a = phase / p.d2s, bq = phase - a * p.d2s;
-        const size_t opix = ((size_t)b * (p.OH * p.d2s) + (size_t)oy * p.d2s + a) * (size_t)(p.OW * p.d2s) + (size_t)ox * p.d2s + bq;
-        float mx = -INFINITY;
-        int amax = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (k < nch && k * 32 + j < p.Cout) {
-              const float v = __uint_as_float(rg[k][j]);
-              if (v > mx) { mx = v; amax = k * 32 + j; }   // first maximum wins (numpy argmax)
-            }
-        if (eo.valid) {
-          if (p.d2s_fuse == 2) {
-            reinterpret_cast<long long*>(p.out)[opix] = amax;
-          } else if (!p.d2s_tma) {
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (k < nch && k * 32 + j < p.Cout) {
-                  const float e = expf(__uint_as_float(rg[k][j]) - mx);
-                  rg[k][j] = __float_as_uint(e);
-                  sum += e;
-                }
-            const float inv = 1.0f / sum;
-            float* o = reinterpret_cast<float*>(p.out) + opix * p.Cout;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int c = k * 32 + 4 * q;
-                if (k < nch && c + 4 <= p.Cout && (p.Cout & 3) == 0) {
-                  *reinterpret_cast<float4*>(o + c) = make_float4(__uint_as_float(rg[k][4 * q]) * inv, __uint_as_float(rg[k][4 * q + 1]) * inv,
-                                                                  __uint_as_float(rg[k][4 * q + 2]) * inv, __uint_as_float(rg[k][4 * q + 3]) * inv);
-                } else if (k < nch) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    if (c + e < p.Cout) o[c + e] = __uint_as_float(rg[k][4 * q + e]) * inv;
-                }
-              }
-          }
-        }
-        if (p.d2s_fuse == 1 && p.d2s_tma) {
-          // Probabilities leave through shared memory: the 128 pixels of this phase form a dense [NB][TH][TW][Cout] fp32 box
-          // that ONE TMA store scatters to out[b][oy*s + a][ox*s + bq][:] (272-byte runs at a 2176-byte pitch for up8);
-          // pixels outside the map are clipped by the tensor map.  Per-thread 16-byte global stores at that pitch ran at
-          // ~1 TB/s; the bulk store runs at HBM speed and frees the LSU for the softmax arithmetic.
-          const uint32_t stg = smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)half * (uint32_t)(128 * p.Cout * 4);
-          const bool issuer = (sub == 0) && (lane == 0);
-          if (issuer) bulk_wait_read0();              // the previous store of this buffer has been read out
-          named_bar_sync(1 + half, 128);
-          float sum = 0.f;
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (k < nch && k * 32 + j < p.Cout) {
-                const float e = __expf(__uint_as_float(rg[k][j]) - mx);
-                rg[k][j] = __float_as_uint(e);
-                sum += e;
-              }
-          const float inv = __fdividef(1.0f, sum);
-          const uint32_t row = stg + (uint32_t)r * (uint32_t)(p.Cout * 4);
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int c = k * 32 + 4 * q;
-              if (k < nch && c + 4 <= p.Cout)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + c * 4), "f"(__uint_as_float(rg[k][4 * q]) * inv),
-                             "f"(__uint_as_float(rg[k][4 * q + 1]) * inv), "f"(__uint_as_float(rg[k][4 * q + 2]) * inv),
-                             "f"(__uint_as_float(rg[k][4 * q + 3]) * inv)
-                             : "memory");
-            }
-          fence_proxy_async_smem();
-          named_bar_sync(1 + half, 128);
-          if (issuer) {
-            tma_store_5d(&tmO, stg, bq * p.Cout, tx * p.TW, a, ty * p.TH, tb * p.NB);
-            bulk_commit();
-          }
-        }
-        if (tr) TRACE(2, ti, 2);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-        continue;
-      }
       for (int ch = half * 32; ch < p.BN; ch += 64) {
         if (p.dbg & 2) break;
         uint32_t regs[32];
@@ -314,17 +208,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
         if (p.dbg & 1) { if ((regs[0] ^ regs[31]) == 0x7fc12345u) eo.valid = false; continue; }
         EpiOut e2 = eo;
-        if (OUT_F32 && p.d2s) {
-          // phase (a, bq) of the transposed conv owns columns [pl*d2s_cpp, (pl+1)*d2s_cpp) of this N tile
-          const int pl = ch / p.d2s_cpp, cb = ch - pl * p.d2s_cpp;
-          const int phase = nt * (p.BN / p.d2s_cpp) + pl;
-          const int a = phase / p.d2s, bq = phase - a * p.d2s;
-          const size_t opix = ((size_t)b * (p.OH * p.d2s) + (size_t)oy * p.d2s + a) * (size_t)(p.OW * p.d2s) + (size_t)ox * p.d2s + bq;
-          e2.c_left = p.Cout - cb;
-          e2.ptr = reinterpret_cast<float*>(p.out) + opix * p.Cout + cb;
-          epilogue_chunk<false, true, false>(regs, p.bias, p.act, lane, p.TW, e2);
-          continue;
-        }
         e2.c_left = p.Cout - n0 - ch;
         if (OUT_F32) e2.ptr = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0 + ch;
         else e2.ptr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0 + ch;
@@ -339,7 +222,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   }
-  if (p.d2s_tma) bulk_wait_read0();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -352,8 +234,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 struct TcConvPlan {
-  CUtensorMap tmA, tmB, tmO;
-  const void* tma_out = nullptr;  // output buffer the store map was encoded for (d2s_tma)
+  CUtensorMap tmA, tmB;
   TmaConvParams p;
   int grid;
   size_t smem;
@@ -368,7 +249,7 @@ bool tc_conv_supported(const ConvGeom& g) {
 }
 
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcConvPlan** out, int d2s, int d2s_cpp, int d2s_fuse, void* d2s_out) {
+                        TcConvPlan** out) {
   if (!h->encode_tiled) { fld_set_error("cuTensorMapEncodeTiled entry point not available"); return FLD_ERR_CUDA; }
   EncodeTiledFn enc = (EncodeTiledFn)h->encode_tiled;
   TcConvPlan* pl = new TcConvPlan();
@@ -379,7 +260,6 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.act = g.act; p.pool = g.pool;
   { const char* e = getenv("FLD_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.trace = nullptr;
-  p.d2s = d2s; p.d2s_cpp = d2s_cpp; p.d2s_fuse = d2s_fuse;
   // M-tile geometry: TW*TH*NB = 128 pixels, TW in {4, 8}: the pool partners are lane^1 and lane^TW
   const int TW = g.OW > 4 ? 8 : 4;
   int TH = 2;
@@ -387,23 +267,16 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   const int NB = 128 / (TW * TH);
   p.TW = TW; p.TH = TH; p.NB = NB;
   // N tile
-  const int BN = d2s ? (d2s_cpp <= 128 && (cout_pad / d2s_cpp) % 2 == 0 ? 2 * d2s_cpp : d2s_cpp)
-                     : (cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128));
+  const int BN = cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128);
   if (cout_pad % BN != 0 || BN % 16 != 0) { delete pl; fld_set_error("tc_conv: bad cout_pad %d", cout_pad); return FLD_ERR_INVALID; }
   p.BN = BN; p.cout_pad = cout_pad; p.n_ntiles = cout_pad / BN;
-  if (d2s_fuse && (BN != 2 * d2s_cpp || d2s_cpp > 96 || d2s_cpp % 32 != 0)) {
-    delete pl; fld_set_error("tc_conv: fused decode needs two phases of <= 96 channels per N tile"); return FLD_ERR_INVALID;
-  }
   p.tiles_x = fld_div_up(g.OW, TW); p.tiles_y = fld_div_up(g.OH, TH); p.tiles_b = fld_div_up(B, NB);
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_ntiles;
   const size_t stage_bytes = 128 * 128 + (size_t)BN * 128;
-  // fused softmax with a 16-byte-granular channel count: probabilities are staged in smem and leave by TMA store
-  p.d2s_tma = (d2s_fuse == 1 && d2s_out && g.Cout % 4 == 0 && !getenv("FLD_TC_D2S_TMA_OFF")) ? 1 : 0;
-  const size_t staging = p.d2s_tma ? (size_t)2 * 128 * g.Cout * 4 : 0;
-  int stages = (int)((200 * 1024 - staging) / stage_bytes);
+  int stages = (int)((200 * 1024) / stage_bytes);
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
-  pl->smem = stages * stage_bytes + staging + 1024;
+  pl->smem = stages * stage_bytes + 1024;
   pl->grid = std::min(p.total_tiles, h->sm_count);
 
   // activations: bf16 NHWC [B][IH][IW][Cin]
@@ -428,19 +301,6 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return FLD_ERR_CUDA; }
   }
-  pl->tmO = pl->tmA;
-  if (p.d2s_tma) {
-    // out fp32 [B][OH*s][OW*s][Cout] seen as (bq*Cout + c, ox, a, oy, b); one box = one phase of one M tile
-    const cuuint64_t s = (cuuint64_t)d2s, C = (cuuint64_t)g.Cout, OWs = (cuuint64_t)g.OW * s, OHs = (cuuint64_t)g.OH * s;
-    cuuint64_t dims[5] = {s * C, (cuuint64_t)g.OW, s, (cuuint64_t)g.OH, (cuuint64_t)B};
-    cuuint64_t strides[4] = {s * C * 4, OWs * C * 4, s * OWs * C * 4, OHs * OWs * C * 4};
-    cuuint32_t box[5] = {(cuuint32_t)g.Cout, (cuuint32_t)TW, 1, (cuuint32_t)TH, (cuuint32_t)NB};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&pl->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, d2s_out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return FLD_ERR_CUDA; }
-    pl->tma_out = d2s_out;
-  }
   *out = pl;
   return FLD_OK;
 }
@@ -457,14 +317,13 @@ int tc_conv_run(const TcConvPlan* pl, const float* bias, void* out, int out_dtyp
     FLD_CUDA(cudaMemsetAsync(tbuf, 0, 3 * kTraceN * 8, st));
     p.trace = tbuf;
   }
-  if (p.d2s_tma && out != pl->tma_out) { fld_set_error("tc_conv: plan was built for another output buffer"); return FLD_ERR_STATE; }
   if (p.pool && out_dtype != FLD_BF16) { fld_set_error("tc_conv: fused pool needs bf16 output"); return FLD_ERR_INVALID; }
   if (out_dtype == FLD_F32) {
     FLD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    conv_tma_kernel<true><<<pl->grid, kTmaThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->tmO, p);
+    conv_tma_kernel<true><<<pl->grid, kTmaThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
   } else {
     FLD_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    conv_tma_kernel<false><<<pl->grid, kTmaThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->tmO, p);
+    conv_tma_kernel<false><<<pl->grid, kTmaThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
   }
   FLD_LAUNCHED();
   if (p.trace) {  // dump CTA 0's event log: "<role> <tag> <clock>" per line

@@ -43,11 +43,17 @@ struct DeconvParams {
   int nsplit, cn, units;  // work unit = (M tile, run of cn consecutive N tiles); units = mtiles * nsplit
   int stages;
   int mode;             // 0 logits, 1 softmax probabilities, 2 int64 argmax class map
+  unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
 };
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
+constexpr int kTraceN = 2048;
+#define DTRACE(role, idx, tag)                                                                                        \
+  do {                                                                                                                \
+    if (p.trace && blockIdx.x == 0 && (idx) < kTraceN) p.trace[(role) * kTraceN + (idx)++] = ((unsigned long long)clock64() << 4) | (tag); \
+  } while (0)
 
 template <int COUT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -87,18 +93,22 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (elect_one()) {
       uint32_t stage = 0, phase = 0, afree_phase = 0;
       bool first = true;
+      int ti = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int mt = u / p.nsplit, nc = u - mt * p.nsplit;
         if (!first) { mbar_wait(afree, afree_phase); afree_phase ^= 1; }          // MMAs reading the previous A block are done
         first = false;
+        DTRACE(0, ti, 3);
         mbar_arrive_expect_tx(afull, (uint32_t)p.kblocks * a_bytes);
         for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(smem_a + kb * a_bytes, &tmA, afull, kb * 64, mt * 128);  // rows past M: zero fill
         for (int nt = nc * p.cn; nt < (nc + 1) * p.cn; ++nt)
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            DTRACE(0, ti, 1);
             const uint32_t fb = full0 + 8 * stage;
             mbar_arrive_expect_tx(fb, b_bytes);
             tma_load_2d(smem_b + stage * b_bytes, &tmB, fb, kb * 64, nt * p.BN);
+            DTRACE(0, ti, 2);
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
       }
@@ -112,16 +122,20 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint64_t bdesc0 = umma_desc(smem_b, 16, 1024, 2);
       const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, aphase = 0;
+      int ti = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         mbar_wait(afull, aphase);
+        DTRACE(1, ti, 4);
         aphase ^= 1;
         for (int t = 0; t < p.cn; ++t) {
           mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+          DTRACE(1, ti, 3);
           tc_fence_after();
           const uint32_t d = tmem_base + acc * 256;
           uint32_t accum = 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(full0 + 8 * stage, phase);
+            DTRACE(1, ti, 1);
             tc_fence_after();
             const uint64_t ad = adesc0 + (uint64_t)(kb * a_step);
             const uint64_t bd = bdesc0 + (uint64_t)(stage * b_step);
@@ -134,6 +148,7 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               umma_commit(tfull0 + 8 * acc);
               if (t == p.cn - 1) umma_commit(afree);
             }
+            DTRACE(1, ti, 2);
             accum = 1u;
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
@@ -165,6 +180,8 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int px0 = gt / nper, q0 = gt - px0 * nper, px_step = 128 / nper, q_step = 128 - px_step * nper;
     float* const outp = reinterpret_cast<float*>(p.out);
     uint32_t acc = 0, acc_phase = 0;
+    int ti = 0;
+    const bool tr = (warp == 2 && lane == 0);
     for (int u = blockIdx.x; u < p.units; u += gridDim.x)
     for (int t = 0; t < p.cn; ++t) {
       const int mt = u / p.nsplit, nt = (u - mt * p.nsplit) * p.cn + t;
@@ -177,7 +194,9 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int a = ph / p.s, bq = ph - a * p.s;
       const long long opix = (b * OHs + (long long)oy * p.s + a) * OWs + (long long)ox * p.s + bq;
 
+      if (tr) DTRACE(2, ti, 0);
       mbar_wait(tfull0 + 8 * acc, acc_phase);
+      if (tr) DTRACE(2, ti, 1);
       tc_fence_after();
       uint32_t rg[3][32];
       const uint32_t tbase = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 256 + half * p.cpp;
@@ -195,6 +214,7 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator is in registers: the MMAs of the tile after next may start
+      if (tr) DTRACE(2, ti, 2);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
 
@@ -223,7 +243,7 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (k * 32 + j < Cout) mx = fmaxf(mx, __uint_as_float(rg[k][j]));
         // exp(v - mx) = 2^(v*log2e - mx*log2e): one FFMA + one MUFU.EX2 per class (flush-to-zero: terms below 2^-126 add nothing)
         const float nmx = -mx * 1.4426950408889634f;
-        float sum = 0.f;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains instead of one 68-deep dependent FADD chain
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -232,9 +252,9 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float e;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(rg[k][j]), 1.4426950408889634f, nmx)));
               rg[k][j] = __float_as_uint(e);
-              sum += e;
+              sum[j & 3] += e;
             }
-        inv = __fdividef(1.0f, sum);
+        inv = __fdividef(1.0f, (sum[0] + sum[1]) + (sum[2] + sum[3]));
       }
       named_bar_sync(1 + half, 128);                   // previous tile's copy-out has drained the staging buffer
 #pragma unroll
@@ -329,7 +349,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-constexpr size_t kSmemMax = 232448;  // 227 KB dynamic shared memory per CTA
+constexpr size_t kSmemMax = 232448 - 4096;  // 227 KB per CTA minus the static part (barriers, goff table)
 
 size_t fixed_smem(int Cin, int Cout) {
   const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);
@@ -393,7 +413,7 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
   const size_t fixed = fixed_smem(Cin, Cout);
   const size_t b_bytes = (size_t)p.BN * 128;
   p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
-  p.mode = 0;
+  p.mode = 0; p.trace = nullptr;
   pl->smem = fixed + (size_t)p.stages * b_bytes;
   // work units: the smallest split of the N range that still gives every SM a few units
   p.nsplit = 1;
@@ -436,14 +456,40 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
     FLD_LAUNCHED();
   }
   DeconvParams p = pl->p;
-  p.out = out; p.mode = mode;
+  p.out = out; p.mode = mode; p.trace = nullptr;
+  if (getenv("FLD_TC_TRACE")) {
+    static unsigned long long* tbuf = nullptr;
+    if (!tbuf) FLD_CUDA(cudaMalloc(&tbuf, 3 * kTraceN * 8));
+    FLD_CUDA(cudaMemsetAsync(tbuf, 0, 3 * kTraceN * 8, st));
+    p.trace = tbuf;
+  }
+  size_t smem = pl->smem;
+  if (mode == 2) {   // class-map mode stages nothing: the staging bytes deepen the weight ring instead
+    const size_t b_bytes = (size_t)p.BN * 128, fixed = (size_t)p.kblocks * 16384 + 1024;
+    p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
+    smem = fixed + (size_t)p.stages * b_bytes;
+  }
   if (p.Cout == 68) {   // the reference's n_classes (scripts/cli.py:39, training.py:110)
-    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    deconv_gemm_kernel<68><<<pl->grid, kThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    deconv_gemm_kernel<68><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
   } else {
-    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    deconv_gemm_kernel<0><<<pl->grid, kThreads, pl->smem, st>>>(pl->tmA, pl->tmB, p);
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    deconv_gemm_kernel<0><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
   }
   FLD_LAUNCHED();
+  if (p.trace) {  // dump CTA 0's event log: "<role> <tag> <clock>" per line
+    static int n_dump = 0;
+    std::vector<unsigned long long> hbuf(3 * kTraceN);
+    FLD_CUDA(cudaStreamSynchronize(st));
+    FLD_CUDA(cudaMemcpy(hbuf.data(), p.trace, hbuf.size() * 8, cudaMemcpyDeviceToHost));
+    char name[256];
+    snprintf(name, sizeof(name), "%s/trace_deconv_%02d_s%d_mode%d.txt", getenv("FLD_TC_TRACE"), n_dump++, p.s, p.mode);
+    if (FILE* f = fopen(name, "w")) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < kTraceN && hbuf[r * kTraceN + i]; ++i)
+          fprintf(f, "%d %llu %llu\n", r, hbuf[r * kTraceN + i] & 15, hbuf[r * kTraceN + i] >> 4);
+      fclose(f);
+    }
+  }
   return FLD_OK;
 }

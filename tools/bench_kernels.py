@@ -89,8 +89,13 @@ def main():
         for _ in range(3):
             m.forward_device(x, dtype)
             acc += np.array([t for _, t in m.layer_times(dev, dtype)])
+        accc = np.zeros(len(m.graph.layers))
+        for _ in range(3):
+            m.forward_classmap_device(x, dtype)
+            accc += np.array([t for _, t in m.layer_times(dev, dtype)])
         m.set_profiling(False, dev, dtype)
         acc /= 3
+        accc /= 3
         med_p, _ = timeit(lambda: m.forward_device(x, dtype), reps=5, warm=1)
         med_c, _ = timeit(lambda: m.forward_classmap_device(x, dtype), reps=5, warm=1)
         names = [L["name"] for L in m.graph.layers]
@@ -98,6 +103,7 @@ def main():
         print(json.dumps({"kernel": label + " forward", "dtype": dtype, "batch": B, "ms_layers_sum": float(acc.sum()),
                           "ms_forward_probs": med_p, "ms_forward_classmap": med_c, "images_per_s_probs": B / med_p * 1e3,
                           "images_per_s_classmap": B / med_c * 1e3,
+                          "last_deconv_ms": {"probs": round(float(acc[-2]), 4), "classmap": round(float(accc[-2]), 4)},
                           "layer_ms": {n: round(float(t), 4) for n, t in (zip(names, acc) if len(names) <= 20 else top)}}), flush=True)
         del x
         m._release()
