@@ -340,6 +340,12 @@ def run_gpu(args, rank, world, local_rank):
     ms_e2e = e2e_all(args.steps)
     e2e_val = total_faces * args.steps / (ms_e2e * 1e-3)
     d2h = marks_h[0].numel() * 4 + crops_h[0].numel()
+    # the host link this box gave us: the same pinned H2D copies alone (the e2e leg cannot be faster than this)
+    def copy_only(k):
+        for d, h in zip(slots[k % 2], pin_sets[k % n_sets]):
+            d.copy_(h, non_blocking=True)
+    ms_link = timed(copy_only, max(args.steps, 5)) / max(args.steps, 5)
+    link_gbps = set_bytes / (ms_link * 1e-3) / 1e9
 
     if rank == 0:
         cpu = None
@@ -357,7 +363,9 @@ def run_gpu(args, rank, world, local_rank):
                            "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2; activations workspace rewritten every step"
                                  % (n_sets, n_sets * set_bytes / 1e6)},
                 "e2e": {"value": e2e_val, "unit": "faces/s", "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_link, "h2d_link_GBps": link_gbps,
+                        "note": "H2D of the step's frames alone takes h2d_only_ms_per_step on this box; the leg is host-link-bound when that "
+                                "is close to ms_per_step"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     return 0
