@@ -266,8 +266,11 @@ class Model:
             N.check(dt)
         return tuple(hwc), dt
 
-    def forward_device(self, x, dtype=None, out=None, return_workspace=False):
-        """x: CUDA tensor [B,H,W,C] (uint8 or float32 per model.in_dtype) -> float32 CUDA tensor of the final layer."""
+    def forward_device(self, x, dtype=None, out=None, return_workspace=False, lane=0):
+        """x: CUDA tensor [B,H,W,C] (uint8 or float32 per model.in_dtype) -> float32 CUDA tensor of the final layer.
+
+        `lane` selects one of several independent activation workspaces, so that forwards of independent batches
+        enqueued on different CUDA streams can overlap (the weights and kernel plans are shared, the activations not)."""
         lib = N.load_library()
         assert x.is_cuda and x.is_contiguous()
         exp = torch.uint8 if self.in_dtype == "uint8" else torch.float32
@@ -281,10 +284,10 @@ class Model:
             net = self.compiled(dev, dtype)
             comp = self._compute_code(dtype)
             need = lib.fld_net_workspace_bytes(net, B)
-            ws = self._ws.get((dev, comp))
+            ws = self._ws.get((dev, comp, lane))
             if ws is None or ws.numel() < need:
                 ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
-                self._ws[(dev, comp)] = ws
+                self._ws[(dev, comp, lane)] = ws
             base = ws.data_ptr()
             al = (-base) % 1024
             oh, ow, oc = self.graph.shapes[-1]
@@ -295,7 +298,7 @@ class Model:
             return out, ws, al
         return out
 
-    def forward_classmap_device(self, x, dtype=None):
+    def forward_classmap_device(self, x, dtype=None, lane=0):
         """Segmentation models: forward + per-pixel argmax over classes (reference prediction.py:208-209) in one call ->
         int64 CUDA [B, oh, ow].  In bfloat16 mode fcn_8's argmax runs inside the last transposed conv's epilogue, so neither
         logits nor probabilities are written to HBM."""
@@ -310,10 +313,10 @@ class Model:
             net = self.compiled(dev, dtype)
             comp = self._compute_code(dtype)
             need = lib.fld_net_workspace_bytes(net, B)
-            ws = self._ws.get((dev, comp))
+            ws = self._ws.get((dev, comp, lane))
             if ws is None or ws.numel() < need:
                 ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
-                self._ws[(dev, comp)] = ws
+                self._ws[(dev, comp, lane)] = ws
             base = ws.data_ptr()
             al = (-base) % 1024
             cmap = torch.empty((B, self.output_height, self.output_width), dtype=torch.int64, device=x.device)

@@ -34,27 +34,29 @@ def _device(device=None):
 
 
 # ----------------------------------------------------------------------------------------------- device ops
-def preprocess_faces_device(frames, boxes, face2frame, size=128, swap_rb=True):
+def preprocess_faces_device(frames, boxes, face2frame, size=128, swap_rb=True, out=None, out_boxes=None):
     """frames uint8 CUDA [F,H,W,3] BGR; boxes int32 CUDA [B,4]; face2frame int32 CUDA [B].
     -> (crops uint8 [B,size,size,3] RGB, faceboxes int32 [B,4]); reference prediction.py:76-83."""
     lib = N.load_library()
     F, H, W, C = frames.shape
     assert C == 3 and frames.dtype == torch.uint8
     B = boxes.shape[0]
-    out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=frames.device)
-    fb = torch.empty((B, 4), dtype=torch.int32, device=frames.device)
+    out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=frames.device) if out is None else out
+    fb = torch.empty((B, 4), dtype=torch.int32, device=frames.device) if out_boxes is None else out_boxes
     with torch.cuda.device(frames.device):
         N.check(lib.fld_preprocess_faces(N.handle(frames.device), N.ptr(frames), F, H, W, N.ptr(boxes), N.ptr(face2frame), B, size,
                                          int(swap_rb), N.ptr(out), N.ptr(fb), N.stream_ptr(frames.device)))
     return out, fb
 
 
-def decode_regress_device(out136, faceboxes, want_uint=True):
+def decode_regress_device(out136, faceboxes, want_uint=True, out=None, out_uint=None):
     """reference prediction.py:88-94 on device: -> (marks float32 [B,68,2], marks uint64-as-int64 [B,68,2] or None)."""
     lib = N.load_library()
     B = out136.shape[0]
-    marks = torch.empty((B, 68, 2), dtype=torch.float32, device=out136.device)
-    marks_u = torch.empty((B, 68, 2), dtype=torch.int64, device=out136.device) if want_uint else None
+    marks = torch.empty((B, 68, 2), dtype=torch.float32, device=out136.device) if out is None else out
+    marks_u = None
+    if want_uint:
+        marks_u = torch.empty((B, 68, 2), dtype=torch.int64, device=out136.device) if out_uint is None else out_uint
     with torch.cuda.device(out136.device):
         N.check(lib.fld_decode_regress(N.handle(out136.device), N.ptr(out136), out136.shape[1], N.ptr(faceboxes), B, N.ptr(marks),
                                        N.ptr(marks_u), N.stream_ptr(out136.device)))
@@ -78,15 +80,18 @@ def _template_device(template, device):
     return t
 
 
-def align_device(frames, face2frame, marks, template=None, out_size=(112, 112), five_point=True, return_matrix=True):
+def align_device(frames, face2frame, marks, template=None, out_size=(112, 112), five_point=True, return_matrix=True, out=None,
+                 out_matrix=None):
     """Umeyama fit + cv2.warpAffine-exact warp on device.  marks float32 CUDA [B,N,2] in frame pixels."""
     lib = N.load_library()
     F, H, W, C = frames.shape
     B, Np = marks.shape[0], marks.shape[1]
     t = _template_device(template, frames.device)
     oh, ow = out_size
-    crops = torch.empty((B, oh, ow, C), dtype=torch.uint8, device=frames.device)
-    M = torch.empty((B, 2, 3), dtype=torch.float64, device=frames.device) if return_matrix else None
+    crops = torch.empty((B, oh, ow, C), dtype=torch.uint8, device=frames.device) if out is None else out
+    M = None
+    if return_matrix:
+        M = torch.empty((B, 2, 3), dtype=torch.float64, device=frames.device) if out_matrix is None else out_matrix
     with torch.cuda.device(frames.device):
         N.check(lib.fld_align(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(marks), Np, N.ptr(t),
                               t.shape[0], int(five_point), B, oh, ow, N.ptr(M), N.ptr(crops), N.stream_ptr(frames.device)))
@@ -127,13 +132,34 @@ class LandmarkPipeline:
         self.template = TEMPLATE_112 if template is None else np.asarray(template, dtype=np.float64)
         self.device = _device(device)
         self.input_size = model.input_height
+        self._bufs = {}
         model.compiled(self.device, dtype)
 
-    def run_device(self, frames, boxes, face2frame, want_uint=False):
-        crops128, fb = preprocess_faces_device(frames, boxes, face2frame, self.input_size, True)
-        out = self.model.forward_device(crops128, self.dtype)
-        marks, marks_u = decode_regress_device(out, fb, want_uint)
-        aligned, M = align_device(frames, face2frame, marks, self.template, self.out_size, True, True)
+    def _buffers(self, lane, B, C, dev):
+        """Per-lane result buffers, allocated once per batch size: no allocator traffic (and no allocator-induced stream
+        synchronisation) in the steady state.  They are overwritten by the lane's next run."""
+        key = (lane, B, C)
+        buf = self._bufs.get(key)
+        if buf is None:
+            S, (oh, ow) = self.input_size, self.out_size
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            buf = {"crops": e((B, S, S, 3), torch.uint8), "faceboxes": e((B, 4), torch.int32),
+                   "net_out": e((B, self.model.n_classes), torch.float32), "marks": e((B, 68, 2), torch.float32),
+                   "marks_uint": e((B, 68, 2), torch.int64), "aligned": e((B, oh, ow, C), torch.uint8),
+                   "M": e((B, 2, 3), torch.float64)}
+            self._bufs[key] = buf
+        return buf
+
+    def run_device(self, frames, boxes, face2frame, want_uint=False, lane=0):
+        """Everything is enqueued on the current CUDA stream.  Independent batches may be enqueued on different streams
+        concurrently when each uses its own `lane` (activation workspace + result buffers): the HBM/issue-bound kernels of
+        one batch (crop/resize, FC, decode, warp) then fill the issue slots the tensor-core convs of the other leave idle.
+        The returned tensors belong to the lane and are overwritten by its next run."""
+        b = self._buffers(lane, boxes.shape[0], frames.shape[3], frames.device)
+        crops128, fb = preprocess_faces_device(frames, boxes, face2frame, self.input_size, True, out=b["crops"], out_boxes=b["faceboxes"])
+        out = self.model.forward_device(crops128, self.dtype, out=b["net_out"], lane=lane)
+        marks, marks_u = decode_regress_device(out, fb, want_uint, out=b["marks"], out_uint=b["marks_uint"])
+        aligned, M = align_device(frames, face2frame, marks, self.template, self.out_size, True, True, out=b["aligned"], out_matrix=b["M"])
         return {"marks": marks, "marks_uint": marks_u, "aligned": aligned, "M": M, "faceboxes": fb, "crops": crops128}
 
     def __call__(self, frames, boxes, face2frame=None):
