@@ -3,6 +3,7 @@ called at prediction.py:207.  The resize + normalisation run on the GPU (fld_ima
 cv2.resize of OpenCV 4.13 followed by the reference's float32 arithmetic).  The training data pipeline
 (dataset pairing, augmentation, generators) is out of scope."""
 import os
+import re
 
 import numpy as np
 import six
@@ -62,3 +63,36 @@ def get_image_array(image, width, height, imgNorm="sub_mean", ordering='channels
     if as_tensor:
         return out
     return out.cpu().numpy()
+
+
+def read_keypoints(keypts_path, is_imgaug_kps=False):
+    """Read a .pts landmark file (reference data/generator.py:138-160): `version: V`, `n_points: N`, `{`, one
+    "x y" line per point, `}`.  Returns (float array [N,2], n_points, version string)."""
+    if is_imgaug_kps:
+        raise DataLoaderError("read_keypoints: imgaug Keypoint output belongs to the training pipeline (out of scope here)")
+    keypoints, n_points, version = [], None, None
+    with open(keypts_path, "r") as fp:
+        for line in fp.readlines():
+            _text = line.strip()
+            if re.match(r"{|}", _text):
+                continue
+            if re.match("version", _text):
+                version = re.findall(r"\d+", _text)[0]
+            elif re.match("n_points", _text):
+                n_points = int(re.findall(r"\d+", _text)[0])
+            else:
+                keypoints.append([float(cord) for cord in _text.split()])
+    return np.array(keypoints), n_points, version
+
+
+def write_keypoints(keypts_path, landmarks, version=1):
+    """Write decoded landmarks ([N,2] array-like, x y per row) in the reference's .pts format
+    (scripts/prepare_dataset.py:46-52), so `detect_marks` / heat-map decode results feed the reference's tooling."""
+    pts = np.asarray(landmarks).reshape(-1, 2)
+    with open(keypts_path, "w") as fp:
+        fp.write("version: %d\n" % version)
+        fp.write("n_points: %d\n" % len(pts))
+        fp.write("{\n")
+        for x, y in pts.tolist():
+            fp.write(" ".join([str(x), str(y)]) + "\n")
+        fp.write("}")

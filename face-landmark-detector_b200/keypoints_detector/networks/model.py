@@ -172,14 +172,43 @@ class Model:
         return self
 
     def save_weights(self, path):
-        np.savez(path if path.endswith(".npz") else path + ".npz", **self.weights)
+        """`.safetensors` when the path says so, else `.npz` (appended if missing); keys = `layer/variable` in Keras layouts."""
+        if path.endswith(".safetensors"):
+            from safetensors.numpy import save_file
+            save_file({k: np.ascontiguousarray(v) for k, v in self.weights.items()}, path)
+        else:
+            np.savez(path if path.endswith(".npz") else path + ".npz", **self.weights)
+
+    @staticmethod
+    def normalize_weight_names(arrays):
+        """Map exported Keras variable names onto this build's `layer/variable` keys: drops the `:0`
+        suffix, collapses h5-style `layer/layer/kernel:0` paths, keeps `depthwise_kernel`, `gamma`, `beta`,
+        `moving_mean`, `moving_variance`.  Layer names are the reference's own (`block1_conv1`, `conv_dw_3`,
+        `res2a_branch2a`, `bn_conv1`, ...), so a checkpoint converted elsewhere with TensorFlow drops in by name."""
+        out = {}
+        for k, v in arrays.items():
+            parts = [p for p in k.split(":")[0].split("/") if p]
+            if len(parts) >= 2:
+                k2 = parts[-2] + "/" + parts[-1]
+            else:
+                k2 = parts[0]
+            out[k2] = v
+        return out
 
     def load_weights(self, path):
-        """Weights container of this build: .npz keyed by layer name in Keras layouts (the reference's
-        TF-checkpoint format cannot be read without TensorFlow)."""
-        p = path if os.path.exists(path) else path + ".npz"
-        with np.load(p) as z:
-            self.set_weights({k: z[k] for k in z.files})
+        """Weights container of this build: `.npz` or `.safetensors` keyed by layer name in Keras layouts (the
+        reference's TF-checkpoint format cannot be read without TensorFlow)."""
+        cands = [path, path + ".npz", path + ".safetensors"]
+        p = next((c for c in cands if os.path.isfile(c)), None)
+        if p is None:
+            raise FileNotFoundError("no weights file at %s(.npz|.safetensors)" % path)
+        if p.endswith(".safetensors"):
+            from safetensors.numpy import load_file
+            arrays = load_file(p)
+        else:
+            with np.load(p) as z:
+                arrays = {k: z[k] for k in z.files}
+        self.set_weights(self.normalize_weight_names(arrays))
         return None
 
     # ------------------------------------------------------------------ device side

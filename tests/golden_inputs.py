@@ -65,3 +65,9 @@ def similarity(seed, w=1920, h=1080, out=112):
 
 RESIZE_SHAPES = [(96, 96, 128, 128), (97, 131, 128, 128), (256, 256, 128, 128), (128, 128, 128, 128), (300, 211, 128, 128),
                  (480, 640, 224, 224), (57, 33, 96, 64)]
+
+
+# a .pts landmark file exactly as the reference's writer emits it (scripts/prepare_dataset.py:46-52)
+PTS_POINTS = [(66.03356, 39.00227), (30.22701, 36.42168), (59.58208, 39.6474), (73.13035, 39.96999), (36.35657, 37.38940),
+              (23.45287, 37.38940), (56.95326, 29.03365), (80.22713, 32.22814), (40.22761, 29.00232), (16.35638, 29.64747)]
+PTS_TEXT = "version: 1\nn_points: %d\n{\n" % len(PTS_POINTS) + "".join("%s %s\n" % (str(x), str(y)) for x, y in PTS_POINTS) + "}"

@@ -114,6 +114,17 @@ def main():
         if i == 0:
             out["warp_crop_0"] = crop
 
+    # F. .pts reader (data/generator.py:138-160) on a file in the reference writer's format (scripts/prepare_dataset.py:46-52)
+    import tempfile
+    from keypoints_detector.data.generator import read_keypoints
+    with tempfile.NamedTemporaryFile("w", suffix=".pts", delete=False) as fp:
+        fp.write(gi.PTS_TEXT)
+    kps, n_points, version = read_keypoints(fp.name)
+    os.unlink(fp.name)
+    out["pts_keypoints"] = np.asarray(kps, dtype=np.float64)
+    out["pts_n_points"] = np.array(n_points)
+    out["pts_version"] = np.array(str(version))
+
     os.makedirs(os.path.join(HERE, "golden"), exist_ok=True)
     path = os.path.join(HERE, "golden", "reference_host.npz")
     np.savez_compressed(path, **out)

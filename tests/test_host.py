@@ -193,3 +193,47 @@ def test_encoder_graphs_match_oracle_shapes():
             assert g.shapes[tid] == (r.shape[2], r.shape[3], r.shape[1])
     with pytest.raises(ValueError):
         mobilenet.get_mobilenet_encoder(pretrained="imagenet")
+
+
+def test_pts_reader_writer_against_reference(golden, tmp_path):
+    """.pts files: the reader agrees with the reference's read_keypoints on a file in the reference
+    writer's format (golden minted by tests/make_golden.py), and the writer round-trips decoded landmarks."""
+    import golden_inputs as gi
+    from keypoints_detector.data.generator import read_keypoints, write_keypoints
+    f = tmp_path / "a.pts"
+    f.write_text(gi.PTS_TEXT)
+    kps, n, ver = read_keypoints(str(f))
+    np.testing.assert_array_equal(kps, golden["pts_keypoints"])
+    assert n == int(golden["pts_n_points"]) and ver == str(golden["pts_version"])
+    marks = np.random.default_rng(0).uniform(0, 400, (68, 2))
+    g = tmp_path / "b.pts"
+    write_keypoints(str(g), marks)
+    k2, n2, _ = read_keypoints(str(g))
+    assert n2 == 68
+    np.testing.assert_array_equal(k2, marks)          # str(float) round-trips exactly
+    assert f.read_text().splitlines()[:3] == g.read_text().splitlines()[:1] + ["n_points: 10", "{"]
+
+
+def test_weight_files_npz_safetensors_and_keras_names(tmp_path):
+    """Weight import: .npz and .safetensors round trips; exported Keras variable names
+    (`layer/layer/kernel:0`) map onto the build's keys; shape errors are reported by name."""
+    from keypoints_detector.networks.fcn import fcn_8_mobilenet
+    m = fcn_8_mobilenet(5, 32, 32).init_weights(2)
+    w = m.get_weights()
+    for ext in (".npz", ".safetensors"):
+        path = str(tmp_path / ("w" + ext))
+        m.save_weights(path)
+        m2 = fcn_8_mobilenet(5, 32, 32)
+        m2.load_weights(path)
+        assert set(m2.weights) == set(w)
+        for k in w:
+            np.testing.assert_array_equal(m2.weights[k], w[k])
+    keras_style = {"%s/%s:0" % (k.split("/")[0], k): v for k, v in w.items()}      # model_weights/<layer>/<layer>/<var>:0
+    np.savez(str(tmp_path / "k.npz"), **keras_style)
+    m3 = fcn_8_mobilenet(5, 32, 32)
+    m3.load_weights(str(tmp_path / "k"))
+    np.testing.assert_array_equal(m3.weights["conv_dw_3/depthwise_kernel"], w["conv_dw_3/depthwise_kernel"])
+    bad = dict(w)
+    bad["conv1/kernel"] = bad["conv1/kernel"][..., :8]
+    with pytest.raises(ValueError, match="conv1/kernel"):
+        fcn_8_mobilenet(5, 32, 32).set_weights(bad)
