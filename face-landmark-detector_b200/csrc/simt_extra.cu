@@ -80,6 +80,101 @@ __global__ void add_act_kernel(const TA* __restrict__ a, int AH, int AW, const T
   stv<TOut>(out + i, actf(v, act));
 }
 
+
+// ---- bf16 x 8 fast paths (C % 8 == 0): one thread = one pixel x 8 channels, 16-byte accesses
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+__global__ void dwconv_bf16x8_kernel(const uint4* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                     uint4* __restrict__ out, int B, int IH, int IW, int C8, int OH, int OW, int kh, int kw, int stride,
+                                     int pad_t, int pad_l, int act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * OH * OW * C8) return;
+  const int c8 = (int)(i % C8);
+  long long r = i / C8;
+  const int x = (int)(r % OW); r /= OW;
+  const int y = (int)(r % OH);
+  const int b = (int)(r / OH);
+  const int C = C8 * 8;
+  float acc[8];
+  if (bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  }
+  for (int a = 0; a < kh; ++a) {
+    const int iy = y * stride + a - pad_t;
+    if (iy < 0 || iy >= IH) continue;
+    for (int d = 0; d < kw; ++d) {
+      const int ix = x * stride + d - pad_l;
+      if (ix < 0 || ix >= IW) continue;
+      float v[8];
+      unpack8(__ldg(in + (((size_t)b * IH + iy) * IW + ix) * C8 + c8), v);
+      const float* wp = w + (size_t)(a * kw + d) * C + c8 * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]); acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+      acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]); acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = actf(acc[e], act);
+  out[i] = pack8(acc);
+}
+
+__global__ void maxpool_bf16x8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int IH, int IW, int C8, int OH, int OW,
+                                      int k, int s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * OH * OW * C8) return;
+  const int c8 = (int)(i % C8);
+  long long r = i / C8;
+  const int x = (int)(r % OW); r /= OW;
+  const int y = (int)(r % OH);
+  const int b = (int)(r / OH);
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+  for (int a = 0; a < k; ++a)
+    for (int d = 0; d < k; ++d) {
+      const int iy = y * s + a, ix = x * s + d;
+      if (iy < IH && ix < IW) {
+        float v[8];
+        unpack8(__ldg(in + (((size_t)b * IH + iy) * IW + ix) * C8 + c8), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    }
+  out[i] = pack8(m);   // max of bf16 values is a bf16 value: exact
+}
+
+__global__ void add_bf16x8_kernel(const uint4* __restrict__ a, int AH, int AW, const uint4* __restrict__ b2, int BH, int BW,
+                                  uint4* __restrict__ out, int B, int OH, int OW, int C8, int act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * OH * OW * C8) return;
+  const int c8 = (int)(i % C8);
+  long long r = i / C8;
+  const int x = (int)(r % OW); r /= OW;
+  const int y = (int)(r % OH);
+  const int b = (int)(r / OH);
+  float u[8], v[8];
+  unpack8(__ldg(a + (((size_t)b * AH + y) * AW + x) * C8 + c8), u);
+  unpack8(__ldg(b2 + (((size_t)b * BH + y) * BW + x) * C8 + c8), v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) u[e] = actf(u[e] + v[e], act);
+  out[i] = pack8(u);
+}
+
 unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
 }  // namespace
@@ -88,6 +183,12 @@ int simt_dwconv(const void* in, int in_dtype, const float* w, const float* bias,
                 int OH, int OW, int kh, int kw, int stride, int pad_t, int pad_l, int act, cudaStream_t st) {
   const long long total = (long long)B * OH * OW * C;
   if (total == 0) return FLD_OK;
+  if (in_dtype == FLD_BF16 && out_dtype == FLD_BF16 && C % 8 == 0) {
+    dwconv_bf16x8_kernel<<<blocks_for(total / 8), 256, 0, st>>>((const uint4*)in, w, bias, (uint4*)out, B, IH, IW, C / 8, OH, OW, kh, kw, stride,
+                                                               pad_t, pad_l, act);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
   if (out_dtype == FLD_F32) {
     float* o = (float*)out;
     if (in_dtype == FLD_F32) dwconv_kernel<float, float><<<blocks_for(total), 256, 0, st>>>((const float*)in, w, bias, o, B, IH, IW, C, OH, OW, kh, kw, stride, pad_t, pad_l, act);
@@ -107,6 +208,11 @@ int simt_maxpool2d(const void* in, int in_dtype, void* out, int out_dtype, int B
                    cudaStream_t st) {
   const long long total = (long long)B * OH * OW * C;
   if (total == 0) return FLD_OK;
+  if (in_dtype == FLD_BF16 && out_dtype == FLD_BF16 && C % 8 == 0) {
+    maxpool_bf16x8_kernel<<<blocks_for(total / 8), 256, 0, st>>>((const uint4*)in, (uint4*)out, B, IH, IW, C / 8, OH, OW, k, s);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
   if (out_dtype == FLD_F32) {
     float* o = (float*)out;
     if (in_dtype == FLD_F32) maxpool2d_kernel<float, float><<<blocks_for(total), 256, 0, st>>>((const float*)in, o, B, IH, IW, C, OH, OW, k, s);
@@ -137,6 +243,12 @@ static int add_out(const void* a, int AH, int AW, const void* b, int BH, int BW,
 int simt_add_act(const void* a, int a_dtype, int AH, int AW, const void* b, int b_dtype, int BH, int BW, void* out, int out_dtype, int B,
                  int OH, int OW, int C, int act, cudaStream_t st) {
   if ((long long)B * OH * OW * C == 0) return FLD_OK;
+  if (a_dtype == FLD_BF16 && b_dtype == FLD_BF16 && out_dtype == FLD_BF16 && C % 8 == 0) {
+    add_bf16x8_kernel<<<blocks_for((long long)B * OH * OW * C / 8), 256, 0, st>>>((const uint4*)a, AH, AW, (const uint4*)b, BH, BW, (uint4*)out, B,
+                                                                               OH, OW, C / 8, act);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
   if (a_dtype == FLD_F32 && b_dtype == FLD_F32) return add_out<float, float>(a, AH, AW, b, BH, BW, out, out_dtype, B, OH, OW, C, act, st);
   if (a_dtype == FLD_F32 && b_dtype == FLD_BF16) return add_out<float, __nv_bfloat16>(a, AH, AW, b, BH, BW, out, out_dtype, B, OH, OW, C, act, st);
   if (a_dtype == FLD_BF16 && b_dtype == FLD_F32) return add_out<__nv_bfloat16, float>(a, AH, AW, b, BH, BW, out, out_dtype, B, OH, OW, C, act, st);

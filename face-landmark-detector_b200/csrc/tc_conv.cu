@@ -34,6 +34,8 @@ struct TmaConvParams {
   void* out;
   int B, OH, OW, Cout; // conv output (pre-pool) dims
   int Cin, kh, kw, pad_t, pad_l;
+  int IH;              // input rows (tap skipping)
+  int st;              // conv stride (1, or 2 for 1x1 convs: the tensor map's element strides pick every second pixel)
   int TW, TH, NB;      // M tile = TW*TH*NB = 128 pixels
   int BN, cout_pad, n_ntiles;
   int tiles_x, tiles_y, tiles_b, total_tiles;
@@ -53,6 +55,16 @@ constexpr int kTraceN = 2048;
     if (p.trace && blockIdx.x == 0 && lane == 0 && (idx) < kTraceN)                                                   \
       p.trace[(role) * kTraceN + (idx)++] = ((unsigned long long)clock64() << 4) | (tag);                             \
   } while (0)
+
+// Kernel rows whose input rows fall into the zero padding for EVERY output row of the tile contribute nothing and are
+// skipped; producer and MMA issuer derive the same range.  With one output row per tile (small maps under the 7x7 'same'
+// head, fcn.py:98) this removes 12 of 49 taps on a 7x7 map.
+__device__ __forceinline__ void ky_range(const TmaConvParams& p, int ty, int& lo, int& hi) {
+  const int r0 = ty * p.TH * p.st, r1 = r0 + (p.TH - 1) * p.st;
+  lo = max(0, p.pad_t - r1);
+  hi = min(p.kh - 1, p.IH - 1 + p.pad_t - r0);
+  if (hi < lo) { lo = 0; hi = p.kh - 1; }
+}
 
 template <bool OUT_F32>
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -82,7 +94,6 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
 
   const int kchunks = p.Cin >> 6;
-  const int kblocks = p.kh * p.kw * kchunks;
   const int mtiles = p.tiles_x * p.tiles_y * p.tiles_b;
 
   if (warp == 0) {
@@ -96,9 +107,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int tb = m / (p.tiles_x * p.tiles_y);
       m -= tb * (p.tiles_x * p.tiles_y);
       const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
-      const int x0 = tx * p.TW - p.pad_l, y0 = ty * p.TH - p.pad_t, b0 = tb * p.NB, n0 = nt * p.BN;
-      int wrow = n0;                            // row of the [taps*cout_pad][Cin] weight matrix
-      for (int ky = 0; ky < p.kh; ++ky) {
+      const int x0 = tx * p.TW * p.st - p.pad_l, y0 = ty * p.TH * p.st - p.pad_t, b0 = tb * p.NB, n0 = nt * p.BN;
+      int ky_lo, ky_hi;
+      ky_range(p, ty, ky_lo, ky_hi);
+      int wrow = n0 + ky_lo * p.kw * p.cout_pad;  // row of the [taps*cout_pad][Cin] weight matrix
+      for (int ky = ky_lo; ky <= ky_hi; ++ky) {
         for (int kx = 0; kx < p.kw; ++kx, wrow += p.cout_pad) {
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -136,12 +149,20 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       TRACE(1, ti, 0);
+      int kblocks_t;
+      {
+        const int m = tile % mtiles;
+        const int ty = (m % (p.tiles_x * p.tiles_y)) / p.tiles_x;
+        int ky_lo, ky_hi;
+        ky_range(p, ty, ky_lo, ky_hi);
+        kblocks_t = (ky_hi - ky_lo + 1) * p.kw * kchunks;
+      }
       mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
       TRACE(1, ti, 3);
       tc_fence_after();
       const uint32_t d = tmem_base + acc * 256;
       uint32_t accum = 0;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = 0; kb < kblocks_t; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
         TRACE(1, ti, 1);
         tc_fence_after();
@@ -158,7 +179,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           TRACE(1, ti, 7);
           umma_commit(empty0 + 8 * stage);                       // stage reusable once these MMAs have read it
-          if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+          if (kb == kblocks_t - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
           TRACE(1, ti, 8);
         }
         accum = 1u;
@@ -241,7 +262,9 @@ struct TcConvPlan {
 };
 
 bool tc_conv_supported(const ConvGeom& g) {
-  if (g.stride != 1 || g.Cin % 64 != 0 || g.Cin < 64) return false;
+  if (g.Cin % 64 != 0 || g.Cin < 64) return false;
+  // stride 2 only for 1x1 / no padding (ResNet50's down-sampling convs, resnet50.py:98,110): the TMA box itself strides
+  if (g.stride != 1 && !(g.stride == 2 && g.kh == 1 && g.kw == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pool == 0)) return false;
   if (g.pool != 0 && g.pool != 2) return false;
   if (g.pool == 2 && (g.Cout % 8 != 0)) return false;
   if (g.kh * g.kw > 64) return false;
@@ -257,13 +280,16 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.bias = nullptr; p.out = nullptr;
   p.B = B; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout;
   p.Cin = g.Cin; p.kh = g.kh; p.kw = g.kw; p.pad_t = g.pad_t; p.pad_l = g.pad_l;
+  p.st = g.stride; p.IH = g.IH;
   p.act = g.act; p.pool = g.pool;
   { const char* e = getenv("FLD_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.trace = nullptr;
   // M-tile geometry: TW*TH*NB = 128 pixels, TW in {4, 8}: the pool partners are lane^1 and lane^TW
   const int TW = g.OW > 4 ? 8 : 4;
-  int TH = 2;
-  while (TH * 2 <= 128 / TW && TH < g.OH) TH *= 2;
+  // one output row per tile under a tall padded kernel on a small map: most kernel rows of the border rows multiply padding
+  const bool row_tiles = g.pool == 0 && g.kh >= 5 && g.pad_t > 0 && g.OH <= 16 && !getenv("FLD_TC_ROWTILES_OFF");
+  int TH = row_tiles ? 1 : 2;
+  while (!row_tiles && TH * 2 <= 128 / TW && TH < g.OH) TH *= 2;
   const int NB = 128 / (TW * TH);
   p.TW = TW; p.TH = TH; p.NB = NB;
   // N tile
@@ -283,8 +309,10 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.IW * g.Cin * 2, (cuuint64_t)g.IH * g.IW * g.Cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // boxDim counts TRAVERSED elements: with element stride s the box loads ceil(boxDim / s) pixels per spatial dimension
+    const cuuint32_t s = (cuuint32_t)g.stride;
+    cuuint32_t box[4] = {64, (cuuint32_t)TW * s, (cuuint32_t)TH * s, (cuuint32_t)NB};
+    cuuint32_t es[4] = {1, s, s, 1};
     CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -300,6 +300,8 @@ def test_tc_conv_layers_against_torch(dev):
     run(64, 48, 64, [("conv2", 64, 3, (1, 1, 1, 1), R, 0), ("conv3", 128, 3, (1, 1, 1, 1), R, 2)], 2)       # un-pooled, ragged tiles
     run(28, 28, 64, [("head7", 512, 7, "same", R, 0), ("head1", 512, 1, (0, 0, 0, 0), R, 0), ("score", 68, 1, (0, 0, 0, 0), 0, 0)], 2)
     run(16, 16, 128, [("conv2", 256, 3, (1, 1, 1, 1), R, 2), ("conv3", 256, 3, (1, 1, 1, 1), R, 2)], 5)     # 4x4 / 2x2 maps, NB > 1
+    run(7, 7, 256, [("head7", 512, 7, "same", R, 0), ("head1", 256, 1, (0, 0, 0, 0), R, 0)], 19)           # one-row tiles, skipped kernel rows, ragged batch
+    run(3, 5, 64, [("head7", 128, 5, "same", R, 0)], 3)                                                    # TW = 8 on a 5-wide map, 3 rows
 
 
 # ------------------------------------------------------------------------------------------------ a6 FCN
