@@ -205,6 +205,25 @@ def run_reference(args, rank, world):
     return 0
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host memory is allocated, so the
+    pinned frame / result buffers are first-touched on the GPU's NUMA node (the e2e leg is host-link-bound).
+    Returns the number of CPUs bound to, or None when NVML gives no usable mask."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args, rank, world, local_rank):
     from keypoints_detector import _native, prediction
@@ -217,6 +236,8 @@ def run_gpu(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    bound_cpus = bind_to_gpu_numa_node(local_rank)
     B = args.batch
     dtype = "bfloat16" if args.dtype == "bf16" else "float32"
     model = landmark_regressor().init_weights(seed=0)
@@ -370,6 +391,7 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0:
         cpu = None
         if not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)             # the CPU leg gets every host core again
             fps, cms, cores = time_cpu(64, 3, 1)
             cpu = {"value": fps, "unit": "faces/s", "cores": cores, "kind": "port",
                    "sample": "3 steps x 64 faces of the same workload: cv2.resize+cvtColor, torch-CPU fp32 restatement of the Keras "
@@ -384,7 +406,7 @@ def run_gpu(args, rank, world, local_rank):
                            "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2; activations workspace rewritten every step"
                                  % (n_sets, n_sets * set_bytes / 1e6)},
                 "e2e": {"value": e2e_val, "unit": "faces/s", "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_link, "h2d_link_GBps": link_gbps,
+                        "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_link, "h2d_link_GBps": link_gbps, "cpus_bound": bound_cpus,
                         "note": "H2D of the step's frames alone takes h2d_only_ms_per_step on this box; the leg is host-link-bound when that "
                                 "is close to ms_per_step"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}

@@ -133,6 +133,7 @@ class LandmarkPipeline:
         self.device = _device(device)
         self.input_size = model.input_height
         self._bufs = {}
+        self.max_batch = 4096
         model.compiled(self.device, dtype)
 
     def _buffers(self, lane, B, C, dev):
@@ -154,13 +155,36 @@ class LandmarkPipeline:
         """Everything is enqueued on the current CUDA stream.  Independent batches may be enqueued on different streams
         concurrently when each uses its own `lane` (activation workspace + result buffers): the HBM/issue-bound kernels of
         one batch (crop/resize, FC, decode, warp) then fill the issue slots the tensor-core convs of the other leave idle.
-        The returned tensors belong to the lane and are overwritten by its next run."""
-        b = self._buffers(lane, boxes.shape[0], frames.shape[3], frames.device)
-        crops128, fb = preprocess_faces_device(frames, boxes, face2frame, self.input_size, True, out=b["crops"], out_boxes=b["faceboxes"])
-        out = self.model.forward_device(crops128, self.dtype, out=b["net_out"], lane=lane)
-        marks, marks_u = decode_regress_device(out, fb, want_uint, out=b["marks"], out_uint=b["marks_uint"])
-        aligned, M = align_device(frames, face2frame, marks, self.template, self.out_size, True, True, out=b["aligned"], out_matrix=b["M"])
-        return {"marks": marks, "marks_uint": marks_u, "aligned": aligned, "M": M, "faceboxes": fb, "crops": crops128}
+        The returned tensors belong to the lane and are overwritten by its next run.  Batches larger than `max_batch`
+        are processed in chunks (bounded activation workspace), results land in one buffer."""
+        B = boxes.shape[0]
+        b = self._buffers(lane, B, frames.shape[3], frames.device)
+        for s0 in range(0, max(B, 1), self.max_batch):
+            s1 = min(B, s0 + self.max_batch)
+            crops128, fb = preprocess_faces_device(frames, boxes[s0:s1], face2frame[s0:s1], self.input_size, True,
+                                                   out=b["crops"][s0:s1], out_boxes=b["faceboxes"][s0:s1])
+            out = self.model.forward_device(crops128, self.dtype, out=b["net_out"][s0:s1], lane=lane)
+            marks, marks_u = decode_regress_device(out, fb, want_uint, out=b["marks"][s0:s1], out_uint=b["marks_uint"][s0:s1])
+            align_device(frames, face2frame[s0:s1], marks, self.template, self.out_size, True, True, out=b["aligned"][s0:s1],
+                         out_matrix=b["M"][s0:s1])
+        return {"marks": b["marks"], "marks_uint": b["marks_uint"] if want_uint else None, "aligned": b["aligned"], "M": b["M"],
+                "faceboxes": b["faceboxes"], "crops": b["crops"]}
+
+    def capture(self, frames, boxes, face2frame, want_uint=False, lane=0):
+        """Record one run over FIXED input buffers into a CUDA graph (small batches are launch-bound: ~12 kernels plus the
+        Python shim per run).  Returns (graph, results): refill `frames` / `boxes` / `face2frame` in place, call
+        `graph.replay()`, read `results` (the lane's buffers)."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):            # warm-up outside the capture: plans, workspaces, buffers get created
+                self.run_device(frames, boxes, face2frame, want_uint, lane)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self.run_device(frames, boxes, face2frame, want_uint, lane)
+        return g, res
 
     def __call__(self, frames, boxes, face2frame=None):
         """NumPy in / NumPy out convenience (H2D, run, D2H)."""

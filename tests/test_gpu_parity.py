@@ -410,6 +410,38 @@ def test_pipeline_end_to_end(dev):
         prediction.detect_marks(frames[0], m, [2, 2, 60, 200])                 # squared box leaves the image on the left
 
 
+def test_pipeline_chunks_lanes_and_graph_bit_identical(dev):
+    """Size-independent properties of the batched pipeline (config C5): chunked execution (max_batch), a second lane on its
+    own stream and a replayed CUDA graph all give results bit-identical to one plain run."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    frames = T(synthetic.make_frames(2, 480, 640, seed=31), dev)
+    boxes = T(synthetic.make_boxes(70, 480, 640, seed=32, max_side=300), dev)
+    f2f = T((np.arange(70) % 2).astype(np.int32), dev)
+    pipe = prediction.LandmarkPipeline(_regressor(9), dtype="bfloat16")
+    keys = ("marks", "aligned", "M", "faceboxes", "crops")
+    ref = {k: v.clone() for k, v in pipe.run_device(frames, boxes, f2f).items() if k in keys}
+    pipe.max_batch = 32                                                          # 32 + 32 + 6
+    got = pipe.run_device(frames, boxes, f2f)
+    for k in keys:
+        assert torch.equal(got[k], ref[k]), k
+    pipe.max_batch = 4096
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        got1 = pipe.run_device(frames, boxes, f2f, lane=1)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for k in keys:
+        assert torch.equal(got1[k], ref[k]), k
+    g, res = pipe.capture(frames, boxes, f2f, lane=2)
+    for k in keys:
+        res[k].zero_()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    for k in keys:
+        assert torch.equal(res[k], ref[k]), k
+
+
 def test_multi_gpu_shards_bit_identical(dev):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
