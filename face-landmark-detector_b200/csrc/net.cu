@@ -347,7 +347,8 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     const LayerRt& L = net->layers[i];
     const TensorInfo& a = net->tensors[L.d.in0];
     if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
-    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) m = std::max(m, tc_deconv_scratch_bytes(B, a.h, a.w, a.c));
+    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
+      m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
   }
   return m;
 }
@@ -375,7 +376,8 @@ extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
 
 extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, int hw, int L, int64_t* class_map, fld_stream stream);
 
-static int net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, int64_t* cmap_out, fld_stream stream) {
+static int net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, int64_t* cmap_out, fld_stream stream,
+                       double* xy_out = nullptr, double xy_thresh = 0.0) {
   FLD_REQUIRE(net, "fld_net_forward: null net");
   int rc = fld_enter(net->h);
   if (rc) return rc;
@@ -392,7 +394,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   std::vector<void*> ptr(nT);
   ptr[0] = const_cast<void*>(in);
   float* dense_scratch = nullptr;
-  bool cmap_done = false;
+  bool cmap_done = false, xy_done = false;
   {
     size_t off = 0;
     for (int t = 1; t < nT; ++t) {
@@ -445,8 +447,9 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         if (L.path == PATH_TC_TMA) {
           // fused decode: 1 = softmax written into the (skipped) SOFTMAX layer's tensor, 2 = int64 class map to the caller
           const bool last_pair = L.dc_fuse_softmax && (int)i + 2 == (int)net->layers.size();
-          const int mode = L.dc_fuse_softmax ? ((cmap_out && last_pair) ? 2 : 1) : 0;
-          void* dst = mode == 2 ? (void*)cmap_out : (mode == 1 ? ptr[i + 2] : pout);
+          const int mode = L.dc_fuse_softmax ? ((xy_out && last_pair) ? 3 : (cmap_out && last_pair) ? 2 : 1) : 0;
+          void* dst = mode == 3 ? (void*)xy_out : mode == 2 ? (void*)cmap_out : (mode == 1 ? ptr[i + 2] : pout);
+          float* acc = (float*)((char*)dense_scratch + align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256));
           TcDeconvPlan* plan = nullptr;
           for (auto& pe : L.dplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
           if (!plan) {
@@ -455,8 +458,9 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
             if (L.dplans.size() >= 8) { tc_deconv_plan_destroy(L.dplans.front().plan); L.dplans.erase(L.dplans.begin()); }
             L.dplans.push_back({B, (const void*)dense_scratch, plan});
           }
-          rc = tc_deconv_run(plan, (const float*)pin, dst, mode, st);
+          rc = tc_deconv_run(plan, (const float*)pin, dst, mode, st, acc, xy_thresh);
           if (mode == 2) cmap_done = true;
+          if (mode == 3) xy_done = true;
         } else if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
         else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
@@ -507,6 +511,12 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
     rc = fld_decode_classmap(net->h, (const float*)ptr[nT - 1], B, o.h * o.w, o.c, cmap_out, stream);
     if (rc) return rc;
   }
+  if (xy_out && !xy_done) {  // no fused centroid available: soft-centroid decode of the final tensor
+    const TensorInfo& o = net->tensors[nT - 1];
+    FLD_REQUIRE(o.dtype == FLD_F32, "fld_net_forward_landmarks: final tensor must be fp32");
+    rc = fld_decode_heatmap_xy(net->h, (const float*)ptr[nT - 1], B, o.h, o.w, o.c, 0, xy_thresh, xy_out, stream);
+    if (rc) return rc;
+  }
   if (out && !direct_out) {
     const TensorInfo& o = net->tensors[nT - 1];
     const size_t n = o.elems() * (size_t)B;
@@ -514,6 +524,12 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
     else { rc = simt_cvt_bf16_f32(ptr[nT - 1], out, (long long)n, st); if (rc) return rc; }
   }
   return FLD_OK;
+}
+
+extern "C" int fld_net_forward_landmarks(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, double thresh, double* xy,
+                                         fld_stream stream) {
+  FLD_REQUIRE(xy, "fld_net_forward_landmarks: null output");
+  return net_forward(net, in, B, workspace, ws_bytes, nullptr, nullptr, stream, xy, thresh);
 }
 
 extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {

@@ -72,5 +72,7 @@ void tc_deconv_pack_weights(const float* w_phase /*[s*s][2][2][Cin][Cout]*/, int
 int tc_deconv_plan_create(const fld_handle* h, void* scratch, const __nv_bfloat16* w_packed, int B, int IH, int IW, int Cin, int Cout,
                           int s, TcDeconvPlan** out);
 void tc_deconv_plan_destroy(TcDeconvPlan* p);
-// mode 0: fp32 logits, 1: softmax probabilities, 2: int64 argmax class map
-int tc_deconv_run(const TcDeconvPlan* p, const float* in, void* out, int mode, cudaStream_t st);
+// mode 0: fp32 logits, 1: softmax probabilities, 2: int64 argmax class map,
+// 3: fused soft centroid of the softmax output -> out = double [B][Cout][2] (x, y), acc = fp32 scratch of tc_deconv_acc_bytes
+size_t tc_deconv_acc_bytes(int B, int Cout);
+int tc_deconv_run(const TcDeconvPlan* p, const float* in, void* out, int mode, cudaStream_t st, float* acc = nullptr, double thresh = 0.0);

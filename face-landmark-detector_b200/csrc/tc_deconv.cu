@@ -42,7 +42,8 @@ struct DeconvParams {
   int n_ntiles, mtiles, total_tiles;
   int nsplit, cn, units;  // work unit = (M tile, run of cn consecutive N tiles); units = mtiles * nsplit
   int stages;
-  int mode;             // 0 logits, 1 softmax probabilities, 2 int64 argmax class map
+  int mode;             // 0 logits, 1 softmax probabilities, 2 int64 argmax class map, 3 per-class soft-centroid sums
+  float* acc;           // mode 3: [B][Cout][3] fp32 (sum p, sum p*col, sum p*row), accumulated with atomics
   unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
 };
 
@@ -234,7 +235,7 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
 
       float inv = 1.0f;
-      if (p.mode == 1) {
+      if (p.mode == 1 || p.mode == 3) {
         float mx = -INFINITY;
 #pragma unroll
         for (int k = 0; k < 3; ++k)
@@ -273,8 +274,59 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (c + e < Cout) asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + (c + e) * 4), "f"(__uint_as_float(rg[k][4 * q + e]) * inv) : "memory");
           }
         }
-      goff[half][r] = valid ? opix * Cout : -1;
+      if (p.mode == 3) {
+        // pixel meta for the reduction: (float column, float row) of this thread's output pixel (utils/metrics.py:57-64 grids)
+        const float2 xyf = make_float2((float)(ox * p.s + bq), (float)(oy * p.s + a));
+        goff[half][r] = *reinterpret_cast<const long long*>(&xyf);
+      } else {
+        goff[half][r] = valid ? opix * Cout : -1;
+      }
       named_bar_sync(1 + half, 128);
+      if (p.mode == 3) {
+        // Fused soft centroid (get_average_xy with n_points < 1 on the softmax output): thread c sums class c over the tile's
+        // pixels (conflict-free column walk through the staging block) and adds the three sums to acc[b][c][:].  A tile of 128
+        // flat rows spans at most two images (runs [0, split) and [split, nvalid)).  The probabilities never leave the SM.
+        if (gt < Cout) {
+          const float* sp = reinterpret_cast<const float*>(__cvta_shared_to_generic((size_t)stg)) + gt;   // column gt of [128][Cout]
+          const long long g0 = (long long)mt * 128;
+          const int per = p.GH * p.GW;
+          const long long b0 = g0 / per;
+          const int nvalid = (int)min((long long)128, p.M - g0);
+          const int split = (int)min((long long)nvalid, (b0 + 1) * per - g0);
+          int lo = 0, hi = split;
+#pragma unroll 1
+          for (int run = 0; run < 2; ++run) {
+            if (hi > lo) {
+              float s0[2] = {0.f, 0.f}, sx[2] = {0.f, 0.f}, sy[2] = {0.f, 0.f};
+              int px = lo;
+              for (; px + 8 <= hi; px += 8) {
+                float v[8];
+                float2 m[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  v[e] = sp[(px + e) * Cout];
+                  m[e] = *reinterpret_cast<const float2*>(&goff[half][px + e]);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  s0[e & 1] += v[e];
+                  sx[e & 1] = fmaf(v[e], m[e].x, sx[e & 1]);
+                  sy[e & 1] = fmaf(v[e], m[e].y, sy[e & 1]);
+                }
+              }
+              for (; px < hi; ++px) {
+                const float v = sp[px * Cout];
+                const float2 m = *reinterpret_cast<const float2*>(&goff[half][px]);
+                s0[0] += v; sx[0] = fmaf(v, m.x, sx[0]); sy[0] = fmaf(v, m.y, sy[0]);
+              }
+              float* d = p.acc + ((size_t)(b0 + run) * Cout + gt) * 3;
+              atomicAdd(d, s0[0] + s0[1]); atomicAdd(d + 1, sx[0] + sx[1]); atomicAdd(d + 2, sy[0] + sy[1]);
+            }
+            lo = split; hi = nvalid;
+          }
+        }
+        continue;
+      }
       // copy-out: consecutive threads write consecutive pieces of each pixel's contiguous Cout*4-byte run
       int px = px0, q = q0;
       if (COUT && vec) {
@@ -345,6 +397,17 @@ __global__ void deconv_im2col_kernel(const float* __restrict__ in, __nv_bfloat16
   A[i] = __floats2bfloat162_rn(v[0], v[1]);
 }
 
+// (x, y) = (sum p*col / sum p, sum p*row / sum p); (-1, -1) when mean(p) <= thresh (utils/metrics.py:78-80)
+__global__ void centroid_finish_kernel(const float* __restrict__ acc, long long n, double hw, double thresh, double* __restrict__ xy) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s0 = acc[i * 3], sx = acc[i * 3 + 1], sy = acc[i * 3 + 2];
+  double x = sx / s0, y = sy / s0;
+  if (s0 / hw <= thresh) { x = -1.0; y = -1.0; }
+  xy[i * 2] = x;
+  xy[i * 2 + 1] = y;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -413,7 +476,7 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
   const size_t fixed = fixed_smem(Cin, Cout);
   const size_t b_bytes = (size_t)p.BN * 128;
   p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
-  p.mode = 0; p.trace = nullptr;
+  p.mode = 0; p.trace = nullptr; p.acc = nullptr;
   pl->smem = fixed + (size_t)p.stages * b_bytes;
   // work units: the smallest split of the N range that still gives every SM a few units
   p.nsplit = 1;
@@ -448,7 +511,9 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
 void tc_deconv_plan_destroy(TcDeconvPlan* p) { delete p; }
 
 // in: fp32 NHWC [B][h][w][C]; out: mode 0/1 fp32 [B][(h+1)s][(w+1)s][Cout], mode 2 int64 [B][(h+1)s][(w+1)s]
-int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st) {
+size_t tc_deconv_acc_bytes(int B, int Cout) { return (size_t)B * Cout * 3 * sizeof(float); }
+
+int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st, float* acc, double thresh) {
   if (pl->p.total_tiles == 0) return FLD_OK;
   {
     const long long n = pl->p.M * (pl->Kp / 2);
@@ -456,7 +521,12 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
     FLD_LAUNCHED();
   }
   DeconvParams p = pl->p;
-  p.out = out; p.mode = mode; p.trace = nullptr;
+  p.out = out; p.mode = mode; p.trace = nullptr; p.acc = acc;
+  if (mode == 3) {
+    if (!acc) { fld_set_error("tc_deconv: mode 3 needs an accumulator buffer"); return FLD_ERR_INVALID; }
+    if (pl->p.GH * pl->p.s > 65535 || pl->p.GW * pl->p.s > 65535) { fld_set_error("tc_deconv: map too large for the fused centroid"); return FLD_ERR_INVALID; }
+    FLD_CUDA(cudaMemsetAsync(acc, 0, tc_deconv_acc_bytes(pl->B, pl->p.Cout), st));
+  }
   if (getenv("FLD_TC_TRACE")) {
     static unsigned long long* tbuf = nullptr;
     if (!tbuf) FLD_CUDA(cudaMalloc(&tbuf, 3 * kTraceN * 8));
@@ -477,6 +547,12 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
     deconv_gemm_kernel<0><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
   }
   FLD_LAUNCHED();
+  if (mode == 3) {
+    const long long n = (long long)pl->B * p.Cout;
+    const double hw = (double)(p.GH * p.s) * (double)(p.GW * p.s);
+    centroid_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, n, hw, thresh, (double*)out);
+    FLD_LAUNCHED();
+  }
   if (p.trace) {  // dump CTA 0's event log: "<role> <tag> <clock>" per line
     static int n_dump = 0;
     std::vector<unsigned long long> hbuf(3 * kTraceN);

@@ -352,6 +352,33 @@ class Model:
             N.check(lib.fld_net_forward_classmap(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(cmap), N.stream_ptr(dev)))
         return cmap
 
+    def forward_landmarks_device(self, x, dtype=None, thresh=0.0, lane=0):
+        """Segmentation models: forward + soft-centroid decode of every class channel (reference utils/metrics.py:46-109,
+        get_average_xy with n_points < 1 over transfer_target's channels) in one call -> float64 CUDA [B, 2L] =
+        (x0, y0, x1, y1, ...).  In bfloat16 mode the sums are accumulated inside the last transposed conv's epilogue
+        (config C3's fused soft-argmax): the probabilities never reach HBM."""
+        assert self.kind == "segmentation"
+        lib = N.load_library()
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != self.graph.input_shape:
+            raise ValueError("input shape %s != model input %s" % (tuple(x.shape[1:]), self.graph.input_shape))
+        dev = x.device.index
+        with torch.cuda.device(dev):
+            net = self.compiled(dev, dtype)
+            comp = self._compute_code(dtype)
+            need = lib.fld_net_workspace_bytes(net, B)
+            ws = self._ws.get((dev, comp, lane))
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+                self._ws[(dev, comp, lane)] = ws
+            base = ws.data_ptr()
+            al = (-base) % 1024
+            xy = torch.empty((B, 2 * self.graph.shapes[-1][2]), dtype=torch.float64, device=x.device)
+            N.check(lib.fld_net_forward_landmarks(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, float(thresh), N.ptr(xy),
+                                                  N.stream_ptr(dev)))
+        return xy
+
     def intermediate(self, x, tensor, dtype=None):
         """Run forward and return intermediate tensor `tensor` ([B,h,w,c] float32 CUDA) — parity checks of the levels."""
         out, ws, al = self.forward_device(x, dtype, return_workspace=True)

@@ -359,6 +359,37 @@ def test_fcn8_fused_classmap(dev):
         assert (cm.cpu().numpy() == ref).mean() > rate
 
 
+def test_fcn8_fused_soft_centroid(dev):
+    """fld_net_forward_landmarks (config C3's fused soft-argmax): per-class soft centroid of the softmax output.  fp32 mode
+    = forward + fld_decode_heatmap_xy (bit-identical); bf16 mode accumulates the sums inside the tensor-core up8 epilogue:
+    equal to the stand-alone decode of the same mode's probabilities to 1e-3 px, and within the 0.5 px bf16 bar of the
+    reference formula (utils/metrics.py:56-64) evaluated on the fp64 oracle's probabilities."""
+    from keypoints_detector.networks.fcn import fcn_8
+    from keypoints_detector.data.generator import get_image_array
+    from keypoints_detector.utils import metrics
+    from oracle import cnn as o_cnn
+    m = fcn_8(68, input_height=64, input_width=96).init_weights(5)
+    imgs = [gi.image(90 + i, 120, 160) for i in range(3)]
+    x = np.stack([get_image_array(im, 96, 64, ordering="channels_last") for im in imgs])
+    pr = o_cnn.fcn_forward(x.astype(np.float64), m.weights, "fcn_8", torch.float64).reshape(3, 72, 104, 68)
+    ref = np.empty((3, 68, 2))
+    ref[..., 0] = (pr * np.arange(104)[None, None, :, None]).sum((1, 2)) / pr.sum((1, 2))
+    ref[..., 1] = (pr * np.arange(72)[None, :, None, None]).sum((1, 2)) / pr.sum((1, 2))
+    xt = T(x, dev)
+    for dtype, tol in (("float32", 0.05), ("bfloat16", 0.5)):
+        xy = m.forward_landmarks_device(xt, dtype)
+        assert xy.dtype == torch.float64 and tuple(xy.shape) == (3, 136)
+        probs = m.forward_device(xt, dtype).view(3, 72, 104, 68)
+        alone = metrics.heatmap_xy_device(probs.contiguous(), 0, 0.0)
+        if dtype == "float32":
+            assert torch.equal(xy, alone)
+        else:
+            assert (xy - alone).abs().max().item() < 1e-3
+        assert np.abs(xy.cpu().numpy().reshape(3, 68, 2) - ref).max() < tol
+    # sentinel: mean probability 1/68 <= thresh -> (-1, -1) for every class
+    assert (m.forward_landmarks_device(xt, "bfloat16", thresh=0.5) == -1).all()
+
+
 def test_prediction_dropin_fcn(dev, tmp_path):
     """keypts_predict / _prediction / model_from_checkpoint_path round trip (reference prediction.py:116-222)."""
     from keypoints_detector import prediction
