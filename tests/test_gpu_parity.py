@@ -473,6 +473,46 @@ def test_pipeline_chunks_lanes_and_graph_bit_identical(dev):
         assert torch.equal(res[k], ref[k]), k
 
 
+def test_full_size_properties_c3_c5(dev):
+    """Size-independent properties at BASELINE.json's sizes (no oracle can run these in seconds):
+    C3  fcn_8/vanilla @224x224, 68 classes, batch 64: probabilities sum to 1, the fused class map equals the argmax of the
+        materialised probabilities (exact ties aside), the fused soft centroid equals the stand-alone decode, and a permuted
+        batch gives the permuted result bit for bit (no cross-image coupling anywhere in the path);
+    C5  5000 faces through the regression pipeline (crosses the 4096-face chunk boundary) equal the same faces run in
+        two halves, bit for bit."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.fcn import fcn_8
+    from keypoints_detector.utils import metrics
+    m = fcn_8(68, input_height=224, input_width=224).init_weights(3)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn((64, 224, 224, 3), generator=g) * 50).to(dev)
+    probs = m.forward_device(x, "bfloat16")
+    assert tuple(probs.shape) == (64, 232 * 232, 68)
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-4
+    cm = m.forward_classmap_device(x, "bfloat16")
+    assert (cm.view(64, -1) == probs.argmax(-1)).float().mean().item() > 0.9995
+    xy = m.forward_landmarks_device(x, "bfloat16")
+    alone = metrics.heatmap_xy_device(probs.view(64, 232, 232, 68), 0, 0.0)
+    assert (xy - alone).abs().max().item() < 2e-3
+    perm = torch.randperm(64, generator=g).to(dev)
+    cm_p = m.forward_classmap_device(x[perm].contiguous(), "bfloat16")
+    assert torch.equal(cm_p, cm[perm])
+    del probs, cm, cm_p, alone
+    torch.cuda.empty_cache()
+
+    frames = T(synthetic.make_frames(8, 480, 640, seed=41), dev)
+    boxes = T(synthetic.make_boxes(5000, 480, 640, seed=42, max_side=300), dev)
+    f2f = T((np.arange(5000) % 8).astype(np.int32), dev)
+    pipe = prediction.LandmarkPipeline(_regressor(9), dtype="bfloat16")
+    keys = ("marks", "aligned", "M")
+    full = {k: v.clone() for k, v in pipe.run_device(frames, boxes, f2f).items() if k in keys}
+    for lo, hi in ((0, 2500), (2500, 5000)):
+        part = pipe.run_device(frames, boxes[lo:hi].contiguous(), f2f[lo:hi].contiguous(), lane=1)
+        for k in keys:
+            assert torch.equal(part[k], full[k][lo:hi]), (k, lo)
+
+
 def test_multi_gpu_shards_bit_identical(dev):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
