@@ -275,14 +275,29 @@ def run_gpu(args, rank, world, local_rank):
     # convs of the other.  Every step still runs completely inside the timed region.
     n_lanes = max(1, args.lanes)
     lane_streams = [torch.cuda.Stream(dev) for _ in range(n_lanes)]
+    model_profiling = [False]                                 # the per-layer event pass runs eagerly
+
+    # Each (input set, lane) pair is recorded once into a CUDA graph (LandmarkPipeline.capture): a step is then ONE launch
+    # from the host instead of ~12 ctypes calls, which otherwise cost as much host time as the step takes on the GPU.
+    use_graph = not args.no_graph
+    if n_sets % n_lanes != 0:
+        n_sets -= n_sets % n_lanes                            # set s always runs on lane s % n_lanes
+    launches_per_step = None
+    graphs = []
+    if use_graph:
+        for sidx in range(n_sets):
+            l_before = _native.launch_count()
+            g, _ = pipe.capture(*dev_sets[sidx], lane=sidx % n_lanes)
+            launches_per_step = (_native.launch_count() - l_before) // 2     # capture() = one warm-up run + the recorded run
+            graphs.append(g)
 
     def step_resident(k):
-        if n_lanes == 1:
-            pipe.run_device(*dev_sets[k % n_sets])
-            return
         ln = k % n_lanes
         with torch.cuda.stream(lane_streams[ln]):
-            pipe.run_device(*dev_sets[k % n_sets], lane=ln)
+            if use_graph and not model_profiling[0]:
+                graphs[k % n_sets].replay()
+            else:
+                pipe.run_device(*dev_sets[k % n_sets], lane=ln)
 
     for k in range(args.warmup):
         step_resident(k)
@@ -291,19 +306,21 @@ def run_gpu(args, rank, world, local_rank):
         sampler.start()
     l0 = _native.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = _native.launch_count() - l0
+    launches = (_native.launch_count() - l0) if not use_graph else launches_per_step * args.steps
     clocks = sampler.stop() if sampler else None
     total_faces = sum_over_ranks(B, dev)
     value = total_faces * args.steps / (ms * 1e-3)
 
     # ---- second timed pass with per-layer CUDA events: live duration of the dominant kernel (roofline)
     model.set_profiling(True, dev, dtype)
+    model_profiling[0] = True
     per_layer = np.zeros(len(model.graph.layers))
     barrier()
     for k in range(args.steps):
         step_resident(k)
         per_layer += np.array([t for _, t in model.layer_times(dev, dtype)])
     model.set_profiling(False, dev, dtype)
+    model_profiling[0] = False
     per_layer /= args.steps
     conv_flops, fc_flops = flops_per_face()
     peaks = {}
@@ -334,17 +351,24 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- end to end through the public API objects with HOST (pinned) buffers: H2D + compute + D2H every step
     pin_sets = [tuple(t.pin_memory() for t in hs) for hs in host_sets]
-    marks_h = [torch.empty((B, 68, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
-    crops_h = [torch.empty((B, 112, 112, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    slots = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(2)]
+    n_slots = max(2, n_lanes)   # in-flight steps: H2D of step k+2 never waits for the compute of step k when there are 3
+    marks_h = [torch.empty((B, 68, 2), dtype=torch.float32).pin_memory() for _ in range(n_slots)]
+    crops_h = [torch.empty((B, 112, 112, 3), dtype=torch.uint8).pin_memory() for _ in range(n_slots)]
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(n_slots)]
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_comp = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(n_slots)]
+    ev_comp = [torch.cuda.Event() for _ in range(n_slots)]
+    ev_out = [torch.cuda.Event() for _ in range(n_slots)]
     main = torch.cuda.current_stream(dev)
 
+    e2e_graphs, e2e_results = [], []
+    if use_graph:
+        for sl in range(n_slots):
+            g, res = pipe.capture(*slots[sl], lane=sl)
+            e2e_graphs.append(g); e2e_results.append(res)
+
     def step_e2e(k):
-        sl = k % 2
+        sl = k % n_slots
         comp = lane_streams[sl % n_lanes]                     # compute stream of this slot (slot = lane: own workspace + results)
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_comp[sl])                      # slot's previous compute finished
@@ -354,7 +378,11 @@ def run_gpu(args, rank, world, local_rank):
         with torch.cuda.stream(comp):
             comp.wait_event(ev_in[sl])
             comp.wait_event(ev_out[sl])                       # the lane's result buffers have been read out
-            r = pipe.run_device(*slots[sl], lane=sl)
+            if use_graph:
+                e2e_graphs[sl].replay()
+                r = e2e_results[sl]
+            else:
+                r = pipe.run_device(*slots[sl], lane=sl)
             ev_comp[sl].record(comp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[sl])
@@ -383,7 +411,7 @@ def run_gpu(args, rank, world, local_rank):
     d2h = marks_h[0].numel() * 4 + crops_h[0].numel()
     # the host link this box gave us: the same pinned H2D copies alone (the e2e leg cannot be faster than this)
     def copy_only(k):
-        for d, h in zip(slots[k % 2], pin_sets[k % n_sets]):
+        for d, h in zip(slots[k % n_slots], pin_sets[k % n_sets]):
             d.copy_(h, non_blocking=True)
     ms_link = timed(copy_only, max(args.steps, 5)) / max(args.steps, 5)
     link_gbps = set_bytes / (ms_link * 1e-3) / 1e9
@@ -402,7 +430,7 @@ def run_gpu(args, rank, world, local_rank):
                 "config": {"workload": "configs[1]: batch-%d crops/GPU from %d 1080p frames, vanilla trunk@128 + FC-136 head, "
                                        "+ decode + 5-point align warp to 112x112" % (B, -(-B // FACES_PER_FRAME)),
                            "batch_per_gpu": B, "global_batch": int(total_faces), "parallelism": "faces sharded, no collective",
-                           "lanes": n_lanes,
+                           "lanes": n_lanes, "cuda_graph": bool(use_graph),
                            "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2; activations workspace rewritten every step"
                                  % (n_sets, n_sets * set_bytes / 1e6)},
                 "e2e": {"value": e2e_val, "unit": "faces/s", "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": int(d2h),
@@ -421,6 +449,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--sets", type=int, default=6)
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--lanes", type=int, default=3, help="independent batches in flight (streams with their own workspace)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
