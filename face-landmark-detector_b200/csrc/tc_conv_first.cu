@@ -30,9 +30,14 @@ struct FirstParams {
   int act, pool;
   int tiles_x, tiles_y, n_tiles;
   unsigned long long mul_x, mul_y;  // ceil(2^40 / tiles_x), ceil(2^40 / tiles_y): exact division for n < 2^21
+  int dbg;                 // FLD_C1_DBG timing experiments (results are garbage): 1 no pooling shuffles, 2 no epilogue math,
+                           // 4 no TMEM loads, 8 no im2col, 16 no MMA, 32 no pixel fetch, 64 no park, 128 no async-proxy fence, 256 no commit / mbarrier wait
 };
 
-constexpr int TWc = 8, THc = 16, PW_ = TWc + 2, PH_ = THc + 2, NPIX = PW_ * PH_;  // 10 x 18 = 180 halo pixels
+// A CTA iteration covers NT stacked 8 x 16 tiles (NT*128 threads, one pixel each).  FLD_C1_DBG bisect at batch 256: full kernel
+// 0.110 ms; without epilogue math, TMEM loads, im2col and MMAs 0.088; also without the pixel fetch 0.064; without park, fence,
+// commit / wait 0.050 — the cost is spread over the per-pixel front end, no single stage dominates.
+constexpr int TWc = 8, PW_ = TWc + 2;
 
 template <typename TIn> struct Raw3 { TIn c[3]; };
 
@@ -46,25 +51,29 @@ __device__ __forceinline__ void load_pixel(const TIn* __restrict__ img, int H, i
   }
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(128, 8)
+// DBG = true compiles the FLD_C1_DBG bisect switches in; the production instantiation carries none of their predicates.
+template <typename TIn, bool DBG, int NT>
+__global__ void __launch_bounds__(128 * NT, 8 / NT)
 conv_first_kernel(const FirstParams p) {
+  constexpr int THc = 16 * NT, PH_ = THc + 2, NPIX = PW_ * PH_, NTHR = 128 * NT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // A [6 kgroups][16 rowgroups][8 rows][16 B] = 12 KB | B [6 kgroups][Cout/8][8][16 B] = Cout*96 B | patch [18][10] x 8 B
+  // A NT x [6 kgroups][16 rowgroups][8 rows][16 B] = NT x 12 KB | B [6 kgroups][Cout/8][8][16 B] = Cout*96 B | patch [PH_][10] x 8 B
   uint8_t* sA = smem_raw;
-  uint8_t* sB = smem_raw + 12288;
+  uint8_t* sB = smem_raw + 12288 * NT;
   uint2* patch = reinterpret_cast<uint2*>(sB + p.Cout * 96);
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = p.Cout <= 32 ? 32 : p.Cout <= 64 ? 64 : p.Cout <= 128 ? 128 : 256;
+  const uint32_t ncols1 = p.Cout <= 32 ? 32 : p.Cout <= 64 ? 64 : p.Cout <= 128 ? 128 : 256;
+  const uint32_t ncols = ncols1 * NT;   // one accumulator block of Cout columns per stacked tile
+  const int thalf = tid >> 7, t128 = tid & 127;
 
   {  // weights (already in core-matrix order) and the all-zero sixth K group of A
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = tid; i < p.Cout * 6; i += 128) dst[i] = src[i];
-    *reinterpret_cast<uint4*>(sA + (5 * 16 + (tid >> 3)) * 128 + (tid & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < p.Cout * 6; i += NTHR) dst[i] = src[i];
+    *reinterpret_cast<uint4*>(sA + thalf * 12288 + (5 * 16 + (t128 >> 3)) * 128 + (t128 & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid == 0) {
     mbar_init(smem_u32(&mma_bar), 1);
@@ -84,9 +93,9 @@ conv_first_kernel(const FirstParams p) {
   const uint64_t adesc0 = umma_desc(smem_u32(sA), a_lbo, 128, 0);
   const uint64_t bdesc0 = umma_desc(smem_u32(sB), b_lbo, 128, 0);
 
-  // halo pixels owned by this thread: e0 = tid, e1 = tid + 128 (< 180 for tid < 52)
+  // halo pixels owned by this thread: e0 = tid, e1 = tid + NTHR (< NPIX for the first NPIX - NTHR threads)
   const int r0 = tid / PW_, c0 = tid - r0 * PW_;
-  const int e1 = tid + 128;
+  const int e1 = tid + NTHR;
   const bool has1 = e1 < NPIX;
   const int r1 = e1 / PW_, c1 = e1 - r1 * PW_;
 
@@ -116,41 +125,50 @@ conv_first_kernel(const FirstParams p) {
     int b, x0, y0;
     tile_origin(tile, b, x0, y0);
     // ---- 1. park this tile's pixels as bf16 RGB0
-    patch[tid] = make_uint2(pack_bf16((float)v0.c[0], (float)v0.c[1]), pack_bf16((float)v0.c[2], 0.f));
-    if (has1) patch[e1] = make_uint2(pack_bf16((float)v1.c[0], (float)v1.c[1]), pack_bf16((float)v1.c[2], 0.f));
+    if (!(DBG && (p.dbg & 64))) {
+      patch[tid] = make_uint2(pack_bf16((float)v0.c[0], (float)v0.c[1]), pack_bf16((float)v0.c[2], 0.f));
+      if (has1) patch[e1] = make_uint2(pack_bf16((float)v1.c[0], (float)v1.c[1]), pack_bf16((float)v1.c[2], 0.f));
+    }
     __syncthreads();
     // ---- prefetch the next tile's pixels (in flight during im2col + MMA + epilogue)
     const int next = tile + gridDim.x;
-    if (next < p.n_tiles) fetch(next, v0, v1);
+    if (next < p.n_tiles && !(DBG && (p.dbg & 32))) fetch(next, v0, v1);
     // ---- 2. im2col row of output pixel (ly, lx)
-    {
+    if (!(DBG && (p.dbg & 8))) {
       uint2 q[3][3];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) q[kh][kw] = patch[(ly + kh) * PW_ + lx + kw];
-      uint8_t* row = sA + (tid >> 3) * 128 + (tid & 7) * 16;  // + kgroup * 16 * 128
+      uint8_t* row = sA + thalf * 12288 + (t128 >> 3) * 128 + (t128 & 7) * 16;  // + kgroup * 16 * 128
       *reinterpret_cast<uint4*>(row + 0 * 2048) = make_uint4(q[0][0].x, q[0][0].y, q[0][1].x, q[0][1].y);
       *reinterpret_cast<uint4*>(row + 1 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
       *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
       *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
       *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0x3f803f80u, 0u);  // k 36,37 = 1.0 (bias)
     }
-    fence_async_smem();
+    if (!(DBG && (p.dbg & 128))) fence_async_smem();
     __syncthreads();
     // ---- 3. three K = 16 MMAs (k groups 0-1, 2-3, 4-5); LBO field moves by 2 groups per step
-    if (warp == 0) {
+    if (warp == 0 && !(DBG && (p.dbg & 256))) {
       tc_fence_after();
       if (elect_one()) {  // single-lane region known to the compiler: plain UTCHMMA / UTCBAR, no waterfall loops
         const uint64_t astep = (uint64_t)((2 * a_lbo) >> 4), bstep = (uint64_t)((2 * b_lbo) >> 4);
-        umma_bf16(tmem_base, adesc0, bdesc0, idesc, 0u);
-        umma_bf16(tmem_base, adesc0 + astep, bdesc0 + bstep, idesc, 1u);
-        umma_bf16(tmem_base, adesc0 + 2 * astep, bdesc0 + 2 * bstep, idesc, 1u);
+        if (!(DBG && (p.dbg & 16))) {
+#pragma unroll
+          for (int hf = 0; hf < NT; ++hf) {
+            const uint64_t ad = adesc0 + (uint64_t)(hf * (12288 >> 4));
+            const uint32_t d = tmem_base + hf * ncols1;
+            umma_bf16(d, ad, bdesc0, idesc, 0u);
+            umma_bf16(d, ad + astep, bdesc0 + bstep, idesc, 1u);
+            umma_bf16(d, ad + 2 * astep, bdesc0 + 2 * bstep, idesc, 1u);
+          }
+        }
         umma_commit(smem_u32(&mma_bar));
       }
       __syncwarp();
     }
-    mbar_wait(smem_u32(&mma_bar), phase);
+    if (!(DBG && (p.dbg & 256))) mbar_wait(smem_u32(&mma_bar), phase);
     phase ^= 1;
     tc_fence_after();
     // ---- 4. epilogue: thread = TMEM lane = tile pixel
@@ -166,8 +184,26 @@ conv_first_kernel(const FirstParams p) {
     }
     for (int ch = 0; ch < p.Cout; ch += 32) {
       uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch, acc);
-      tmem_ld_wait();
+      if (!(DBG && (p.dbg & 4))) {
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + thalf * ncols1 + ch, acc);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = (uint32_t)(tile + j);
+      }
+      if (DBG && (p.dbg & 2)) { if ((acc[0] ^ acc[31]) == 0x7fc12345u) eo.valid = false; continue; }
+      if (DBG && (p.dbg & 1)) {   // per-thread max only, one 16-byte store: no SHFL / SEL
+        uint32_t k2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          k2[i] = max_bf16x2(max_bf16x2(pack_bf16(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])),
+                                        pack_bf16(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3]))),
+                             max_bf16x2(pack_bf16(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])),
+                                        pack_bf16(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7]))));
+        if (eo.valid) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(eo.ptr) + ch + (lane & 1) * 8 + ((lane & TWc) ? 16 : 0)) =
+            make_uint4(k2[0], k2[1], k2[2], k2[3]);
+        continue;
+      }
       EpiOut e2 = eo;
       e2.ptr = reinterpret_cast<__nv_bfloat16*>(eo.ptr) + ch;
       e2.c_left = p.Cout - ch;
@@ -216,27 +252,39 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
   FirstParams p;
   p.in = in; p.w = w_packed; p.bias = bias; p.out = out;
   p.B = B; p.H = g.IH; p.W = g.IW; p.Cout = g.Cout; p.act = g.act; p.pool = g.pool;
-  p.tiles_x = fld_div_up(g.OW, TWc); p.tiles_y = fld_div_up(g.OH, THc);
+  const int ncols1 = g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : g.Cout <= 128 ? 128 : 256;
+  // stacked tiles per CTA iteration: measured equal within noise at batch 256 (0.112 ms with 2 vs 0.109 ms with 1), so the
+  // kernel's time is per-pixel work, not the per-iteration barrier chain; 2 stays available for experiments (FLD_C1_NT=2)
+  int NT = 1;
+  { const char* e = getenv("FLD_C1_NT"); if (e && atoi(e) == 2 && g.OH >= 32 && ncols1 <= 128) NT = 2; }
+  const int TH = 16 * NT;
+  p.tiles_x = fld_div_up(g.OW, TWc); p.tiles_y = fld_div_up(g.OH, TH);
   p.n_tiles = B * p.tiles_x * p.tiles_y;
   p.mul_x = ((1ull << 40) + p.tiles_x - 1) / p.tiles_x;
   p.mul_y = ((1ull << 40) + p.tiles_y - 1) / p.tiles_y;
+  { const char* e = getenv("FLD_C1_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (p.n_tiles >= (1 << 21)) { fld_set_error("tc_conv_first: too many tiles (%d)", p.n_tiles); return FLD_ERR_INVALID; }
-  const size_t smem = 12288 + (size_t)g.Cout * 96 + NPIX * 8 + 64;
-  const int ncols = g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : g.Cout <= 128 ? 128 : 256;
-  const int cta_per_sm = std::max(1, std::min(512 / ncols, 8));
+  const size_t smem = (size_t)12288 * NT + (size_t)g.Cout * 96 + (size_t)PW_ * (TH + 2) * 8 + 64;
+  const int cta_per_sm = std::max(1, std::min(512 / (ncols1 * NT), 8 / NT));
   const int grid = std::min(p.n_tiles, h->sm_count * cta_per_sm);
-  FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  auto launch = [&](auto kern) -> int {
+    FLD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (smem > 48 * 1024) FLD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128 * NT, smem, st>>>(p);
+    return FLD_OK;
+  };
+  int rc;
   if (in_dtype == FLD_U8) {
-    if (smem > 48 * 1024) FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_first_kernel<uint8_t><<<grid, 128, smem, st>>>(p);
+    if (NT == 2) rc = p.dbg ? launch(conv_first_kernel<uint8_t, true, 2>) : launch(conv_first_kernel<uint8_t, false, 2>);
+    else rc = p.dbg ? launch(conv_first_kernel<uint8_t, true, 1>) : launch(conv_first_kernel<uint8_t, false, 1>);
   } else if (in_dtype == FLD_F32) {
-    if (smem > 48 * 1024) FLD_CUDA(cudaFuncSetAttribute(conv_first_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_first_kernel<float><<<grid, 128, smem, st>>>(p);
+    if (NT == 2) rc = p.dbg ? launch(conv_first_kernel<float, true, 2>) : launch(conv_first_kernel<float, false, 2>);
+    else rc = p.dbg ? launch(conv_first_kernel<float, true, 1>) : launch(conv_first_kernel<float, false, 1>);
   } else {
     fld_set_error("tc_conv_first: input must be u8 or f32");
     return FLD_ERR_INVALID;
   }
+  if (rc) return rc;
   FLD_LAUNCHED();
   return FLD_OK;
 }
