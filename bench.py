@@ -285,11 +285,16 @@ def run_gpu(args, rank, world, local_rank):
     launches_per_step = None
     graphs = []
     if use_graph:
-        for sidx in range(n_sets):
-            l_before = _native.launch_count()
-            g, _ = pipe.capture(*dev_sets[sidx], lane=sidx % n_lanes)
-            launches_per_step = (_native.launch_count() - l_before) // 2     # capture() = one warm-up run + the recorded run
-            graphs.append(g)
+        try:
+            for sidx in range(n_sets):
+                l_before = _native.launch_count()
+                g, _ = pipe.capture(*dev_sets[sidx], lane=sidx % n_lanes)
+                launches_per_step = (_native.launch_count() - l_before) // 2  # capture() = one warm-up run + the recorded run
+                graphs.append(g)
+        except Exception as e:                                # keep measuring: every kernel is then enqueued from Python
+            print("bench: CUDA graph capture failed (%s); running eagerly" % e, file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize(dev)
 
     def step_resident(k):
         ln = k % n_lanes
@@ -362,10 +367,16 @@ def run_gpu(args, rank, world, local_rank):
     main = torch.cuda.current_stream(dev)
 
     e2e_graphs, e2e_results = [], []
-    if use_graph:
-        for sl in range(n_slots):
-            g, res = pipe.capture(*slots[sl], lane=sl)
-            e2e_graphs.append(g); e2e_results.append(res)
+    use_graph_e2e = use_graph
+    if use_graph_e2e:
+        try:
+            for sl in range(n_slots):
+                g, res = pipe.capture(*slots[sl], lane=sl)
+                e2e_graphs.append(g); e2e_results.append(res)
+        except Exception as e:
+            print("bench: CUDA graph capture failed in the e2e leg (%s); running eagerly" % e, file=sys.stderr)
+            use_graph_e2e = False
+            torch.cuda.synchronize(dev)
 
     def step_e2e(k):
         sl = k % n_slots
@@ -378,7 +389,7 @@ def run_gpu(args, rank, world, local_rank):
         with torch.cuda.stream(comp):
             comp.wait_event(ev_in[sl])
             comp.wait_event(ev_out[sl])                       # the lane's result buffers have been read out
-            if use_graph:
+            if use_graph_e2e:
                 e2e_graphs[sl].replay()
                 r = e2e_results[sl]
             else:

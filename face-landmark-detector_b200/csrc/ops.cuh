@@ -41,7 +41,6 @@ void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_ho
 bool tc_conv_supported(const ConvGeom& g);
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
                         TcConvPlan** out);
-int simt_pad_cvt_bf16(const float* in, void* out_bf16, long long n_px, int C, int Cpad, cudaStream_t st);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype, cudaStream_t st);
 

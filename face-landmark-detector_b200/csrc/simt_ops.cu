@@ -277,15 +277,6 @@ __global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__
   out[i] = m;
 }
 
-// fp32 [n_px][C] -> bf16 [n_px][Cpad], channels C..Cpad-1 zero (operand of the tensor-core transposed conv)
-__global__ void pad_cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n_px, int C, int Cpad) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_px * Cpad) return;
-  const long long px = i / Cpad;
-  const int c = (int)(i - px * Cpad);
-  out[i] = __float2bfloat16_rn(c < C ? in[px * C + c] : 0.f);
-}
-
 __global__ void cvt_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(in[i]);
@@ -387,10 +378,3 @@ int simt_cvt_bf16_f32(const void* in, float* out, long long n, cudaStream_t st) 
   return FLD_OK;
 }
 
-int simt_pad_cvt_bf16(const float* in, void* out_bf16, long long n_px, int C, int Cpad, cudaStream_t st) {
-  if (n_px == 0) return FLD_OK;
-  const long long n = n_px * Cpad;
-  pad_cvt_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat16*)out_bf16, n_px, C, Cpad);
-  FLD_LAUNCHED();
-  return FLD_OK;
-}
