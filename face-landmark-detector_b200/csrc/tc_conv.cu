@@ -34,6 +34,8 @@ struct TmaConvParams {
   void* out;
   int B, OH, OW, Cout; // conv output (pre-pool) dims
   int Cin, kh, kw, pad_t, pad_l;
+  int flat;            // 1x1 / stride 1 / no padding / no pool: the M tile is 128 CONSECUTIVE pixels of the flattened [B*H*W] list
+  long long npx;       //   (2-D tensor map, no per-image tile padding: a 7x7 map wastes 23 % of an 8x8 tile otherwise)
   int IH;              // input rows (tap skipping)
   int st;              // conv stride (1, or 2 for 1x1 convs: the tensor map's element strides pick every second pixel)
   int TW, TH, NB;      // M tile = TW*TH*NB = 128 pixels
@@ -123,7 +125,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               TRACE(0, ti, 5);
               mbar_arrive_expect_tx(fb, bytes);
               TRACE(0, ti, 6);
-              if (!(p.dbg & 4)) tma_load_4d(sa, &tmA, fb, kc * 64, x0 + kx, y0 + ky, b0);
+              if (!(p.dbg & 4)) {
+                if (p.flat) tma_load_2d(sa, &tmA, fb, kc * 64, tb * 128);     // rows past npx are zero-filled
+                else tma_load_4d(sa, &tmA, fb, kc * 64, x0 + kx, y0 + ky, b0);
+              }
               TRACE(0, ti, 7);
               if (!(p.dbg & 8)) tma_load_2d(sa + a_bytes, &tmB, fb, kc * 64, wrow);
               TRACE(0, ti, 8);
@@ -215,6 +220,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (p.pool) {
         eo.valid = (b < p.B) && ((oy >> 1) < PH) && ((ox >> 1) < PW);
         pix = ((size_t)b * PH + (oy >> 1)) * PW + (ox >> 1);
+      } else if (p.flat) {
+        pix = (size_t)tb * 128 + r;
+        eo.valid = (long long)pix < p.npx;
       } else {
         eo.valid = (b < p.B) && (oy < p.OH) && (ox < p.OW);
         pix = ((size_t)b * p.OH + oy) * p.OW + ox;
@@ -296,7 +304,11 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   const int BN = cout_pad <= 256 ? cout_pad : ((cout_pad % 256 == 0) ? 256 : 128);
   if (cout_pad % BN != 0 || BN % 16 != 0) { delete pl; fld_set_error("tc_conv: bad cout_pad %d", cout_pad); return FLD_ERR_INVALID; }
   p.BN = BN; p.cout_pad = cout_pad; p.n_ntiles = cout_pad / BN;
+  p.flat = (g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pool == 0 && g.OH == g.IH && g.OW == g.IW &&
+            !getenv("FLD_TC_FLAT_OFF")) ? 1 : 0;
+  p.npx = (long long)B * g.OH * g.OW;
   p.tiles_x = fld_div_up(g.OW, TW); p.tiles_y = fld_div_up(g.OH, TH); p.tiles_b = fld_div_up(B, NB);
+  if (p.flat) { p.tiles_x = 1; p.tiles_y = 1; p.tiles_b = (int)((p.npx + 127) / 128); }
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_ntiles;
   const size_t stage_bytes = 128 * 128 + (size_t)BN * 128;
   int stages = (int)((200 * 1024) / stage_bytes);
@@ -306,7 +318,16 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   pl->grid = std::min(p.total_tiles, h->sm_count);
 
   // activations: bf16 NHWC [B][IH][IW][Cin]
-  {
+  if (p.flat) {
+    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)p.npx};
+    cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(in), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(A, flat) failed: %d", (int)r); return FLD_ERR_CUDA; }
+  } else {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.IW * g.Cin * 2, (cuuint64_t)g.IH * g.IW * g.Cin * 2};
     // boxDim counts TRAVERSED elements: with element stride s the box loads ceil(boxDim / s) pixels per spatial dimension

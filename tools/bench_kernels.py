@@ -120,7 +120,8 @@ def main():
         from keypoints_detector.networks import fcn
         for name, build in (("fcn_8_mobilenet", fcn.fcn_8_mobilenet), ("fcn_8_resnet50", fcn.fcn_8_resnet50), ("fcn_8_vgg", fcn.fcn_8_vgg)):
             m = build(68, 224, 224).init_weights(0)
-            fcn_bench(name + "@224", m, "bfloat16", 32)
+            for B in (32, 128):
+                fcn_bench(name + "@224", m, "bfloat16", B)
 
 
 if __name__ == "__main__":
