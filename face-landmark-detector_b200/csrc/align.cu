@@ -238,6 +238,7 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
                  int out_h, int out_w, double* M_out, uint8_t* crops, cudaStream_t st) {
   int rc = fld_enter(h);
   if (rc) return rc;
+  if (B == 0) return FLD_OK;   // empty batch: nothing to read or write (empty tensors have null data pointers)
   FLD_REQUIRE(frames && face2frame && crops, "fld_align: null pointer");
   FLD_REQUIRE(C == 1 || C == 3 || C == 4, "fld_align: C must be 1, 3 or 4 (got %d)", C);
   FLD_REQUIRE(F > 0 && H > 1 && W > 1 && out_h > 0 && out_w > 0 && B >= 0, "fld_align: bad shape");

@@ -182,6 +182,7 @@ extern "C" int fld_decode_regress(fld_handle* h, const float* out136, int stride
                                   float* marks_f32, uint64_t* marks_u64, fld_stream stream) {
   int rc = fld_enter(h);
   if (rc) return rc;
+  if (B == 0) return FLD_OK;
   FLD_REQUIRE(out136 && faceboxes && marks_f32, "fld_decode_regress: null pointer");
   FLD_REQUIRE(stride >= 136 && B >= 0, "fld_decode_regress: stride must be >= 136");
   if (B == 0) return FLD_OK;
@@ -196,6 +197,7 @@ extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, in
                                    fld_stream stream) {
   int rc = fld_enter(h);
   if (rc) return rc;
+  if (B == 0) return FLD_OK;
   FLD_REQUIRE(scores && class_map, "fld_decode_classmap: null pointer");
   FLD_REQUIRE(B >= 0 && hw > 0 && L > 0 && L <= 384, "fld_decode_classmap: need 0 < L <= 384");
   if (B == 0) return FLD_OK;
@@ -213,6 +215,7 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
                                      double* xy, fld_stream stream) {
   int rc = fld_enter(h);
   if (rc) return rc;
+  if (B == 0) return FLD_OK;
   FLD_REQUIRE(hm && xy, "fld_decode_heatmap_xy: null pointer");
   FLD_REQUIRE(B >= 0 && H > 0 && W > 0 && L > 0 && L <= 1024, "fld_decode_heatmap_xy: need 0 < L <= 1024");
   FLD_REQUIRE(n_points <= FLD_MAX_TOPN, "fld_decode_heatmap_xy: n_points must be <= %d", FLD_MAX_TOPN);

@@ -382,7 +382,9 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   int rc = fld_enter(net->h);
   if (rc) return rc;
   if (!net->finalized) { fld_set_error("fld_net_forward: call fld_net_finalize first"); return FLD_ERR_STATE; }
-  FLD_REQUIRE(in && workspace && B >= 0, "fld_net_forward: null pointer");
+  FLD_REQUIRE(B >= 0, "fld_net_forward: negative batch");
+  if (B == 0) return FLD_OK;   // an empty batch is legal (empty tensors have null data pointers)
+  FLD_REQUIRE(in && workspace, "fld_net_forward: null pointer");
   FLD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "fld_net_forward: workspace must be 1024-byte aligned");
   if (ws_bytes < fld_net_workspace_bytes(net, B)) {
     fld_set_error("fld_net_forward: workspace %zu < required %zu", ws_bytes, fld_net_workspace_bytes(net, B));

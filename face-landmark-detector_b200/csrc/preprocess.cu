@@ -155,6 +155,7 @@ extern "C" int fld_preprocess_faces(fld_handle* h, const uint8_t* frames, int F,
                                     fld_stream stream) {
   int rc = fld_enter(h);
   if (rc) return rc;
+  if (B == 0) return FLD_OK;
   FLD_REQUIRE(frames && boxes && out, "fld_preprocess_faces: null pointer");
   FLD_REQUIRE(F > 0 && H > 0 && W > 0 && S > 0 && S <= 4096 && B >= 0, "fld_preprocess_faces: bad shape");
   if (B == 0) return FLD_OK;
@@ -170,6 +171,7 @@ extern "C" int fld_image_array(fld_handle* h, const uint8_t* images, int B, int 
                                fld_stream stream) {
   int rc = fld_enter(h);
   if (rc) return rc;
+  if (B == 0) return FLD_OK;
   FLD_REQUIRE(images && out, "fld_image_array: null pointer");
   FLD_REQUIRE(H > 0 && W > 0 && ow > 0 && oh > 0 && ow <= 8192 && B >= 0, "fld_image_array: bad shape");
   FLD_REQUIRE(norm >= 0 && norm <= 2, "fld_image_array: norm must be 0 (sub_mean), 1 (sub_and_divide) or 2 (divide)");

@@ -548,3 +548,38 @@ def test_fcn8_other_class_counts_bf16(dev, n_classes):
     assert (probs.reshape(3, 72, 104, n_classes).argmax(-1) == ref).mean() > 0.97
     cm = m.forward_classmap_device(xt, "bfloat16").cpu().numpy()
     assert (cm == ref).mean() > 0.97
+
+
+def test_error_behaviour_through_the_abi(dev):
+    """Errors surface as exceptions with the library's message (no silent fallback): wrong shapes / dtypes, an undersized
+    workspace, an unfinalised net, unsupported arguments; empty batches are legal and return empty results."""
+    import ctypes
+    from keypoints_detector import _native as N, prediction
+    from keypoints_detector.utils import metrics
+    m = _regressor(3)
+    with pytest.raises(ValueError):
+        m.forward_device(torch.zeros((1, 64, 64, 3), dtype=torch.uint8, device=dev))
+    with pytest.raises(TypeError):
+        m.forward_device(torch.zeros((1, 128, 128, 3), dtype=torch.float32, device=dev))
+    out = m.forward_device(torch.zeros((0, 128, 128, 3), dtype=torch.uint8, device=dev))
+    assert tuple(out.shape) == (0, 136)
+    lib = N.load_library()
+    net = m.compiled(dev.index, "bfloat16")
+    x = torch.zeros((2, 128, 128, 3), dtype=torch.uint8, device=dev)
+    ws = torch.empty(4096 + 1024, dtype=torch.uint8, device=dev)
+    al = (-ws.data_ptr()) % 1024
+    o = torch.empty((2, 136), dtype=torch.float32, device=dev)
+    rc = lib.fld_net_forward(net, N.ptr(x), 2, N._vp(ws.data_ptr() + al), 4096, N.ptr(o), N.stream_ptr(dev.index))
+    assert rc != 0 and b"workspace" in lib.fld_last_error()
+    with pytest.raises(N.FldError):
+        N.check(rc)
+    with pytest.raises(ValueError):
+        metrics.heatmap_xy_device(torch.zeros((1, 8, 8, 2), device=dev), n_points=N.MAX_TOPN + 1)
+    frames = torch.zeros((1, 64, 64, 3), dtype=torch.uint8, device=dev)
+    crops, M = prediction.align_device(frames, torch.zeros(0, dtype=torch.int32, device=dev),
+                                       torch.zeros((0, 68, 2), dtype=torch.float32, device=dev))
+    assert tuple(crops.shape) == (0, 112, 112, 3) and tuple(M.shape) == (0, 2, 3)
+    # degenerate landmarks (all points equal): the fit has no solution -> NaN matrix, zero crop, no crash
+    marks = torch.full((1, 68, 2), 10.0, device=dev)
+    crops, M = prediction.align_device(frames, torch.zeros(1, dtype=torch.int32, device=dev), marks)
+    assert torch.isnan(M).all() and int(crops.sum()) == 0
