@@ -146,7 +146,7 @@ int infer_shapes(fld_net* net) {
       const bool want_f32 = f32_needed[i + 1] != 0;
       if (L.d.op == FLD_OP_DWCONV || L.d.op == FLD_OP_MAXPOOL || L.d.op == FLD_OP_ADD) { o.dtype = want_f32 ? FLD_F32 : FLD_BF16; continue; }
       if (L.d.op != FLD_OP_CONV) { o.dtype = FLD_F32; continue; }
-      const bool in_ok_first = (a.dtype == FLD_U8 || a.dtype == FLD_F32) && tc_conv_first_supported(L.g);
+      const bool in_ok_first = (a.dtype == FLD_U8 || a.dtype == FLD_F32) && (tc_conv_first_supported(L.g) || tc_conv_stem_supported(L.g));
       const bool in_ok_tma = (a.dtype == FLD_BF16) && tc_conv_supported(L.g);
       if (in_ok_first && !want_f32) { L.path = PATH_TC_FIRST; o.dtype = FLD_BF16; }
       else if (in_ok_tma && !(want_f32 && L.g.pool)) { L.path = PATH_TC_TMA; o.dtype = want_f32 ? FLD_F32 : FLD_BF16; }
@@ -319,6 +319,12 @@ extern "C" int fld_net_finalize(fld_net* net) {
     } else if (L.path == PATH_SIMT) {
       FLD_CUDA(cudaMalloc(&L.d_w, L.w_host.size() * sizeof(float)));
       FLD_CUDA(cudaMemcpy(L.d_w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
+      // strided stem (tc_conv_stem.cu): [KG][Cout/8][8][8], k' = 4*tap + c
+      std::vector<uint16_t> pk((size_t)Cout * 8 * tc_conv_stem_kgroups(L.d.kh), 0);
+      tc_conv_stem_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), L.d.kh, Cout, f2bf, pk.data());
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
       // core-matrix packed [6 kgroups][Cout/8][8][8], k' = kh*12 + kw*4 + c (see tc_conv_first.cu)
       std::vector<uint16_t> pk((size_t)Cout * 48, 0);
@@ -419,7 +425,9 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
     void* pout = ptr[i + 1];
     switch (d.op) {
       case FLD_OP_CONV:
-        if (L.path == PATH_TC_FIRST) {
+        if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
+          rc = tc_conv_stem(net->h, pin, a.dtype, L.d_wbf, (__nv_bfloat16*)pout, L.g, B, st);
+        } else if (L.path == PATH_TC_FIRST) {
           rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st);
         } else if (L.path == PATH_TC_TMA && o.dtype == FLD_BF16 && tc_halo_supported(L.g, L.cout_pad)) {
           TcHaloPlan* plan = nullptr;

@@ -37,6 +37,13 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
 bool tc_conv_first_supported(const ConvGeom& g);
 void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_host /*[Cout] or null*/, int Cout,
                         uint16_t (*f2bf)(float), uint16_t* out /*[Cout*48]*/);
+// strided stems (tc_conv_stem.cu): k x k (3 or 7), stride 2, Cin = 3, any zero padding, bias folded, no pool; bf16 NHWC out
+bool tc_conv_stem_supported(const ConvGeom& g);
+int tc_conv_stem_kgroups(int ks);
+void tc_conv_stem_pack(const float* w_host /*[k*k*3][Cout]*/, const float* bias_host, int ks, int Cout, uint16_t (*f2bf)(float),
+                       uint16_t* out /*[kgroups*8][Cout] core-matrix packed*/);
+int tc_conv_stem(const fld_handle* h, const void* in, int in_dtype, const __nv_bfloat16* w_packed, __nv_bfloat16* out, const ConvGeom& g,
+                 int B, cudaStream_t st);
 // generic: stride 1, Cin % 64 == 0, bf16 NHWC in; weights bf16 [kh*kw][Cout_pad][Cin]; out bf16 or f32 NHWC
 bool tc_conv_supported(const ConvGeom& g);
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,

@@ -20,7 +20,7 @@ for r in rows[hdr + 1:]:
     agg.setdefault(n, []).append(v)
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(P, "%s_ncu_launches.txt" % tag), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 : python bench.py --steps 2 --warmup 3 --no-cpu --dtype bf16\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 : python bench.py --steps 2 --warmup 3 --no-cpu --dtype bf16 --no-graph --lanes 1\n")
     f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
     f.write("%-52s %5s %10s %7s\n" % ("kernel", "n", "avg_us", "share"))
     for n, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -38,7 +38,7 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
 with open(os.path.join(P, "%s_ncu_conv_full.txt" % tag), "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on -k regex:conv_ -s 15 -c 5 : python bench.py --steps 2 --warmup 3 --no-cpu --dtype bf16\n")
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:conv_ -s 15 -c 5 : python bench.py --steps 2 --warmup 3 --no-cpu --dtype bf16 --no-graph --lanes 1\n")
     f.write("# one step of the regression trunk at batch 256: conv1 (conv_first_kernel), conv2..4 (conv_halo_kernel), conv5 (conv_tma_kernel)\n")
     for r in rows[2:]:
         f.write("\n== %s\n" % r[H.index("Kernel Name")].split("(")[0])
@@ -53,6 +53,7 @@ for name in ("bench_bf16", "bench_fp32", "bench_reference"):
         line = open(src).read().strip().splitlines()[-1]
         json.loads(line)
         open(os.path.join(P, "%s_%s.json" % (tag, name)), "w").write(line + "\n")
-if os.path.exists(os.path.join(G, "kernels.jsonl")):
-    open(os.path.join(P, "%s_kernels.jsonl" % tag), "w").write(open(os.path.join(G, "kernels.jsonl")).read())
+for src, dst in (("kernels.jsonl", "kernels.jsonl"), ("sweep_bf16.jsonl", "sweep_bf16.jsonl")):
+    if os.path.exists(os.path.join(G, src)):
+        open(os.path.join(P, "%s_%s" % (tag, dst)), "w").write(open(os.path.join(G, src)).read())
 print("wrote", sorted(os.listdir(P)))
