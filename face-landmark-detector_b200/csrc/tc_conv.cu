@@ -26,6 +26,10 @@
 #include <vector>
 #include "tc_common.cuh"
 
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 namespace {
 using namespace tc;
 
@@ -36,7 +40,9 @@ struct TmaConvParams {
   int Cin, kh, kw, pad_t, pad_l;
   int flat;            // 1x1 / stride 1 / no padding / no pool: the M tile is 128 CONSECUTIVE pixels of the flattened [B*H*W] list
   long long npx;       //   (2-D tensor map, no per-image tile padding: a 7x7 map wastes 23 % of an 8x8 tile otherwise)
-  int IH;              // input rows (tap skipping)
+  int IH, IW;          // input rows / columns (tap skipping)
+  const int* sched;    // optional [n_iter]: CTA c runs tiles sched[c], sched[c + grid], ... (-1 = none).  Tap skipping makes tile
+  int n_iter;          // costs unequal; the host balances them (longest-processing-time first).  Without it n_iter = total_tiles
   int st;              // conv stride (1, or 2 for 1x1 convs: the tensor map's element strides pick every second pixel)
   int TW, TH, NB;      // M tile = TW*TH*NB = 128 pixels
   int BN, cout_pad, n_ntiles;
@@ -66,6 +72,12 @@ __device__ __forceinline__ void ky_range(const TmaConvParams& p, int ty, int& lo
   lo = max(0, p.pad_t - r1);
   hi = min(p.kh - 1, p.IH - 1 + p.pad_t - r0);
   if (hi < lo) { lo = 0; hi = p.kh - 1; }
+}
+__device__ __forceinline__ void kx_range(const TmaConvParams& p, int tx, int& lo, int& hi) {
+  const int c0 = tx * p.TW * p.st, c1 = c0 + (p.TW - 1) * p.st;
+  lo = max(0, p.pad_l - c1);
+  hi = min(p.kw - 1, p.IW - 1 + p.pad_l - c0);
+  if (hi < lo) { lo = 0; hi = p.kw - 1; }
 }
 
 template <bool OUT_F32>
@@ -103,18 +115,21 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (elect_one()) {
     uint32_t stage = 0, phase = 0;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int it = blockIdx.x; it < p.n_iter; it += gridDim.x) {
+      const int tile = p.sched ? __ldg(p.sched + it) : it;
+      if (tile < 0) continue;
       const int nt = tile / mtiles;             // N tile is the slow index: concurrent CTAs share the weight tile
       int m = tile - nt * mtiles;
       const int tb = m / (p.tiles_x * p.tiles_y);
       m -= tb * (p.tiles_x * p.tiles_y);
       const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
       const int x0 = tx * p.TW * p.st - p.pad_l, y0 = ty * p.TH * p.st - p.pad_t, b0 = tb * p.NB, n0 = nt * p.BN;
-      int ky_lo, ky_hi;
+      int ky_lo, ky_hi, kx_lo, kx_hi;
       ky_range(p, ty, ky_lo, ky_hi);
-      int wrow = n0 + ky_lo * p.kw * p.cout_pad;  // row of the [taps*cout_pad][Cin] weight matrix
+      kx_range(p, tx, kx_lo, kx_hi);
       for (int ky = ky_lo; ky <= ky_hi; ++ky) {
-        for (int kx = 0; kx < p.kw; ++kx, wrow += p.cout_pad) {
+        for (int kx = kx_lo; kx <= kx_hi; ++kx) {
+          const int wrow = n0 + (ky * p.kw + kx) * p.cout_pad;  // row of the [taps*cout_pad][Cin] weight matrix
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             TRACE(0, ti, 1);
@@ -152,15 +167,19 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t stage_step = stage_bytes >> 4;
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int it = blockIdx.x; it < p.n_iter; it += gridDim.x) {
+      const int tile = p.sched ? __ldg(p.sched + it) : it;
+      if (tile < 0) continue;
       TRACE(1, ti, 0);
       int kblocks_t;
       {
         const int m = tile % mtiles;
-        const int ty = (m % (p.tiles_x * p.tiles_y)) / p.tiles_x;
-        int ky_lo, ky_hi;
+        const int mm = m % (p.tiles_x * p.tiles_y);
+        const int ty = mm / p.tiles_x, tx = mm - ty * p.tiles_x;
+        int ky_lo, ky_hi, kx_lo, kx_hi;
         ky_range(p, ty, ky_lo, ky_hi);
-        kblocks_t = (ky_hi - ky_lo + 1) * p.kw * kchunks;
+        kx_range(p, tx, kx_lo, kx_hi);
+        kblocks_t = (ky_hi - ky_lo + 1) * (kx_hi - kx_lo + 1) * kchunks;
       }
       mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
       TRACE(1, ti, 3);
@@ -207,7 +226,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t acc = 0, acc_phase = 0;
     int ti = 0;
     const bool tr = (warp == 2);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int it = blockIdx.x; it < p.n_iter; it += gridDim.x) {
+      const int tile = p.sched ? __ldg(p.sched + it) : it;
+      if (tile < 0) continue;
       const int nt = tile / mtiles;
       int m = tile - nt * mtiles;
       const int tb = m / (p.tiles_x * p.tiles_y);
@@ -263,6 +284,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 struct TcConvPlan {
+  int* d_perm = nullptr;
   CUtensorMap tmA, tmB;
   TmaConvParams p;
   int grid;
@@ -288,16 +310,19 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.bias = nullptr; p.out = nullptr;
   p.B = B; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout;
   p.Cin = g.Cin; p.kh = g.kh; p.kw = g.kw; p.pad_t = g.pad_t; p.pad_l = g.pad_l;
-  p.st = g.stride; p.IH = g.IH;
+  p.st = g.stride; p.IH = g.IH; p.IW = g.IW;
   p.act = g.act; p.pool = g.pool;
   { const char* e = getenv("FLD_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.trace = nullptr;
   // M-tile geometry: TW*TH*NB = 128 pixels, TW in {4, 8}: the pool partners are lane^1 and lane^TW
-  const int TW = g.OW > 4 ? 8 : 4;
+  int TW = g.OW > 4 ? 8 : 4;
   // one output row per tile under a tall padded kernel on a small map: most kernel rows of the border rows multiply padding
   const bool row_tiles = g.pool == 0 && g.kh >= 5 && g.pad_t > 0 && g.OH <= 16 && !getenv("FLD_TC_ROWTILES_OFF");
   int TH = row_tiles ? 1 : 2;
   while (!row_tiles && TH * 2 <= 128 / TW && TH < g.OH) TH *= 2;
+  // with >= 96 images a tile can be ONE output pixel of 128 images: kernel columns that only see padding are skipped too
+  // (7x7 'same' on a 7x7 map: 57 % of the taps remain instead of 76 %)
+  if (row_tiles && g.kw >= 5 && g.pad_l > 0 && B >= 96 && !getenv("FLD_TC_PIXTILES_OFF")) TW = 1;
   const int NB = 128 / (TW * TH);
   p.TW = TW; p.TH = TH; p.NB = NB;
   // N tile
@@ -310,12 +335,51 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.tiles_x = fld_div_up(g.OW, TW); p.tiles_y = fld_div_up(g.OH, TH); p.tiles_b = fld_div_up(B, NB);
   if (p.flat) { p.tiles_x = 1; p.tiles_y = 1; p.tiles_b = (int)((p.npx + 127) / 128); }
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_ntiles;
+  p.sched = nullptr;
+  p.n_iter = p.total_tiles;
+
   const size_t stage_bytes = 128 * 128 + (size_t)BN * 128;
   int stages = (int)((200 * 1024) / stage_bytes);
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
   pl->smem = stages * stage_bytes + 1024;
   pl->grid = std::min(p.total_tiles, h->sm_count);
+  if (row_tiles && !p.flat && p.total_tiles > pl->grid && p.total_tiles <= (1 << 20)) {
+    // tile cost = k-blocks that touch the map (same formulas as ky_range / kx_range) + a fixed epilogue / pipeline-fill share
+    const int mt = p.tiles_x * p.tiles_y * p.tiles_b, G = pl->grid, kch = g.Cin / 64;
+    std::vector<std::pair<long long, int>> cost(p.total_tiles);
+    for (int t = 0; t < p.total_tiles; ++t) {
+      const int mm = (t % mt) % (p.tiles_x * p.tiles_y), ty = mm / p.tiles_x, tx = mm % p.tiles_x;
+      const int r0 = ty * TH * g.stride, r1 = r0 + (TH - 1) * g.stride, c0 = tx * TW * g.stride, c1 = c0 + (TW - 1) * g.stride;
+      const int nky = std::min(g.kh - 1, g.IH - 1 + g.pad_t - r0) - std::max(0, g.pad_t - r1) + 1;
+      const int nkx = std::min(g.kw - 1, g.IW - 1 + g.pad_l - c0) - std::max(0, g.pad_l - c1) + 1;
+      cost[t] = {-((long long)std::max(nky, 1) * std::max(nkx, 1) * kch * 2 * BN + 3000), t};   // ~cycles
+    }
+    std::stable_sort(cost.begin(), cost.end());
+    std::vector<std::vector<int>> lists(G);
+    std::vector<std::pair<long long, int>> heap(G);   // (load, cta) min-heap
+    for (int c = 0; c < G; ++c) heap[c] = {0, c};
+    auto cmp = [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a > b; };
+    std::make_heap(heap.begin(), heap.end(), cmp);
+    for (auto& ct : cost) {
+      std::pop_heap(heap.begin(), heap.end(), cmp);
+      auto& top = heap.back();
+      lists[top.second].push_back(ct.second);
+      top.first += -ct.first;
+      std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+    size_t rounds = 0;
+    for (auto& l : lists) { std::sort(l.begin(), l.end()); rounds = std::max(rounds, l.size()); }   // ascending id: N tile slow per CTA
+    std::vector<int> sched(rounds * G, -1);
+    for (int c = 0; c < G; ++c)
+      for (size_t i = 0; i < lists[c].size(); ++i) sched[i * G + c] = lists[c][i];
+    if (cudaMalloc(&pl->d_perm, sched.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(pl->d_perm, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete pl; fld_set_error("tc_conv: tile schedule upload failed"); return FLD_ERR_CUDA;
+    }
+    p.sched = pl->d_perm;
+    p.n_iter = (int)sched.size();
+  }
 
   // activations: bf16 NHWC [B][IH][IW][Cin]
   if (p.flat) {
@@ -354,7 +418,10 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   return FLD_OK;
 }
 
-void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
+void tc_conv_plan_destroy(TcConvPlan* p) {
+  if (p && p->d_perm) cudaFree(p->d_perm);
+  delete p;
+}
 
 int tc_conv_run(const TcConvPlan* pl, const float* bias, void* out, int out_dtype, cudaStream_t st) {
   if (pl->p.total_tiles == 0) return FLD_OK;

@@ -301,6 +301,7 @@ def test_tc_conv_layers_against_torch(dev):
     run(28, 28, 64, [("head7", 512, 7, "same", R, 0), ("head1", 512, 1, (0, 0, 0, 0), R, 0), ("score", 68, 1, (0, 0, 0, 0), 0, 0)], 2)
     run(16, 16, 128, [("conv2", 256, 3, (1, 1, 1, 1), R, 2), ("conv3", 256, 3, (1, 1, 1, 1), R, 2)], 5)     # 4x4 / 2x2 maps, NB > 1
     run(7, 7, 256, [("head7", 512, 7, "same", R, 0), ("head1", 256, 1, (0, 0, 0, 0), R, 0)], 19)           # one-row tiles, skipped kernel rows, ragged batch
+    run(7, 7, 64, [("head7", 256, 7, "same", R, 0)], 130)                                                  # one-pixel tiles of 128 images: kernel rows AND columns skipped
     run(3, 5, 64, [("head7", 128, 5, "same", R, 0)], 3)                                                    # TW = 8 on a 5-wide map, 3 rows
 
 
