@@ -107,13 +107,52 @@ def flops_per_face():
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  The region is a few milliseconds long, so the sampler
+    polls NVML from a thread (sub-millisecond per sample); `nvidia-smi -lms` (one sample per ~100 ms) is only the fallback."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nv, self.h, self.samples, self.run, self.thread = None, None, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                pr = torch.cuda.get_device_properties(index)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.samples.append((mhz, mask))
+
+    def _poll(self):
+        while self.run:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        if self.nv is not None:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -126,6 +165,21 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            try:
+                self._sample()                                # the GPU has just finished the last timed kernel
+            except Exception:
+                pass
+            self.run = False
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            if not self.samples:
+                return None
+            mask = 0
+            for _, m in self.samples:
+                mask |= m
+            return {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for bit, n in self.REASONS if mask & bit), "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -142,7 +196,8 @@ class ClockSampler:
                 pass
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------- CPU reference arm
