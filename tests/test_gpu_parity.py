@@ -584,3 +584,60 @@ def test_error_behaviour_through_the_abi(dev):
     marks = torch.full((1, 68, 2), 10.0, device=dev)
     crops, M = prediction.align_device(frames, torch.zeros(1, dtype=torch.int32, device=dev), marks)
     assert torch.isnan(M).all() and int(crops.sum()) == 0
+
+
+def test_no_out_of_bounds_writes(dev):
+    """Guard-band check (compute-sanitizer is not available on the pool): every caller-owned output lives inside a larger
+    sentinel-filled buffer; after the calls the bands on both sides, and the workspace tail, must be untouched."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.fcn import fcn_8
+
+    def guarded(shape, dtype, pad=4096):
+        n = int(np.prod(shape))
+        es = torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((n * es + 2 * pad,), 0xA5, dtype=torch.uint8, device=dev)
+        view = raw[pad:pad + n * es].view(dtype).view(shape)
+        return raw, view, pad
+
+    def intact(raw, pad):
+        return bool((raw[:pad] == 0xA5).all()) and bool((raw[-pad:] == 0xA5).all())
+
+    frames = T(synthetic.make_frames(2, 240, 320, seed=51), dev)
+    boxes = T(synthetic.make_boxes(5, 240, 320, seed=52, max_side=150), dev)
+    f2f = T((np.arange(5) % 2).astype(np.int32), dev)
+    m = _regressor(4)
+    for dtype in ("bfloat16", "float32"):
+        bufs = {}
+        rc, crops, p = guarded((5, 128, 128, 3), torch.uint8); bufs["crops"] = (rc, p)
+        rb, fb, p = guarded((5, 4), torch.int32); bufs["fb"] = (rb, p)
+        prediction.preprocess_faces_device(frames, boxes, f2f, 128, True, out=crops, out_boxes=fb)
+        ro, out, p = guarded((5, 136), torch.float32); bufs["out"] = (ro, p)
+        _, ws, al = m.forward_device(crops, dtype, out=out, return_workspace=True)
+        lib = N_lib()
+        need = lib.fld_net_workspace_bytes(m.compiled(dev.index, dtype), 5)
+        ws[al + need:].fill_(0x5A)
+        m.forward_device(crops, dtype, out=out)
+        assert bool((ws[al + need:] == 0x5A).all()), "workspace tail overwritten (%s)" % dtype
+        rm, marks, p = guarded((5, 68, 2), torch.float32); bufs["marks"] = (rm, p)
+        ru, marks_u, p = guarded((5, 68, 2), torch.int64); bufs["marks_u"] = (ru, p)
+        prediction.decode_regress_device(out, fb, True, out=marks, out_uint=marks_u)
+        ra, aligned, p = guarded((5, 112, 112, 3), torch.uint8); bufs["aligned"] = (ra, p)
+        rM, M, p = guarded((5, 2, 3), torch.float64); bufs["M"] = (rM, p)
+        prediction.align_device(frames, f2f, marks, None, (112, 112), True, True, out=aligned, out_matrix=M)
+        torch.cuda.synchronize(dev)
+        for k, (raw, pad) in bufs.items():
+            assert intact(raw, pad), (k, dtype)
+    net = fcn_8(68, input_height=64, input_width=96).init_weights(5)
+    x = torch.randn((3, 64, 96, 3), device=dev) * 40
+    for dtype in ("bfloat16", "float32"):
+        raw, out, pad = guarded((3, 72 * 104, 68), torch.float32)
+        net.forward_device(x, dtype, out=out)
+        torch.cuda.synchronize(dev)
+        assert intact(raw, pad), dtype
+        assert (out.sum(-1) - 1).abs().max().item() < 1e-4
+
+
+def N_lib():
+    from keypoints_detector import _native as N
+    return N.load_library()
