@@ -280,11 +280,24 @@ def resnet50_encoder_t(x, w):
     return levels
 
 
+def vgg_encoder_t(x, w):
+    """vgg16.py:17-81: blocks of 2-2-3-3-3 Conv2D(3x3, 'same', bias, relu), channels 64/128/256/512/512, MaxPool 2x2/2 after
+    each block (no BatchNormalization); levels f1..f5 are the pooled block outputs.  x NCHW."""
+    levels = []
+    for b, (n, _f) in enumerate(((2, 64), (2, 128), (3, 256), (3, 512), (3, 512)), start=1):
+        for i in range(1, n + 1):
+            name = "block%d_conv%d" % (b, i)
+            x = F.relu(conv2d_t(x, w[name + "/kernel"], w[name + "/bias"], pad=same_pad(3)))
+        x = F.max_pool2d(x, 2, 2)
+        levels.append(x)
+    return levels
+
+
 def fcn_forward_encoder(x_nhwc, weights, encoder="mobilenet", dtype=torch.float64, return_levels=False):
-    """fcn_8 over the MobileNet / ResNet50 encoder: float NHWC -> probs [B, oh*ow, n]."""
+    """fcn_8 over the MobileNet / ResNet50 / VGG16 encoder: float NHWC -> probs [B, oh*ow, n]."""
     w = _prep(weights, dtype)
     x = _t(x_nhwc, dtype).permute(0, 3, 1, 2)
-    levels = mobilenet_encoder_t(x, w) if encoder == "mobilenet" else resnet50_encoder_t(x, w)
+    levels = {"mobilenet": mobilenet_encoder_t, "resnet50": resnet50_encoder_t, "vgg": vgg_encoder_t}[encoder](x, w)
     probs = segmentation_probs_t(fcn_8_logits_t(levels, w)).numpy()
     if return_levels:
         return probs, [l.permute(0, 2, 3, 1).contiguous().numpy() for l in levels]

@@ -84,6 +84,10 @@ def _encoder_case(dev, name, dtype, H, W, B=3, seed=21):
     if name == "mobilenet":
         m = fcn.fcn_8_mobilenet(68, H, W).init_weights(seed)
         _, levels = mobilenet.get_mobilenet_encoder(H, W)
+    elif name == "vgg":
+        from keypoints_detector.networks import vgg16
+        m = fcn.fcn_8_vgg(68, H, W).init_weights(seed)
+        _, levels = vgg16.get_vgg_encoder(H, W)
     else:
         m = fcn.fcn_8_resnet50(68, H, W).init_weights(seed)
         _, levels = resnet50.get_resnet50_encoder(H, W)
@@ -95,7 +99,7 @@ def _encoder_case(dev, name, dtype, H, W, B=3, seed=21):
     return m, probs, probs_ref, lv, [lv_ref[i] for i in (2, 3, 4)]
 
 
-@pytest.mark.parametrize("name,H,W", [("mobilenet", 64, 96), ("resnet50", 96, 64)])
+@pytest.mark.parametrize("name,H,W", [("mobilenet", 64, 96), ("resnet50", 96, 64), ("vgg", 64, 96)])
 def test_fcn8_encoder_fp32(dev, name, H, W):
     m, probs, probs_ref, lv, lv_ref = _encoder_case(dev, name, "float32", H, W)
     assert m.model_name == "fcn_8_" + name
@@ -109,7 +113,7 @@ def test_fcn8_encoder_fp32(dev, name, H, W):
     assert (probs.reshape(-1, oh, ow, 68).argmax(-1) == ref).mean() > 0.999
 
 
-@pytest.mark.parametrize("name,H,W", [("mobilenet", 64, 96), ("resnet50", 96, 64)])
+@pytest.mark.parametrize("name,H,W", [("mobilenet", 64, 96), ("resnet50", 96, 64), ("vgg", 64, 96)])
 def test_fcn8_encoder_bf16(dev, name, H, W):
     """bf16 operands / fp32 accumulation through 27 (MobileNet) / 53 (ResNet50) stacked layers on random-init weights:
     the levels stay within a few percent of the fp64 oracle, the class map agrees on the bulk of the pixels."""
@@ -136,3 +140,8 @@ def test_fcn32_mobilenet_and_registry(dev):
     probs = m.forward_device(T(x, dev), "float32").cpu().numpy()
     assert probs.shape == ref.shape
     assert np.abs(probs - ref).max() < 1e-4
+    # bf16: the 64x64 / stride-32 transposed conv runs as a tensor-core GEMM with 1024 phases
+    probs16 = m.forward_device(T(x, dev), "bfloat16").cpu().numpy()
+    assert np.abs(probs16 - ref).mean() < 2e-3
+    oh, ow = m.output_height, m.output_width
+    assert (probs16.reshape(2, oh, ow, 68).argmax(-1) == ref.reshape(2, oh, ow, 68).argmax(-1)).mean() > 0.9

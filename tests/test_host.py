@@ -183,8 +183,10 @@ def test_encoder_graphs_match_oracle_shapes():
         m = build(5, input_height=32, input_width=64)
         assert m.n_classes == 5 and m.output_height > 0 and m.weight_specs()
     x = torch.zeros(1, 3, 32, 64, dtype=torch.float32)
+    from keypoints_detector.networks import vgg16
     for getter, enc_t in ((mobilenet.get_mobilenet_encoder, o_cnn.mobilenet_encoder_t),
-                          (resnet50.get_resnet50_encoder, o_cnn.resnet50_encoder_t)):
+                          (resnet50.get_resnet50_encoder, o_cnn.resnet50_encoder_t),
+                          (vgg16.get_vgg_encoder, o_cnn.vgg_encoder_t)):
         g, levels = getter(32, 64)
         from keypoints_detector.networks.model import Model
         w = o_cnn._prep(Model(g, "segmentation").init_weights(0).weights, torch.float32)
