@@ -190,6 +190,13 @@ uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
 
 }  // namespace
 
+// Bytes tensor t occupies in the workspace for batch B.  The logits of a transposed conv whose softmax / argmax / centroid is
+// fused into its epilogue are never written (14.6 MB per 224x224 image for fcn_8): they get no space.
+static size_t tensor_ws_bytes(const fld_net* net, int t, int B) {
+  if (t >= 1 && net->layers[t - 1].dc_fuse_softmax) return 0;
+  return align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+}
+
 extern "C" int fld_net_create(fld_handle* h, const fld_layer_desc* layers_h, int n_layers, int in_h, int in_w, int in_c, int in_dtype,
                               int compute, fld_net** out) {
   int rc = fld_enter(h);
@@ -369,14 +376,14 @@ extern "C" int fld_net_tensor_shape(const fld_net* net, int tensor, int32_t* hwc
 extern "C" int64_t fld_net_tensor_offset(const fld_net* net, int tensor, int B) {
   if (!net || tensor < 1 || tensor >= (int)net->tensors.size() || B < 0) { fld_set_error("fld_net_tensor_offset: bad argument"); return FLD_ERR_INVALID; }
   size_t off = 0;
-  for (int t = 1; t < tensor; ++t) off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+  for (int t = 1; t < tensor; ++t) off += tensor_ws_bytes(net, t, B);
   return (int64_t)off;
 }
 
 extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
   if (!net || B < 0) return 0;
   size_t off = 0;
-  for (size_t t = 1; t < net->tensors.size(); ++t) off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+  for (size_t t = 1; t < net->tensors.size(); ++t) off += tensor_ws_bytes(net, (int)t, B);
   return off + align_up(dense_scratch_bytes(net, B), 1024) + 1024;
 }
 
@@ -407,7 +414,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
     size_t off = 0;
     for (int t = 1; t < nT; ++t) {
       ptr[t] = (char*)workspace + off;
-      off += align_up(net->tensors[t].elems() * net->tensors[t].esz() * (size_t)B, 1024);
+      off += tensor_ws_bytes(net, t, B);
     }
     dense_scratch = (float*)((char*)workspace + off);
   }
