@@ -113,7 +113,7 @@ def main():
     if "fcn" in which:
         from keypoints_detector.networks.fcn import fcn_8
         m = fcn_8(68, input_height=224, input_width=224).init_weights(0)
-        for dtype, B in (("bfloat16", 32), ("bfloat16", 256), ("float32", 4)):
+        for dtype, B in (("bfloat16", 32), ("bfloat16", 256), ("bfloat16", 1024), ("float32", 4)):   # 1024 = config C3
             fcn_bench("fcn_8/vanilla@224", m, dtype, B)
 
     if "encoders" in which:
