@@ -50,6 +50,32 @@ classmap_kernel(const float* __restrict__ scores, long long n_px, int L, long lo
   }
 }
 
+// L % 4 == 0: 16-byte loads, 16-byte shared-memory stores and row scans (pitch L floats: a quarter warp of float4 accesses at a
+// 4L-byte pitch hits 32 distinct banks when L/4 is odd, e.g. 68 classes) -- a quarter of the memory instructions
+__global__ void __launch_bounds__(kCmThreads)
+classmap_vec4_kernel(const float4* __restrict__ scores, long long n_px, int L4, long long* __restrict__ cmap) {
+  extern __shared__ float4 tile4[];  // [kCmThreads][L4]
+  const long long px0 = (long long)blockIdx.x * kCmThreads;
+  const int npx = (int)min((long long)kCmThreads, n_px - px0);
+  const float4* src = scores + px0 * L4;
+  const int n = npx * L4;
+  for (int i = threadIdx.x; i < n; i += kCmThreads) tile4[i] = __ldg(src + i);
+  __syncthreads();
+  if (threadIdx.x < npx) {
+    const float4* row = tile4 + threadIdx.x * L4;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int q = 0; q < L4; ++q) {
+      const float4 v = row[q];
+      if (q == 0) { best = v.x; bi = 0; } else if (v.x > best) { best = v.x; bi = 4 * q; }   // first maximum wins (numpy argmax)
+      if (v.y > best) { best = v.y; bi = 4 * q + 1; }
+      if (v.z > best) { best = v.z; bi = 4 * q + 2; }
+      if (v.w > best) { best = v.w; bi = 4 * q + 3; }
+    }
+    cmap[px0 + threadIdx.x] = bi;
+  }
+}
+
 // ---------------------------------------------------------------- heat-map centroids (utils/metrics.py:46-80)
 struct Cand { float v; int idx; };
 __device__ __forceinline__ bool better(float av, int ai, float bv, int bi) {
@@ -58,26 +84,31 @@ __device__ __forceinline__ bool better(float av, int ai, float bv, int bi) {
 
 // partial[((b*S + s)*L + l)*n + k] : per-slab top-n candidates (unsorted), idx = -1 for empty
 template <int NMAX>
-__global__ void topn_partial_kernel(const float* __restrict__ hm, int HW, int L, int R, int S, int n,
+__global__ void __launch_bounds__(1024)   // blockDim = R * L can reach 1024 (L up to 1024): keep every variant launchable
+topn_partial_kernel(const float* __restrict__ hm, int HW, int L, int R, int S, int n,
                                     Cand* __restrict__ partial) {
   const int b = blockIdx.x, s = blockIdx.y;
   const int t = threadIdx.x;
-  const int l = t % L, r = t / L;
-  if (r >= R) return;
+  const int l = t % L, r = t / L;   // blockDim.x == R * L exactly: every thread reaches the barrier below
   Cand top[NMAX];
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) { top[k].v = -INFINITY; top[k].idx = -1; }
   int mn = 0;  // position of the current worst entry
+  float wv = -INFINITY;   // ... and a register copy of it: the common (no insertion) path is one compare per value
+  int wi = -1;
   const int per = (HW + S - 1) / S;
   const int p0 = s * per, p1 = min(HW, p0 + per);
   const float* base = hm + (size_t)b * HW * L;
   auto consider = [&](float v, int p) {
-    if (better(v, p, top[mn].v, top[mn].idx)) {
+    if (better(v, p, wv, wi)) {
 #pragma unroll
       for (int k = 0; k < NMAX; ++k) if (k == mn) { top[k].v = v; top[k].idx = p; }
       mn = 0;  // rescan for the worst
 #pragma unroll
       for (int k = 1; k < NMAX; ++k) if (k < n && better(top[mn].v, top[mn].idx, top[k].v, top[k].idx)) mn = k;
+      wv = top[0].v; wi = top[0].idx;
+#pragma unroll
+      for (int k = 1; k < NMAX; ++k) if (k == mn) { wv = top[k].v; wi = top[k].idx; }
     }
   };
   int p = p0 + r;
@@ -87,9 +118,28 @@ __global__ void topn_partial_kernel(const float* __restrict__ hm, int HW, int L,
     consider(v0, p); consider(v1, p + R); consider(v2, p + 2 * R); consider(v3, p + 3 * R);
   }
   for (; p < p1; p += R) consider(__ldg(base + (size_t)p * L + l), p);
-  // every (slab, r) lane writes its n candidates; merge kernel selects among S*R*n
-  Cand* dst = partial + ((((size_t)b * S + s) * R + r) * L + l) * n;
-  for (int k = 0; k < n; ++k) dst[k] = top[k];
+  if (NMAX > 16) {  // large n: every (slab, r) lane writes its n candidates; the merge kernel selects among S*R*n
+    Cand* dst = partial + ((((size_t)b * S + s) * R + r) * L + l) * n;
+    for (int k = 0; k < n; ++k) dst[k] = top[k];
+    return;
+  }
+  // n <= 16: block-level selection over the R pixel lanes, so that only ONE list per (slab, class) reaches the (serial) merge kernel
+  extern __shared__ Cand cand_s[];   // [R][L][n]
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k)
+    if (k < n) cand_s[((size_t)r * L + l) * n + k] = top[k];
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < R; ++rr)
+      for (int k = 0; k < n; ++k) {
+        const Cand c = cand_s[((size_t)rr * L + l) * n + k];
+        if (c.idx >= 0) consider(c.v, c.idx);
+      }
+    Cand* dst = partial + (((size_t)b * S + s) * L + l) * n;
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+      if (k < n) dst[k] = top[k];
+  }
 }
 
 __global__ void topn_merge_kernel(const Cand* __restrict__ partial, int W, int L, int SR, int n, int B, float thresh,
@@ -176,6 +226,123 @@ __global__ void soft_merge_kernel(const double* __restrict__ partial, int HW, in
   xy[(size_t)i * 2 + 1] = y;
 }
 
+// ---- L % 4 == 0 variants: thread (r, q) owns classes 4q .. 4q+3 of pixel lane r and reads them with ONE 16-byte load; a warp
+// reads 512 contiguous bytes.  Same partial layout as the scalar kernels (the merge kernels are shared).
+__global__ void soft_partial_vec4_kernel(const float4* __restrict__ hm, int HW, int W, int L4, int R, int S, double* __restrict__ partial) {
+  const int b = blockIdx.x, s = blockIdx.y;
+  const int t = threadIdx.x;
+  const int q = t % L4, r = t / L4;   // blockDim.x == R * L4 exactly: no thread leaves before the barrier
+  const int per = (HW + S - 1) / S;
+  const int p0 = s * per, p1 = min(HW, p0 + per);
+  const float4* base = hm + (size_t)b * HW * L4 + q;
+  // per-thread sums in fp32 (a thread adds ~200 values; the reference itself sums float32 arrays, metrics.py:58-64), fp64 from the
+  // block-level reduction on
+  float sh[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0};
+  auto acc = [&](const float4& v, int p) {
+    const int row = p / W, col = p - row * W;
+    const float fc = (float)col, fr = (float)row;
+    sh[0] += v.x; sx[0] = fmaf(v.x, fc, sx[0]); sy[0] = fmaf(v.x, fr, sy[0]);
+    sh[1] += v.y; sx[1] = fmaf(v.y, fc, sx[1]); sy[1] = fmaf(v.y, fr, sy[1]);
+    sh[2] += v.z; sx[2] = fmaf(v.z, fc, sx[2]); sy[2] = fmaf(v.z, fr, sy[2]);
+    sh[3] += v.w; sx[3] = fmaf(v.w, fc, sx[3]); sy[3] = fmaf(v.w, fr, sy[3]);
+  };
+  int p = p0 + r;
+  for (; p + 3 * R < p1; p += 4 * R) {  // four independent 16-byte loads in flight per thread
+    const float4 v0 = __ldg(base + (size_t)p * L4), v1 = __ldg(base + (size_t)(p + R) * L4);
+    const float4 v2 = __ldg(base + (size_t)(p + 2 * R) * L4), v3 = __ldg(base + (size_t)(p + 3 * R) * L4);
+    acc(v0, p); acc(v1, p + R); acc(v2, p + 2 * R); acc(v3, p + 3 * R);
+  }
+  for (; p < p1; p += R) acc(__ldg(base + (size_t)p * L4), p);
+  // block-level reduction over the R pixel lanes: one partial triple per (slab, class) reaches the merge kernel
+  extern __shared__ double red[];   // [R][L][3]
+  const int L = L4 * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double* d = red + ((size_t)r * L + 4 * q + k) * 3;
+    d[0] = (double)sh[k]; d[1] = (double)sx[k]; d[2] = (double)sy[k];
+  }
+  __syncthreads();
+  if (t < L) {
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int rr = 0; rr < R; ++rr) {
+      const double* d = red + ((size_t)rr * L + t) * 3;
+      a0 += d[0]; a1 += d[1]; a2 += d[2];
+    }
+    double* dst = partial + (((size_t)b * S + s) * L + t) * 3;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2;
+  }
+}
+
+// n <= 4, L % 4 == 0: thread (r, q) owns classes 4q .. 4q+3 of pixel lane r (one 16-byte load per pixel) and keeps a SORTED top-4
+// per class; the common path is one compare per value, an insertion is three predicated compare-and-swaps.
+__global__ void __launch_bounds__(512)
+topn4_vec4_kernel(const float4* __restrict__ hm, int HW, int L4, int R, int S, int n, Cand* __restrict__ partial) {
+  const int b = blockIdx.x, s = blockIdx.y;
+  const int t = threadIdx.x;
+  const int q = t % L4, r = t / L4;   // blockDim.x == R * L4 exactly
+  float tv[4][4];
+  int ti[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { tv[c][k] = -INFINITY; ti[c][k] = -1; }
+  const int per = (HW + S - 1) / S;
+  const int p0 = s * per, p1 = min(HW, p0 + per);
+  const float4* base = hm + (size_t)b * HW * L4 + q;
+#define FLD_TOPN4_CONSIDER(V, P, C)                                                                      \
+  if ((V) >= tv[C][3]) {                                                                                 \
+    if (better((V), (P), tv[C][3], ti[C][3])) {                                                          \
+      tv[C][3] = (V); ti[C][3] = (P);                                                                    \
+      _Pragma("unroll") for (int k = 3; k > 0; --k)                                                      \
+        if (better(tv[C][k], ti[C][k], tv[C][k - 1], ti[C][k - 1])) {                                    \
+          const float fv = tv[C][k]; tv[C][k] = tv[C][k - 1]; tv[C][k - 1] = fv;                         \
+          const int fi = ti[C][k]; ti[C][k] = ti[C][k - 1]; ti[C][k - 1] = fi;                           \
+        }                                                                                                \
+    }                                                                                                    \
+  }
+#define FLD_TOPN4_CONSIDER4(V4, P) \
+  { FLD_TOPN4_CONSIDER((V4).x, (P), 0) FLD_TOPN4_CONSIDER((V4).y, (P), 1) FLD_TOPN4_CONSIDER((V4).z, (P), 2) FLD_TOPN4_CONSIDER((V4).w, (P), 3) }
+  int p = p0 + r;
+  for (; p + 3 * R < p1; p += 4 * R) {  // four independent 16-byte loads in flight per thread
+    const float4 v0 = __ldg(base + (size_t)p * L4), v1 = __ldg(base + (size_t)(p + R) * L4);
+    const float4 v2 = __ldg(base + (size_t)(p + 2 * R) * L4), v3 = __ldg(base + (size_t)(p + 3 * R) * L4);
+    FLD_TOPN4_CONSIDER4(v0, p) FLD_TOPN4_CONSIDER4(v1, p + R) FLD_TOPN4_CONSIDER4(v2, p + 2 * R) FLD_TOPN4_CONSIDER4(v3, p + 3 * R)
+  }
+  for (; p < p1; p += R) {
+    const float4 v = __ldg(base + (size_t)p * L4);
+    FLD_TOPN4_CONSIDER4(v, p)
+  }
+  // block-level selection over the R pixel lanes: lane r == 0 folds the other lanes' lists into its own
+  extern __shared__ Cand cand4[];   // [R][L][4]
+  const int L = L4 * 4;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { cand4[((size_t)r * L + 4 * q + c) * 4 + k].v = tv[c][k]; cand4[((size_t)r * L + 4 * q + c) * 4 + k].idx = ti[c][k]; }
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < R; ++rr)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Cand c0 = cand4[((size_t)rr * L + 4 * q + 0) * 4 + k], c1 = cand4[((size_t)rr * L + 4 * q + 1) * 4 + k];
+        const Cand c2 = cand4[((size_t)rr * L + 4 * q + 2) * 4 + k], c3 = cand4[((size_t)rr * L + 4 * q + 3) * 4 + k];
+        if (c0.idx >= 0) FLD_TOPN4_CONSIDER(c0.v, c0.idx, 0)
+        if (c1.idx >= 0) FLD_TOPN4_CONSIDER(c1.v, c1.idx, 1)
+        if (c2.idx >= 0) FLD_TOPN4_CONSIDER(c2.v, c2.idx, 2)
+        if (c3.idx >= 0) FLD_TOPN4_CONSIDER(c3.v, c3.idx, 3)
+      }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      Cand* dst = partial + (((size_t)b * S + s) * L + 4 * q + c) * n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n) { dst[k].v = tv[c][k]; dst[k].idx = ti[c][k]; }
+    }
+  }
+#undef FLD_TOPN4_CONSIDER4
+#undef FLD_TOPN4_CONSIDER
+}
+
 }  // namespace
 
 extern "C" int fld_decode_regress(fld_handle* h, const float* out136, int stride, const int32_t* faceboxes, int B,
@@ -202,6 +369,15 @@ extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, in
   FLD_REQUIRE(B >= 0 && hw > 0 && L > 0 && L <= 384, "fld_decode_classmap: need 0 < L <= 384");
   if (B == 0) return FLD_OK;
   const long long n_px = (long long)B * hw;
+  if (L % 4 == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0 && !getenv("FLD_DECODE_SCALAR")) {
+    const size_t smem4 = (size_t)kCmThreads * L * sizeof(float);
+    if (smem4 > 48 * 1024) FLD_CUDA(cudaFuncSetAttribute(classmap_vec4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    const long long blocks4 = (n_px + kCmThreads - 1) / kCmThreads;
+    FLD_REQUIRE(blocks4 < (1ll << 31), "fld_decode_classmap: too many pixels");
+    classmap_vec4_kernel<<<(unsigned)blocks4, kCmThreads, smem4, (cudaStream_t)stream>>>((const float4*)scores, n_px, L / 4, (long long*)class_map);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
   const size_t smem = (size_t)kCmThreads * (L | 1) * sizeof(float);
   if (smem > 48 * 1024) FLD_CUDA(cudaFuncSetAttribute(classmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (n_px + kCmThreads - 1) / kCmThreads;
@@ -222,11 +398,21 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
   if (B == 0) return FLD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
-  const int R = (L >= 256) ? 1 : fld_div_up(256, L);  // pixel lanes per CTA
-  const int threads = R * L;
-  // slabs: enough CTAs to cover the machine ~8x (the kernels are latency-bound: one strided stream per thread),
-  // at least 64 pixels per lane
-  int S = fld_div_up(8 * h->sm_count, B);
+  const bool vec4 = L % 4 == 0 && (reinterpret_cast<uintptr_t>(hm) & 15) == 0 && n_points <= 4 && L <= 128 && !getenv("FLD_DECODE_SCALAR");
+  const int Lt = vec4 ? L / 4 : L;                      // threads per pixel lane
+  const int R = (Lt >= 256) ? 1 : fld_div_up(256, Lt);  // pixel lanes per CTA
+  const int threads = R * Lt;
+  // slabs: B * S CTAs fill ONE wave of resident CTAs (a 2.05-wave grid measured 68 % efficient), at least 64 pixels per lane
+  int occ = 0;
+  if (n_points < 1) {
+    if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, soft_partial_vec4_kernel, threads, (size_t)R * L * 3 * sizeof(double));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, soft_partial_kernel, threads, 0);
+  } else if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn4_vec4_kernel, threads, (size_t)R * L * 4 * sizeof(Cand));
+  else if (n_points <= 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<4>, threads, (size_t)R * L * n_points * sizeof(Cand));
+  else if (n_points <= 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<16>, threads, (size_t)R * L * n_points * sizeof(Cand));
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<FLD_MAX_TOPN>, threads, 0);
+  occ = max(occ, 1);
+  int S = max(1, (h->sm_count * occ) / B);
   S = max(1, min(S, HW / (64 * R) > 0 ? HW / (64 * R) : 1));
   S = min(S, 65535);
   dim3 grid(B, S);
@@ -235,9 +421,10 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
     void* scratch;
     rc = fld_scratch(h, (size_t)B * S * R * L * 3 * sizeof(double), &scratch);
     if (rc) return rc;
-    soft_partial_kernel<<<grid, threads, 0, st>>>(hm, HW, W, L, R, S, (double*)scratch);
+    if (vec4) soft_partial_vec4_kernel<<<grid, threads, (size_t)R * L * 3 * sizeof(double), st>>>((const float4*)hm, HW, W, L / 4, R, S, (double*)scratch);
+    else soft_partial_kernel<<<grid, threads, 0, st>>>(hm, HW, W, L, R, S, (double*)scratch);
     FLD_LAUNCHED();
-    soft_merge_kernel<<<fld_div_up(nBL, 128), 128, 0, st>>>((const double*)scratch, HW, L, S * R, B, (float)thresh, xy);
+    soft_merge_kernel<<<fld_div_up(nBL, 128), 128, 0, st>>>((const double*)scratch, HW, L, vec4 ? S : S * R, B, (float)thresh, xy);
     FLD_LAUNCHED();
     return FLD_OK;
   }
@@ -250,11 +437,17 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
   if (rc) return rc;
   Cand* partial = (Cand*)scratch;
   Cand* sel = (Cand*)((char*)scratch + part_bytes);
-  if (n <= 4) topn_partial_kernel<4><<<grid, threads, 0, st>>>(hm, HW, L, R, S, n, partial);
-  else if (n <= 16) topn_partial_kernel<16><<<grid, threads, 0, st>>>(hm, HW, L, R, S, n, partial);
+  const size_t csm = (size_t)R * L * n * sizeof(Cand);   // block-level candidate exchange (n <= 16)
+  if (n <= 16 && csm > 48 * 1024) {
+    FLD_CUDA(cudaFuncSetAttribute(topn_partial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+    FLD_CUDA(cudaFuncSetAttribute(topn_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+  }
+  if (vec4) topn4_vec4_kernel<<<grid, threads, (size_t)R * L * 4 * sizeof(Cand), st>>>((const float4*)hm, HW, L / 4, R, S, n, partial);
+  else if (n <= 4) topn_partial_kernel<4><<<grid, threads, csm, st>>>(hm, HW, L, R, S, n, partial);
+  else if (n <= 16) topn_partial_kernel<16><<<grid, threads, csm, st>>>(hm, HW, L, R, S, n, partial);
   else topn_partial_kernel<FLD_MAX_TOPN><<<grid, threads, 0, st>>>(hm, HW, L, R, S, n, partial);
   FLD_LAUNCHED();
-  topn_merge_kernel<<<fld_div_up(nBL, 128), 128, 0, st>>>(partial, W, L, S * R, n, B, (float)thresh, xy, sel);
+  topn_merge_kernel<<<fld_div_up(nBL, 128), 128, 0, st>>>(partial, W, L, n <= 16 ? S : S * R, n, B, (float)thresh, xy, sel);
   FLD_LAUNCHED();
   return FLD_OK;
 }
