@@ -408,9 +408,6 @@ __global__ void centroid_finish_kernel(const float* __restrict__ acc, long long 
   xy[i * 2 + 1] = y;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 constexpr size_t kSmemMax = 232448 - 4096;  // 227 KB per CTA minus the static part (barriers, goff table)
 
