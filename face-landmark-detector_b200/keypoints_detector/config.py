@@ -1,0 +1,1 @@
+"""Placeholder of the reference module of the same name (empty there too)."""

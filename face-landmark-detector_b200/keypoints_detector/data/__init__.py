@@ -1,0 +1,1 @@
+"""Inference-side subset of the reference data package (see generator.py)."""

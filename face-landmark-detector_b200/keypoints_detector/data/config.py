@@ -1,7 +1,3 @@
-"""Mirror of reference data/config.py:2-6 — the one configuration option of the reference."""
-IMAGE_ORDERING_CHANNELS_LAST = "channels_last"
-IMAGE_ORDERING_CHANNELS_FIRST = "channels_first"
-
-# Default IMAGE_ORDERING = channels_last (the only ordering the CUDA kernels implement; MobileNet in the
-# reference already asserts it, mobilenet.py:64-67)
-IMAGE_ORDERING = IMAGE_ORDERING_CHANNELS_LAST
+"""Tensor ordering switch of the reference's data pipeline (data/config.py): re-exported from the networks
+package so that both modules can never disagree."""
+from ..networks.config import IMAGE_ORDERING, IMAGE_ORDERING_CHANNELS_FIRST, IMAGE_ORDERING_CHANNELS_LAST  # noqa: F401

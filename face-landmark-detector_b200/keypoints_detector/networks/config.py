@@ -1,7 +1,5 @@
-"""Mirror of reference networks/config.py:1-5 — the one configuration option of the reference."""
-IMAGE_ORDERING_CHANNELS_LAST = "channels_last"
-IMAGE_ORDERING_CHANNELS_FIRST = "channels_first"
-
-# Default IMAGE_ORDERING = channels_last (the only ordering the CUDA kernels implement; MobileNet in the
-# reference already asserts it, mobilenet.py:64-67)
-IMAGE_ORDERING = IMAGE_ORDERING_CHANNELS_LAST
+"""Tensor ordering switch of the reference (networks/config.py).  The CUDA kernels are NHWC-only, so the
+one supported value is 'channels_last'; the second constant exists because callers compare against it."""
+_ORDERINGS = ("channels_last", "channels_first")
+IMAGE_ORDERING_CHANNELS_LAST, IMAGE_ORDERING_CHANNELS_FIRST = _ORDERINGS
+IMAGE_ORDERING = _ORDERINGS[0]   # the reference's default as well; its MobileNet builder asserts it (mobilenet.py:64-67)

@@ -1,0 +1,1 @@
+"""Heat-map decode wrappers (metrics.py) and drawing helpers (plots.py)."""
