@@ -10,6 +10,9 @@ model definitions with Keras layer semantics:
   fcn_8 / fcn_32       networks/fcn.py:89-150
   segmentation softmax networks/utils.py:22-30
   regression net       build-defined: vanilla_encoder@128 -> Flatten -> Dense(136)
+  VGG16 encoder        networks/vgg16.py:17-81
+  MobileNet-v1 encoder networks/mobilenet.py:12-104
+  ResNet50 encoder     networks/resnet50.py:23-173
                        standing in for the opaque SavedModel at prediction.py:84
 
 Two independent restatements are kept and must agree: torch functional ops (``*_t``) and a numpy
