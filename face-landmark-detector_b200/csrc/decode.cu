@@ -111,13 +111,16 @@ topn_partial_kernel(const float* __restrict__ hm, int HW, int L, int R, int S, i
       for (int k = 1; k < NMAX; ++k) if (k == mn) { wv = top[k].v; wi = top[k].idx; }
     }
   };
-  int p = p0 + r;
-  for (; p + 3 * R < p1; p += 4 * R) {  // four independent loads in flight per thread
-    const float v0 = __ldg(base + (size_t)p * L + l), v1 = __ldg(base + (size_t)(p + R) * L + l);
-    const float v2 = __ldg(base + (size_t)(p + 2 * R) * L + l), v3 = __ldg(base + (size_t)(p + 3 * R) * L + l);
-    consider(v0, p); consider(v1, p + R); consider(v2, p + 2 * R); consider(v3, p + 3 * R);
+  // Pixels are visited in DESCENDING index order: among equal values the higher index wins, so a tie arriving later never
+  // displaces an entry (heat maps with long runs of equal values, e.g. saturated softmax outputs, stay on the one-compare path).
+  int cnt = (p0 + r < p1) ? (p1 - (p0 + r) + R - 1) / R : 0;
+  int p = p0 + r + (cnt - 1) * R;
+  for (; cnt >= 4; cnt -= 4, p -= 4 * R) {  // four independent loads in flight per thread
+    const float v0 = __ldg(base + (size_t)p * L + l), v1 = __ldg(base + (size_t)(p - R) * L + l);
+    const float v2 = __ldg(base + (size_t)(p - 2 * R) * L + l), v3 = __ldg(base + (size_t)(p - 3 * R) * L + l);
+    consider(v0, p); consider(v1, p - R); consider(v2, p - 2 * R); consider(v3, p - 3 * R);
   }
-  for (; p < p1; p += R) consider(__ldg(base + (size_t)p * L + l), p);
+  for (; cnt > 0; --cnt, p -= R) consider(__ldg(base + (size_t)p * L + l), p);
   if (NMAX > 16) {  // large n: every (slab, r) lane writes its n candidates; the merge kernel selects among S*R*n
     Cand* dst = partial + ((((size_t)b * S + s) * R + r) * L + l) * n;
     for (int k = 0; k < n; ++k) dst[k] = top[k];
@@ -290,6 +293,17 @@ topn4_vec4_kernel(const float4* __restrict__ hm, int HW, int L4, int R, int S, i
   const int p0 = s * per, p1 = min(HW, p0 + per);
   const float4* base = hm + (size_t)b * HW * L4 + q;
 #define FLD_TOPN4_CONSIDER(V, P, C)                                                                      \
+  if ((V) > tv[C][3] || ((V) == tv[C][3] && ti[C][3] < 0)) {                                             \
+    if (better((V), (P), tv[C][3], ti[C][3])) {                                                          \
+      tv[C][3] = (V); ti[C][3] = (P);                                                                    \
+      _Pragma("unroll") for (int k = 3; k > 0; --k)                                                      \
+        if (better(tv[C][k], ti[C][k], tv[C][k - 1], ti[C][k - 1])) {                                    \
+          const float fv = tv[C][k]; tv[C][k] = tv[C][k - 1]; tv[C][k - 1] = fv;                         \
+          const int fi = ti[C][k]; ti[C][k] = ti[C][k - 1]; ti[C][k - 1] = fi;                           \
+        }                                                                                                \
+    }                                                                                                    \
+  }
+#define FLD_TOPN4_MERGE(V, P, C)                                                                            \
   if ((V) >= tv[C][3]) {                                                                                 \
     if (better((V), (P), tv[C][3], ti[C][3])) {                                                          \
       tv[C][3] = (V); ti[C][3] = (P);                                                                    \
@@ -302,13 +316,15 @@ topn4_vec4_kernel(const float4* __restrict__ hm, int HW, int L4, int R, int S, i
   }
 #define FLD_TOPN4_CONSIDER4(V4, P) \
   { FLD_TOPN4_CONSIDER((V4).x, (P), 0) FLD_TOPN4_CONSIDER((V4).y, (P), 1) FLD_TOPN4_CONSIDER((V4).z, (P), 2) FLD_TOPN4_CONSIDER((V4).w, (P), 3) }
-  int p = p0 + r;
-  for (; p + 3 * R < p1; p += 4 * R) {  // four independent 16-byte loads in flight per thread
-    const float4 v0 = __ldg(base + (size_t)p * L4), v1 = __ldg(base + (size_t)(p + R) * L4);
-    const float4 v2 = __ldg(base + (size_t)(p + 2 * R) * L4), v3 = __ldg(base + (size_t)(p + 3 * R) * L4);
-    FLD_TOPN4_CONSIDER4(v0, p) FLD_TOPN4_CONSIDER4(v1, p + R) FLD_TOPN4_CONSIDER4(v2, p + 2 * R) FLD_TOPN4_CONSIDER4(v3, p + 3 * R)
+  // descending pixel order: ties (higher index wins) arriving later never displace an entry
+  int cnt = (p0 + r < p1) ? (p1 - (p0 + r) + R - 1) / R : 0;
+  int p = p0 + r + (cnt - 1) * R;
+  for (; cnt >= 4; cnt -= 4, p -= 4 * R) {  // four independent 16-byte loads in flight per thread
+    const float4 v0 = __ldg(base + (size_t)p * L4), v1 = __ldg(base + (size_t)(p - R) * L4);
+    const float4 v2 = __ldg(base + (size_t)(p - 2 * R) * L4), v3 = __ldg(base + (size_t)(p - 3 * R) * L4);
+    FLD_TOPN4_CONSIDER4(v0, p) FLD_TOPN4_CONSIDER4(v1, p - R) FLD_TOPN4_CONSIDER4(v2, p - 2 * R) FLD_TOPN4_CONSIDER4(v3, p - 3 * R)
   }
-  for (; p < p1; p += R) {
+  for (; cnt > 0; --cnt, p -= R) {
     const float4 v = __ldg(base + (size_t)p * L4);
     FLD_TOPN4_CONSIDER4(v, p)
   }
@@ -326,10 +342,10 @@ topn4_vec4_kernel(const float4* __restrict__ hm, int HW, int L4, int R, int S, i
       for (int k = 0; k < 4; ++k) {
         const Cand c0 = cand4[((size_t)rr * L + 4 * q + 0) * 4 + k], c1 = cand4[((size_t)rr * L + 4 * q + 1) * 4 + k];
         const Cand c2 = cand4[((size_t)rr * L + 4 * q + 2) * 4 + k], c3 = cand4[((size_t)rr * L + 4 * q + 3) * 4 + k];
-        if (c0.idx >= 0) FLD_TOPN4_CONSIDER(c0.v, c0.idx, 0)
-        if (c1.idx >= 0) FLD_TOPN4_CONSIDER(c1.v, c1.idx, 1)
-        if (c2.idx >= 0) FLD_TOPN4_CONSIDER(c2.v, c2.idx, 2)
-        if (c3.idx >= 0) FLD_TOPN4_CONSIDER(c3.v, c3.idx, 3)
+        if (c0.idx >= 0) FLD_TOPN4_MERGE(c0.v, c0.idx, 0)   // other lanes' indices are not ordered against ours: exact tie rule
+        if (c1.idx >= 0) FLD_TOPN4_MERGE(c1.v, c1.idx, 1)
+        if (c2.idx >= 0) FLD_TOPN4_MERGE(c2.v, c2.idx, 2)
+        if (c3.idx >= 0) FLD_TOPN4_MERGE(c3.v, c3.idx, 3)
       }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -340,6 +356,7 @@ topn4_vec4_kernel(const float4* __restrict__ hm, int HW, int L4, int R, int S, i
     }
   }
 #undef FLD_TOPN4_CONSIDER4
+#undef FLD_TOPN4_MERGE
 #undef FLD_TOPN4_CONSIDER
 }
 

@@ -390,7 +390,7 @@ extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
 extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, int hw, int L, int64_t* class_map, fld_stream stream);
 
 static int net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, int64_t* cmap_out, fld_stream stream,
-                       double* xy_out = nullptr, double xy_thresh = 0.0) {
+                       double* xy_out = nullptr, double xy_thresh = 0.0, int xy_n = 0) {
   FLD_REQUIRE(net, "fld_net_forward: null net");
   int rc = fld_enter(net->h);
   if (rc) return rc;
@@ -464,8 +464,11 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         if (L.path == PATH_TC_TMA) {
           // fused decode: 1 = softmax written into the (skipped) SOFTMAX layer's tensor, 2 = int64 class map to the caller
           const bool last_pair = L.dc_fuse_softmax && (int)i + 2 == (int)net->layers.size();
-          const int mode = L.dc_fuse_softmax ? ((xy_out && last_pair) ? 3 : (cmap_out && last_pair) ? 2 : 1) : 0;
-          void* dst = mode == 3 ? (void*)xy_out : mode == 2 ? (void*)cmap_out : (mode == 1 ? ptr[i + 2] : pout);
+          // fused landmark decode: the soft centroid (n_points < 1); top-n decodes the materialised probabilities (a fused
+          // variant measured slower, see tc_deconv.cu)
+          const bool xy_fused = xy_out && last_pair && xy_n < 1;
+          const int mode = L.dc_fuse_softmax ? (xy_fused ? 3 : (cmap_out && last_pair) ? 2 : 1) : 0;
+          void* dst = mode >= 3 ? (void*)xy_out : mode == 2 ? (void*)cmap_out : (mode == 1 ? ptr[i + 2] : pout);
           float* acc = (float*)((char*)dense_scratch + align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256));
           TcDeconvPlan* plan = nullptr;
           for (auto& pe : L.dplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
@@ -477,7 +480,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           }
           rc = tc_deconv_run(plan, (const float*)pin, dst, mode, st, acc, xy_thresh);
           if (mode == 2) cmap_done = true;
-          if (mode == 3) xy_done = true;
+          if (mode >= 3) xy_done = true;
         } else if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
         else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
@@ -531,7 +534,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   if (xy_out && !xy_done) {  // no fused centroid available: soft-centroid decode of the final tensor
     const TensorInfo& o = net->tensors[nT - 1];
     FLD_REQUIRE(o.dtype == FLD_F32, "fld_net_forward_landmarks: final tensor must be fp32");
-    rc = fld_decode_heatmap_xy(net->h, (const float*)ptr[nT - 1], B, o.h, o.w, o.c, 0, xy_thresh, xy_out, stream);
+    rc = fld_decode_heatmap_xy(net->h, (const float*)ptr[nT - 1], B, o.h, o.w, o.c, xy_n < 1 ? 0 : xy_n, xy_thresh, xy_out, stream);
     if (rc) return rc;
   }
   if (out && !direct_out) {
@@ -543,10 +546,11 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   return FLD_OK;
 }
 
-extern "C" int fld_net_forward_landmarks(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, double thresh, double* xy,
-                                         fld_stream stream) {
-  FLD_REQUIRE(xy, "fld_net_forward_landmarks: null output");
-  return net_forward(net, in, B, workspace, ws_bytes, nullptr, nullptr, stream, xy, thresh);
+extern "C" int fld_net_forward_landmarks(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int n_points, double thresh,
+                                         double* xy, fld_stream stream) {
+  FLD_REQUIRE(B == 0 || xy, "fld_net_forward_landmarks: null output");
+  FLD_REQUIRE(n_points <= FLD_MAX_TOPN, "fld_net_forward_landmarks: n_points must be <= %d", FLD_MAX_TOPN);
+  return net_forward(net, in, B, workspace, ws_bytes, nullptr, nullptr, stream, xy, thresh, n_points);
 }
 
 extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {

@@ -54,7 +54,7 @@ SIGNATURES = {
     "fld_net_tensor_offset": (ctypes.c_int64, [_vp, _i, _i]),
     "fld_net_forward": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "fld_net_forward_classmap": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
-    "fld_net_forward_landmarks": (_i, [_vp, _vp, _i, _vp, _sz, ctypes.c_double, _vp, _vp]),
+    "fld_net_forward_landmarks": (_i, [_vp, _vp, _i, _vp, _sz, _i, ctypes.c_double, _vp, _vp]),
     "fld_net_set_profiling": (_i, [_vp, _i]),
     "fld_net_layer_times": (_i, [_vp, _vp, _i]),
     "fld_decode_regress": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),

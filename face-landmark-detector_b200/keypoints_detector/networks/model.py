@@ -352,11 +352,12 @@ class Model:
             N.check(lib.fld_net_forward_classmap(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(cmap), N.stream_ptr(dev)))
         return cmap
 
-    def forward_landmarks_device(self, x, dtype=None, thresh=0.0, lane=0):
-        """Segmentation models: forward + soft-centroid decode of every class channel (reference utils/metrics.py:46-109,
-        get_average_xy with n_points < 1 over transfer_target's channels) in one call -> float64 CUDA [B, 2L] =
-        (x0, y0, x1, y1, ...).  In bfloat16 mode the sums are accumulated inside the last transposed conv's epilogue
-        (config C3's fused soft-argmax): the probabilities never reach HBM."""
+    def forward_landmarks_device(self, x, dtype=None, thresh=0.0, lane=0, n_points=0):
+        """Segmentation models: forward + landmark decode of every class channel (reference utils/metrics.py:46-109,
+        get_average_xy over transfer_target's channels; n_points < 1 = soft centroid, n_points >= 1 = top-n centroid) in one
+        call -> float64 CUDA [B, 2L] = (x0, y0, x1, y1, ...).  In bfloat16 mode the soft centroid is accumulated inside the last
+        transposed conv's epilogue (config C3's fused soft-argmax): the probabilities never reach HBM; top-n decodes the
+        probabilities materialised in the workspace."""
         assert self.kind == "segmentation"
         lib = N.load_library()
         assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
@@ -375,8 +376,8 @@ class Model:
             base = ws.data_ptr()
             al = (-base) % 1024
             xy = torch.empty((B, 2 * self.graph.shapes[-1][2]), dtype=torch.float64, device=x.device)
-            N.check(lib.fld_net_forward_landmarks(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, float(thresh), N.ptr(xy),
-                                                  N.stream_ptr(dev)))
+            N.check(lib.fld_net_forward_landmarks(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, int(n_points), float(thresh),
+                                                  N.ptr(xy), N.stream_ptr(dev)))
         return xy
 
     def intermediate(self, x, tensor, dtype=None):

@@ -136,14 +136,15 @@ FLD_API int fld_net_forward(fld_net* net, const void* in, int B, void* workspace
 FLD_API int fld_net_forward_classmap(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int64_t* class_map,
                                      fld_stream stream);
 
-/* Forward of a segmentation graph followed by the soft-centroid decode of every class channel of its softmax output
- * (utils/metrics.py:46-80 get_average_xy with n_points < 1, applied per channel as transfer_target does, :83-109):
- * xy double [B, 2L] = (x0, y0, x1, y1, ...) in heat-map pixels, (-1, -1) where mean(p) <= thresh.  In FLD_BF16 mode, when
- * the graph ends in Conv2DTranspose(k = 2*stride) + softmax (fcn_8 / fcn_32), the per-class sums are accumulated in the
- * transposed conv's epilogue (fp32 atomics: summation order, hence the last bits, vary from run to run) and the
- * probabilities are never written to HBM; otherwise the final tensor is decoded by fld_decode_heatmap_xy. */
-FLD_API int fld_net_forward_landmarks(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, double thresh, double* xy,
-                                      fld_stream stream);
+/* Forward of a segmentation graph followed by the landmark decode of every class channel of its softmax output
+ * (utils/metrics.py:46-80 get_average_xy applied per channel as transfer_target does, :83-109): n_points < 1 = soft centroid over
+ * the whole map, n_points >= 1 = weighted centroid of the n_points largest values.  xy double [B, 2L] = (x0, y0, x1, y1, ...) in
+ * heat-map pixels, (-1, -1) where sum / n <= thresh.  In FLD_BF16 mode, when the graph ends in Conv2DTranspose(k = 2*stride) +
+ * softmax (fcn_8 / fcn_32), the SOFT centroid is accumulated in the transposed conv's epilogue (fp32 atomics: summation order,
+ * hence the last bits, vary from run to run) and the probabilities are never written to HBM.  In every other case (top-n,
+ * fp32 mode, other graphs) the final tensor is materialised in the workspace and decoded by fld_decode_heatmap_xy. */
+FLD_API int fld_net_forward_landmarks(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int n_points, double thresh,
+                                      double* xy, fld_stream stream);
 
 /* Per-layer device timing (bench.py's live roofline measurement): when enabled, fld_net_forward brackets
  * every layer with CUDA events on the launching stream; fld_net_layer_times waits for the last profiled

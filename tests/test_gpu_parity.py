@@ -132,6 +132,14 @@ def test_heatmap_xy_golden_and_oracle(dev, golden):
         np.testing.assert_allclose(xy, ref, rtol=1e-12, atol=1e-12)
     xy = metrics.heatmap_xy_device(T(big, dev), 0, 0.0).cpu().numpy()
     np.testing.assert_allclose(xy, o_dec.transfer_target(big, 0.0, 0, reproduce_slip=False), rtol=1e-5)
+    # tie-heavy maps (saturated softmax outputs are mostly exact zeros / ones): the higher flat index wins among equal values
+    ties = np.round(gi.heatmaps(43, 2, 72, 104, 68) * 3).astype(np.float32) / 3
+    ties[0, :, :, :20] = 0.0
+    ties[1, 10:40, :, 20:30] = 1.0
+    for n in (4, 2, 9):
+        xy = metrics.heatmap_xy_device(T(ties, dev), n, -1.0).cpu().numpy()
+        ref = o_dec.transfer_target(ties, -1.0, n, reproduce_slip=False)
+        np.testing.assert_allclose(xy, ref, rtol=1e-12, atol=1e-12)
 
 
 # ------------------------------------------------------------------------------------------------ a10 alignment
@@ -389,6 +397,14 @@ def test_fcn8_fused_soft_centroid(dev):
         assert np.abs(xy.cpu().numpy().reshape(3, 68, 2) - ref).max() < tol
     # sentinel: mean probability 1/68 <= thresh -> (-1, -1) for every class
     assert (m.forward_landmarks_device(xt, "bfloat16", thresh=0.5) == -1).all()
+    # top-n centroid (the reference wrappers' effective default is n_points = 4) behind the same entry point: probabilities are
+    # materialised in the workspace and decoded by the stand-alone kernel, bit-identical to doing the two steps by hand
+    for dtype in ("bfloat16", "float32"):
+        probs = m.forward_device(xt, dtype).view(3, 72, 104, 68).contiguous()
+        for n in (1, 3, 4, 9):
+            xy = m.forward_landmarks_device(xt, dtype, n_points=n)
+            assert torch.equal(xy, metrics.heatmap_xy_device(probs, n, 0.0)), (dtype, n)
+    assert (m.forward_landmarks_device(xt, "bfloat16", thresh=1.5, n_points=4) == -1).all()   # probabilities never exceed 1
 
 
 def test_prediction_dropin_fcn(dev, tmp_path):

@@ -104,11 +104,13 @@ def main():
         med_p, _ = timeit(lambda: m.forward_device(x, dtype), reps=5, warm=1)
         med_c, _ = timeit(lambda: m.forward_classmap_device(x, dtype), reps=5, warm=1)
         med_l, _ = timeit(lambda: m.forward_landmarks_device(x, dtype), reps=5, warm=1)
+        med_t, _ = timeit(lambda: m.forward_landmarks_device(x, dtype, n_points=4), reps=5, warm=1)
         names = [L["name"] for L in m.graph.layers]
         top = sorted(zip(names, acc), key=lambda t: -t[1])[:12]
         print(json.dumps({"kernel": label + " forward", "dtype": dtype, "batch": B, "ms_layers_sum": float(acc.sum()),
                           "ms_forward_probs": med_p, "ms_forward_classmap": med_c, "images_per_s_probs": B / med_p * 1e3,
                           "images_per_s_classmap": B / med_c * 1e3, "ms_forward_soft_centroid": med_l, "images_per_s_soft_centroid": B / med_l * 1e3,
+                          "ms_forward_top4_centroid": med_t, "images_per_s_top4_centroid": B / med_t * 1e3,
                           "last_deconv_ms": {"probs": round(float(acc[-2]), 4), "classmap": round(float(accc[-2]), 4)},
                           "layer_ms": {n: round(float(t), 4) for n, t in (zip(names, acc) if len(names) <= 20 else top)}}), flush=True)
         del x
