@@ -657,3 +657,29 @@ def test_no_out_of_bounds_writes(dev):
 def N_lib():
     from keypoints_detector import _native as N
     return N.load_library()
+
+
+def test_cli_predict_end_to_end(dev, tmp_path):
+    """`face_landmark_detect predict --checkpoints_path P --inp IMG` (reference scripts/cli.py:68-74) through
+    a saved checkpoint + `_config.json` sidecar; the coloured class map it writes decodes back to the model's own class map."""
+    import cv2
+    import sys
+    from click.testing import CliRunner
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1] / "face-landmark-detector_b200"))
+    from scripts import cli
+    from keypoints_detector import prediction
+    from keypoints_detector.networks.basic_models import LANDMARKS_MODELS
+    m = LANDMARKS_MODELS["fcn_8_vanilla"](68, input_height=64, input_width=64).init_weights(8)
+    ck = str(tmp_path / "w")
+    m.save_weights(ck + ".00001")
+    m.save_config(ck, "fcn_8_vanilla")
+    img = gi.image(77, 90, 120)
+    inp = str(tmp_path / "face.png")
+    cv2.imwrite(inp, img)
+    out = str(tmp_path / "seg.png")
+    res = CliRunner().invoke(cli.main, ["predict", "--checkpoints_path", ck, "--inp", inp, "--out_fname", out])
+    assert res.exit_code == 0, res.output
+    seg = cv2.imread(out)
+    assert seg is not None and seg.shape[2] == 3
+    cm = prediction.keypts_predict(checkpoints_path=ck, inp=inp)
+    assert cm.shape == (m.output_height, m.output_width) and cm.dtype == np.int64
