@@ -398,6 +398,30 @@ __global__ void deconv_im2col_kernel(const float* __restrict__ in, __nv_bfloat16
   A[i] = __floats2bfloat162_rn(v[0], v[1]);
 }
 
+// C % 4 == 0: one warp per row of A; lane j handles the 8-byte chunk j (4 channels of one tap): a 16-byte load, an 8-byte store,
+// the row's index arithmetic once per warp.  (The element-wise kernel above ran at 0.5 TB/s: 0.26 ms per 256 images for up8.)
+__global__ void deconv_im2col_vec4_kernel(const float4* __restrict__ in, uint2* __restrict__ A, long long M, int h, int w, int C4, int Kp4) {
+  const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int GW = w + 1, GH = h + 1;
+  const long long b = g / (GH * GW);
+  const int rem = (int)(g - b * (GH * GW));
+  const int oy = rem / GW, ox = rem - oy * GW;
+  uint2* row = A + g * Kp4;
+  for (int j = lane; j < Kp4; j += 32) {
+    const int t = j / C4, q = j - t * C4;
+    const int iy = oy - 1 + (t >> 1), ix = ox - 1 + (t & 1);
+    uint2 o = make_uint2(0u, 0u);
+    if (t < 4 && iy >= 0 && iy < h && ix >= 0 && ix < w) {
+      const float4 v = __ldg(in + ((b * h + iy) * w + ix) * C4 + q);
+      o.x = pack_bf16(v.x, v.y);
+      o.y = pack_bf16(v.z, v.w);
+    }
+    row[j] = o;
+  }
+}
+
 // (x, y) = (sum p*col / sum p, sum p*row / sum p); (-1, -1) when mean(p) <= thresh (utils/metrics.py:78-80)
 __global__ void centroid_finish_kernel(const float* __restrict__ acc, long long n, double hw, double thresh, double* __restrict__ xy) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,7 +540,11 @@ size_t tc_deconv_acc_bytes(int B, int Cout) { return (size_t)B * Cout * 3 * size
 
 int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st, float* acc, double thresh) {
   if (pl->p.total_tiles == 0) return FLD_OK;
-  {
+  if (pl->C % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    deconv_im2col_vec4_kernel<<<(unsigned)((pl->p.M + 7) / 8), 256, 0, st>>>((const float4*)in, (uint2*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C / 4,
+                                                                          pl->Kp / 4);
+    FLD_LAUNCHED();
+  } else {
     const long long n = pl->p.M * (pl->Kp / 2);
     deconv_im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat162*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C, pl->Kp);
     FLD_LAUNCHED();
