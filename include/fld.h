@@ -90,11 +90,13 @@ FLD_API int fld_image_array(fld_handle* h, const uint8_t* images, int B, int H, 
 typedef enum {
   FLD_OP_CONV = 0,    /* Conv2D (+ZeroPadding2D) [+BatchNormalization folded] [+ReLU/ReLU6] [+MaxPool 2x2] */
   FLD_OP_DECONV = 1,  /* Conv2DTranspose padding='valid', no bias (fcn.py:104,114,121,145) */
-  FLD_OP_ADD = 2,     /* fcn.py:55-86 crop + KL.Add: both inputs cropped (bottom/right) to the smaller */
+  FLD_OP_ADD = 2,     /* fcn.py:55-86 crop + KL.Add: both inputs cropped (bottom/right) to the smaller; with `act`:
+                         the residual add -> ReLU of resnet50.py:68-69,117-118 */
   FLD_OP_DENSE = 3,   /* Flatten (H,W,C row-major) + Dense */
   FLD_OP_SOFTMAX = 4, /* networks/utils.py:28-30: softmax over channels, output [B, oh*ow, C] */
-  FLD_OP_DWCONV = 5,  /* DepthwiseConv2D 3x3 (mobilenet.py:37-47) */
-  FLD_OP_MAXPOOL = 6  /* stand-alone MaxPooling2D (resnet50.py:149) */
+  FLD_OP_DWCONV = 5,  /* ZeroPadding2D + DepthwiseConv2D(depth_multiplier 1) [+BN folded] [+ReLU6] (mobilenet.py:37-47);
+                         kh, kw, stride, pad_*, act as for CONV; cout = 0 or the input channel count */
+  FLD_OP_MAXPOOL = 6  /* stand-alone MaxPooling2D((kh,kh), strides=stride) 'valid' (resnet50.py:149) */
 } fld_op;
 
 typedef enum { FLD_ACT_NONE = 0, FLD_ACT_RELU = 1, FLD_ACT_RELU6 = 2 } fld_act;
@@ -126,8 +128,10 @@ FLD_API int fld_net_tensor_shape(const fld_net* net, int tensor, int32_t* hwc);
 FLD_API size_t fld_net_workspace_bytes(const fld_net* net, int B);
 /* Offset (bytes) of a tensor inside the workspace for batch B (debug / parity of intermediate levels) */
 FLD_API int64_t fld_net_tensor_offset(const fld_net* net, int tensor, int B);
-/* in: uint8 or float32 NHWC [B,in_h,in_w,in_c].  out: float32, final tensor [B, ...] (converted from
- * bf16 in FLD_BF16 mode), may be NULL when only the workspace copy is wanted. */
+/* in: uint8 or float32 NHWC [B,in_h,in_w,in_c].  out: float32, final tensor [B, ...]; the last layer writes straight into it
+ * (no device-to-device copy).  NULL keeps the result in the workspace only (fld_net_tensor_offset).  The workspace holds
+ * the activations of ONE forward: forwards that overlap on different streams need a workspace each; the net object (weights,
+ * kernel plans) is shared. */
 FLD_API int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream);
 
 /* Forward of a segmentation graph followed by prediction.py:209 (argmax over classes, first max wins): class_map int64
