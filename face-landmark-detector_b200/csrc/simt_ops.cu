@@ -183,6 +183,20 @@ __global__ void add_crop_kernel(const float* __restrict__ a, int AH, int AW, con
   out[i] = a[(((size_t)b * AH + y) * AW + x) * C + c] + b2[(((size_t)b * BH + y) * BW + x) * C + c];
 }
 
+// C % 4 == 0: 16-byte accesses (the FCN skip adds work on 68-channel fp32 score maps)
+__global__ void add_crop_vec4_kernel(const float4* __restrict__ a, int AH, int AW, const float4* __restrict__ b2, int BH, int BW,
+                                     float4* __restrict__ out, int B, int OH, int OW, int C4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * OH * OW * C4) return;
+  const int c = (int)(i % C4);
+  long long r = i / C4;
+  const int x = (int)(r % OW); r /= OW;
+  const int y = (int)(r % OH);
+  const int b = (int)(r / OH);
+  const float4 u = __ldg(a + (((size_t)b * AH + y) * AW + x) * C4 + c), v = __ldg(b2 + (((size_t)b * BH + y) * BW + x) * C4 + c);
+  out[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+}
+
 // networks/utils.py:28-30: softmax over the channel axis, one warp per pixel
 __global__ void softmax_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_px, int C) {
   const long long px = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -333,6 +347,12 @@ int simt_add_crop(const float* a, int AH, int AW, const float* b, int BH, int BW
                   cudaStream_t st) {
   if (B == 0) return FLD_OK;
   const long long total = (long long)B * OH * OW * C;
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    add_crop_vec4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>((const float4*)a, AH, AW, (const float4*)b, BH, BW, (float4*)out, B, OH,
+                                                                            OW, C / 4);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
   add_crop_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, AH, AW, b, BH, BW, out, B, OH, OW, C);
   FLD_LAUNCHED();
   return FLD_OK;
