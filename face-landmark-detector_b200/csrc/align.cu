@@ -4,14 +4,31 @@
 // are "fp64 closed-form Umeyama, then cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of OpenCV
 // 4.13", reproduced bit-exactly with OpenCV's fixed-point scheme (1/32 px sub-pixel, 15-bit weights).
 //
-// One CTA per face.  Thread 0 fits (sequential fp64 sums, no FMA contraction, so M is bit-identical
-// to the CPU oracle), the CTA builds the per-column / per-row fixed-point coordinate tables in shared
-// memory, then every thread produces 4 consecutive output pixels (12 bytes -> three 32-bit stores)
-// from 8-byte-aligned source loads.  Algorithmic traffic ~37.6 kB written + source footprint read per face.
-// MEASURED (ncu, round 1, config C4): DRAM runs at 17 % while the L1 tag stage is the busiest unit — every warp-level
-// load touches ~21 sectors on many lines (rotated faces put each lane on its own source row).  Two leaner-ALU rewrites
-// (IDP.4A blends, 32-bit funnel loads, loads hoisted for MLP) were SLOWER (0.34 / 0.39 ms vs 0.32 ms) because they issue
-// more, narrower requests; the next step is a 2-D warp->pixel mapping with shared-memory staged stores.
+// The fit is warp-parallel: lane l accumulates points l, l+32, ... in index order, then a fixed xor-butterfly
+// (16, 8, 4, 2, 1) combines the lanes in fp64 without FMA contraction — a deterministic summation tree that
+// oracle/align.py mirrors, so M is bit-identical to the CPU oracle.
+//
+// Two warp kernels:
+//   * align_tile_kernel (round 2; C == 3, 16-byte-aligned frame rows, output a multiple of 16 x 16, <= 256 x 256):
+//     round 1's per-pixel global gathers were L1-tag / issue bound (ncu: ~21 sectors per warp load, 107 instructions per
+//     output pixel, DRAM at 16 %).  Here a 64-thread CTA walks the 16 x 16-pixel output tiles of its face; the source
+//     bounding box of a tile (a square for a similarity transform) arrives by ONE TMA load into a shared-memory ring
+//     (out-of-frame bytes are zero-filled by the tensor map = BORDER_CONSTANT 0, so the blend has no bounds checks and
+//     32-bit addresses), with the next tiles' boxes in flight while the current one is blended.  The tensor-map box is
+//     fixed per map, so eight maps (box sides 16..80 source pixels) are passed and the face picks the smallest that fits.
+//     The blend is exact integer arithmetic: out = (sum_ij a_i b_j p_ij + 512) >> 10 with a = (32 - fx, fx),
+//     b = (32 - fy, fy) (OpenCV's 15-bit table is exactly 32 a_i b_j for 5-bit fractions; its +-1 fix-ups at fx = fy = 0
+//     cannot change the rounded byte), computed as two IDP.4A per channel over the gathered (p00, p01, p10, p11) bytes.
+//     Tiles whose box does not fit the class (never for similarity transforms; possible for caller matrices with
+//     shear) and faces scaled down by more than ~3.7x take the per-pixel global path below.
+//   * align_warp_kernel (round 1): any C in {1, 3, 4}, any shape; one CTA per (face, row block), per-pixel global loads.
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include <cuda.h>
 #include "common.cuh"
 
 namespace {
@@ -28,42 +45,50 @@ struct Fit {
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
 
-__device__ void fit_similarity(const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int Nt,
-                               int five_point, double* M) {
-  // source points
-  double px[5], py[5];
+// fixed summation tree over the warp: every lane ends up with the same value
+__device__ __forceinline__ double warp_tree_sum(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = da(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+// Whole warp (all 32 lanes converged).  Source point i: five_point ? reduced iBUG-68 point : marks[i].
+// Sums: lane l takes points l, l+32, ... sequentially, then warp_tree_sum.  Lane 0 writes M[6].
+__device__ void fit_similarity_warp(const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int five_point,
+                                    double* M, int lane) {
   const int n = five_point ? 5 : N;
-  double mpx = 0, mpy = 0, mqx = 0, mqy = 0;
-  if (five_point) {
-    double ax = 0, ay = 0, bx = 0, by = 0;
-    for (int i = 36; i < 42; ++i) { ax = da(ax, (double)marks[2 * i]); ay = da(ay, (double)marks[2 * i + 1]); }
-    for (int i = 42; i < 48; ++i) { bx = da(bx, (double)marks[2 * i]); by = da(by, (double)marks[2 * i + 1]); }
-    px[0] = ax / 6.0; py[0] = ay / 6.0;
-    px[1] = bx / 6.0; py[1] = by / 6.0;
-    px[2] = marks[60]; py[2] = marks[61];
-    px[3] = marks[96]; py[3] = marks[97];
-    px[4] = marks[108]; py[4] = marks[109];
-    for (int i = 0; i < 5; ++i) {
-      mpx = da(mpx, px[i]); mpy = da(mpy, py[i]);
-      mqx = da(mqx, tmpl[2 * i]); mqy = da(mqy, tmpl[2 * i + 1]);
+  auto src_pt = [&](int i, double& x, double& y) {
+    if (!five_point) { x = (double)marks[2 * i]; y = (double)marks[2 * i + 1]; return; }
+    if (i < 2) {  // eye centres: six landmarks summed in index order, / 6
+      const int b0 = i == 0 ? 36 : 42;
+      double ax = 0, ay = 0;
+      for (int k = b0; k < b0 + 6; ++k) { ax = da(ax, (double)marks[2 * k]); ay = da(ay, (double)marks[2 * k + 1]); }
+      x = ax / 6.0; y = ay / 6.0;
+    } else {
+      const int k = i == 2 ? 30 : (i == 3 ? 48 : 54);
+      x = (double)marks[2 * k]; y = (double)marks[2 * k + 1];
     }
-  } else {
-    for (int i = 0; i < n; ++i) {
-      mpx = da(mpx, (double)marks[2 * i]); mpy = da(mpy, (double)marks[2 * i + 1]);
-      mqx = da(mqx, tmpl[2 * i]); mqy = da(mqy, tmpl[2 * i + 1]);
-    }
+  };
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int i = lane; i < n; i += 32) {
+    double x, y;
+    src_pt(i, x, y);
+    s0 = da(s0, x); s1 = da(s1, y); s2 = da(s2, tmpl[2 * i]); s3 = da(s3, tmpl[2 * i + 1]);
   }
   const double dn = (double)n;
-  mpx = mpx / dn; mpy = mpy / dn; mqx = mqx / dn; mqy = mqy / dn;
+  const double mpx = warp_tree_sum(s0) / dn, mpy = warp_tree_sum(s1) / dn;
+  const double mqx = warp_tree_sum(s2) / dn, mqy = warp_tree_sum(s3) / dn;
   double var = 0, a = 0, b = 0, c = 0, d = 0;
-  for (int i = 0; i < n; ++i) {
-    const double sx = five_point ? px[i] : (double)marks[2 * i];
-    const double sy = five_point ? py[i] : (double)marks[2 * i + 1];
+  for (int i = lane; i < n; i += 32) {
+    double sx, sy;
+    src_pt(i, sx, sy);
     const double x = da(sx, -mpx), y = da(sy, -mpy);
     const double qx = da(tmpl[2 * i], -mqx), qy = da(tmpl[2 * i + 1], -mqy);
     var = da(var, da(dm(x, x), dm(y, y)));
     a = da(a, dm(qx, x)); b = da(b, dm(qx, y)); c = da(c, dm(qy, x)); d = da(d, dm(qy, y));
   }
+  var = warp_tree_sum(var); a = warp_tree_sum(a); b = warp_tree_sum(b); c = warp_tree_sum(c); d = warp_tree_sum(d);
+  if (lane != 0) return;
   const double P = da(a, d), Q = da(c, -b);
   if (var == 0.0 || (P == 0.0 && Q == 0.0) || !isfinite(var) || !isfinite(P) || !isfinite(Q)) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -83,7 +108,35 @@ __device__ void invert_affine(const double* M, double* iM) {
   iM[3] = i10; iM[4] = i11; iM[5] = da(dm(-i10, M[2]), -dm(i11, M[5]));
 }
 
+// Warp 0 of the CTA: fit (or take the caller's matrix), validate, invert; every thread reads `fit` after a __syncthreads.
+__device__ __forceinline__ void cta_fit(Fit& fit, int face, int F, const int32_t* __restrict__ face2frame,
+                                        const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int five_point,
+                                        const double* __restrict__ M_in, double* __restrict__ M_out, bool write_M, int tid) {
+  if (tid >= 32) return;
+  if (M_in) {
+    if (tid < 6) fit.M[tid] = M_in[(size_t)face * 6 + tid];
+  } else {
+    fit_similarity_warp(marks + (size_t)face * N * 2, N, tmpl, five_point, fit.M, tid);
+  }
+  __syncwarp();
+  if (tid == 0) {
+    int ok = 1;
+    for (int i = 0; i < 6; ++i) ok &= isfinite(fit.M[i]) ? 1 : 0;
+    const int fr = face2frame[face];
+    if (fr < 0 || fr >= F) ok = 0;
+    if (ok) invert_affine(fit.M, fit.iM);
+    fit.ok = ok;
+    if (M_out && write_M) for (int i = 0; i < 6; ++i) M_out[(size_t)face * 6 + i] = fit.M[i];
+  }
+}
+
 __device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
+
+// cv2's fixed-point coordinate tables (App. B.2 step 2)
+__device__ __forceinline__ int tab_ad(const Fit& fit, int x) { return (int)__double2ll_rn(dm(dm(fit.iM[0], (double)x), 1024.0)); }
+__device__ __forceinline__ int tab_bd(const Fit& fit, int x) { return (int)__double2ll_rn(dm(dm(fit.iM[3], (double)x), 1024.0)); }
+__device__ __forceinline__ int tab_X0(const Fit& fit, int y) { return (int)__double2ll_rn(dm(da(dm(fit.iM[1], (double)y), fit.iM[2]), 1024.0)) + 16; }
+__device__ __forceinline__ int tab_Y0(const Fit& fit, int y) { return (int)__double2ll_rn(dm(da(dm(fit.iM[4], (double)y), fit.iM[5]), 1024.0)) + 16; }
 
 // six consecutive bytes starting at an arbitrary address, from two aligned 8-byte loads
 __device__ __forceinline__ uint64_t load6(const uint8_t* p) {
@@ -96,6 +149,232 @@ __device__ __forceinline__ uint64_t load6(const uint8_t* p) {
   return (lo >> sh) | (hi << (64 - sh));
 }
 
+// One output pixel of a 3-channel frame by per-pixel global loads with full bounds handling (BORDER_CONSTANT 0).
+// X, Y: fixed-point source coordinates (1/32 px).  Returns the three bytes in bits [0,24).
+__device__ __forceinline__ uint32_t blend_px_global3(const uint8_t* __restrict__ frame, int H, int W, size_t row, int X, int Y) {
+  const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+  const int fx = X & 31, fy = Y & 31;
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32;
+  const int w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  int c[3] = {0, 0, 0};
+  if (sx >= -1 && sy >= -1 && sx < W && sy < H) {
+    const bool x0in = sx >= 0, x1in = sx + 1 < W, y0in = sy >= 0, y1in = sy + 1 < H;
+    const uint8_t* p0 = frame + (ptrdiff_t)sy * (ptrdiff_t)row + (ptrdiff_t)sx * 3;
+    const uint8_t* p1 = p0 + row;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int t0 = (y0in && x0in) ? p0[ch] : 0, t1 = (y0in && x1in) ? p0[3 + ch] : 0;
+      const int t2 = (y1in && x0in) ? p1[ch] : 0, t3 = (y1in && x1in) ? p1[3 + ch] : 0;
+      c[ch] = w00 * t0 + w01 * t1 + w10 * t2 + w11 * t3;
+    }
+  }
+  return (uint32_t)((c[0] + 16384) >> 15) | ((uint32_t)((c[1] + 16384) >> 15) << 8) | ((uint32_t)((c[2] + 16384) >> 15) << 16);
+}
+
+// ------------------------------------------------------------------------------------------------ PTX (TMA / mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < 20000000u; ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  printf("fld align: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ tile kernel
+constexpr int kTile = 16;          // output tile edge
+constexpr int kTileThreads = 64;   // 16 rows x 4 groups of 4 pixels
+constexpr int kNumCls = 8;
+constexpr int kMaxOut = 128;       // tables are static shared arrays
+constexpr int kMaxBuf = 4;
+constexpr int kRingBytes = 27 * 1024;
+// box side (source pixels) per class; rows = side, bytes per row = round16(3 * side + 15) (start is floored to 16 bytes)
+__host__ __device__ constexpr int cls_side(int k) { return k == 0 ? 16 : k == 1 ? 20 : k == 2 ? 24 : k == 3 ? 32 : k == 4 ? 40 : k == 5 ? 48 : k == 6 ? 64 : 80; }
+__host__ __device__ constexpr int cls_bw(int k) { return (3 * cls_side(k) + 15 + 15) & ~15; }
+
+struct AlignMaps { CUtensorMap m[kNumCls]; };
+
+struct TileArgs {
+  const uint8_t* frames;
+  const int32_t* face2frame;
+  const float* marks;
+  const double* tmpl;
+  const double* M_in;
+  double* M_out;
+  uint8_t* crops;
+  int F, H, W, N, five_point, out_h, out_w, ysplit;
+};
+
+__global__ void __launch_bounds__(kTileThreads)
+align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ Fit fit;
+  __shared__ __align__(16) int s_ad[kMaxOut], s_bd[kMaxOut], s_X0[kMaxOut], s_Y0[kMaxOut];
+  __shared__ int s_ox[(kMaxOut / kTile) * (kMaxOut / kTile)], s_oy[(kMaxOut / kTile) * (kMaxOut / kTile)];   // per tile of this CTA: box origin (byte column, row); ox = INT_MIN -> global path
+  __shared__ __align__(8) uint64_t full_bar[kMaxBuf];
+  __shared__ int s_cls;
+
+  const int tid = threadIdx.x;
+  const int face = blockIdx.x;
+  const int tiles_x = p.out_w / kTile, tiles_y = p.out_h / kTile;
+  const int ty_per = (tiles_y + p.ysplit - 1) / p.ysplit;
+  const int ty0 = blockIdx.y * ty_per, ty1 = min(tiles_y, ty0 + ty_per);
+  const int T = max(0, ty1 - ty0) * tiles_x;
+  const uint32_t ring = (smem_u32(ring_raw) + 127u) & ~127u;
+
+  cta_fit(fit, face, p.F, p.face2frame, p.marks, p.N, p.tmpl, p.five_point, p.M_in, p.M_out, blockIdx.y == 0, tid);
+  if (tid == 0) {
+    for (int i = 0; i < kMaxBuf; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint8_t* crop = p.crops + (size_t)face * p.out_h * p.out_w * 3;
+  if (T == 0) return;
+  if (!fit.ok) {
+    uint32_t* c4 = reinterpret_cast<uint32_t*>(crop + (size_t)ty0 * kTile * p.out_w * 3);   // 16 * out_w * 3 bytes per tile row: 4-byte multiple
+    const int n4 = (ty1 - ty0) * kTile * p.out_w * 3 / 4;
+    for (int i = tid; i < n4; i += kTileThreads) c4[i] = 0u;
+    return;
+  }
+  for (int x = tid; x < p.out_w; x += kTileThreads) { s_ad[x] = tab_ad(fit, x); s_bd[x] = tab_bd(fit, x); }
+  for (int y = ty0 * kTile + tid; y < ty1 * kTile; y += kTileThreads) { s_X0[y] = tab_X0(fit, y); s_Y0[y] = tab_Y0(fit, y); }
+  if (tid == 0) {
+    // box class from the linear part: a 16 x 16 tile spans 15 * (|i00| + |i01|) source columns and 15 * (|i10| + |i11|) rows,
+    // plus the second tap and the floor/round slack
+    const double ex = 15.0 * (fabs(fit.iM[0]) + fabs(fit.iM[1])), ey = 15.0 * (fabs(fit.iM[3]) + fabs(fit.iM[4]));
+    const double e = fmax(ex, ey) + 3.0;
+    int cls = -1;
+    if (e < 4096.0) {
+      const int side = (int)ceil(e);
+      for (int k = 0; k < kNumCls; ++k) if (side <= cls_side(k)) { cls = k; break; }
+    }
+    s_cls = cls;
+  }
+  __syncthreads();
+  const int cls = s_cls;
+  const int BW = cls >= 0 ? cls_bw(cls) : 0, BH = cls >= 0 ? cls_side(cls) : 0;
+  // tile origins (exact extremes: the tables are monotone, so min / max sit at the tile's first / last column and row)
+  for (int t = tid; t < T; t += kTileThreads) {
+    const int ty = ty0 + t / tiles_x, tx = t - (t / tiles_x) * tiles_x;
+    const int xa = s_ad[tx * kTile], xb = s_ad[tx * kTile + kTile - 1], ya = s_X0[ty * kTile], yb = s_X0[ty * kTile + kTile - 1];
+    const int ua = s_bd[tx * kTile], ub = s_bd[tx * kTile + kTile - 1], va = s_Y0[ty * kTile], vb = s_Y0[ty * kTile + kTile - 1];
+    const long long xmin = (long long)min(xa, xb) + min(ya, yb), xmax = (long long)max(xa, xb) + max(ya, yb);
+    const long long ymin = (long long)min(ua, ub) + min(va, vb), ymax = (long long)max(ua, ub) + max(va, vb);
+    int ox = INT_MIN, oy = 0;
+    if (cls >= 0 && xmin > -(1ll << 30) && xmax < (1ll << 30) && ymin > -(1ll << 30) && ymax < (1ll << 30)) {
+      const int sx0 = (int)(xmin >> 10), sx1 = (int)(xmax >> 10), sy0 = (int)(ymin >> 10), sy1 = (int)(ymax >> 10);
+      const int bx = (3 * sx0) & ~15;                  // floor to 16 bytes (two's complement: also for negatives)
+      if (3 * (sx1 + 2) - bx <= BW && sy1 + 2 - sy0 <= BH && sx0 > -30000 && sx1 < 30000 && sy0 > -30000 && sy1 < 30000) { ox = bx; oy = sy0; }
+    }
+    s_ox[t] = ox; s_oy[t] = oy;
+  }
+  __syncthreads();
+
+  const int frame_idx = p.face2frame[face];
+  const uint8_t* frame = p.frames + (size_t)frame_idx * p.H * p.W * 3;
+  const size_t row = (size_t)p.W * 3;
+  const uint32_t box_bytes = (uint32_t)(BW * BH);
+  const uint32_t buf_pitch = (box_bytes + 16u + 127u) & ~127u;       // + 16: the last pixel's third word may lie past the box
+  const int nbuf = cls >= 0 ? max(1, min(kMaxBuf, (int)(kRingBytes / buf_pitch))) : 1;
+  const CUtensorMap* tm = &maps.m[cls >= 0 ? cls : 0];
+
+  auto issue = [&](int t) {   // one thread
+    const int ox = s_ox[t];
+    if (ox == INT_MIN) return;
+    const int buf = t % nbuf;
+    const uint32_t bar = smem_u32(&full_bar[buf]);
+    mbar_arrive_expect_tx(bar, box_bytes);
+    tma_load_3d(ring + buf * buf_pitch, tm, bar, ox >> 2, s_oy[t], frame_idx);   // 32-bit elements: column = byte / 4
+  };
+  if (tid == 0) for (int t = 0; t < min(nbuf, T); ++t) issue(t);
+
+  const int yl = tid >> 2, xg = (tid & 3) << 2;
+  uint32_t phase_bits = 0u;   // bit b = parity the next wait on buffer b expects (slow tiles do not use their slot)
+  for (int t = 0; t < T; ++t) {
+    const int ty = ty0 + t / tiles_x, tx = t - (t / tiles_x) * tiles_x;
+    const int y = ty * kTile + yl, x = tx * kTile + xg;
+    const int bxv = s_X0[y], byv = s_Y0[y];
+    const int4 a4 = *reinterpret_cast<const int4*>(&s_ad[x]);
+    const int4 b4 = *reinterpret_cast<const int4*>(&s_bd[x]);
+    const int av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    const int ox = s_ox[t], oy = s_oy[t];
+    uint32_t q[4];
+    if (ox != INT_MIN) {
+      const int buf = t % nbuf;
+      mbar_wait(smem_u32(&full_bar[0]) + 8u * buf, (phase_bits >> buf) & 1u);
+      phase_bits ^= 1u << buf;
+      const uint32_t base = ring + buf * buf_pitch;
+      const int corr = -oy * BW - ox;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int X = (bxv + av[j]) >> 5, Y = (byv + bv[j]) >> 5;
+        const int sx = X >> 5, sy = Y >> 5;
+        const uint32_t fx = X & 31, fy = Y & 31;
+        const uint32_t o = base + (uint32_t)(sy * BW + sx * 3 + corr);
+        const uint32_t oa = o & ~3u, k8 = (o & 3u) << 3;
+        const uint32_t l0 = lds32(oa), l1 = lds32(oa + 4), l2 = lds32(oa + 8);
+        const uint32_t m0 = lds32(oa + BW), m1 = lds32(oa + BW + 4), m2 = lds32(oa + BW + 8);
+        const uint32_t w0 = __funnelshift_r(l0, l1, k8), w1 = __funnelshift_r(l1, l2, k8);   // row sy  : c0 c1 c2 c0' | c1' c2'
+        const uint32_t v0 = __funnelshift_r(m0, m1, k8), v1 = __funnelshift_r(m1, m2, k8);   // row sy+1
+        const uint32_t t0 = prmt(w0, w1, 0x5241u), t1 = prmt(v0, v1, 0x5241u);                 // c1 c1' c2 c2'
+        const uint32_t P0 = prmt(w0, v0, 0x7430u), P1 = prmt(t0, t1, 0x5410u), P2 = prmt(t0, t1, 0x7632u);   // p00 p01 p10 p11 per channel
+        const uint32_t A0 = fx * 255u + 32u;          // bytes (32 - fx, fx, 0, 0)
+        const uint32_t A1 = A0 << 16;                 // bytes (0, 0, 32 - fx, fx)
+        const uint32_t b1 = fy << 6, b0 = 2048u - b1; // (32 - fy, fy) << 6: the result byte lands in bits [16, 24)
+        const uint32_t S0 = b0 * __dp4a(P0, A0, 0u) + b1 * __dp4a(P0, A1, 0u) + 32768u;
+        const uint32_t S1 = b0 * __dp4a(P1, A0, 0u) + b1 * __dp4a(P1, A1, 0u) + 32768u;
+        const uint32_t S2 = b0 * __dp4a(P2, A0, 0u) + b1 * __dp4a(P2, A1, 0u) + 32768u;
+        q[j] = prmt(prmt(S0, S1, 0x0062u), S2, 0x0610u);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = blend_px_global3(frame, p.H, p.W, row, (bxv + av[j]) >> 5, (byv + bv[j]) >> 5);
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(crop + ((size_t)y * p.out_w + x) * 3);
+    dst[0] = prmt(q[0], q[1], 0x4210u);
+    dst[1] = prmt(q[1], q[2], 0x5421u);
+    dst[2] = prmt(q[2], q[3], 0x6542u);
+    __syncthreads();   // every thread has finished reading this tile's buffer
+    if (tid == 0 && t + nbuf < T) issue(t + nbuf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ generic kernel
 template <int C, bool FAST>
 __global__ void __launch_bounds__(kAlignThreads)
 align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const int32_t* __restrict__ face2frame,
@@ -113,35 +392,15 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
   const int tid = threadIdx.x;
   const int nc = FAST ? C : rtC;
 
-  if (tid == 0) {
-    if (M_in) {
-      for (int i = 0; i < 6; ++i) fit.M[i] = M_in[(size_t)face * 6 + i];
-    } else {
-      fit_similarity(marks + (size_t)face * N * 2, N, tmpl, Nt, five_point, fit.M);
-    }
-    int ok = 1;
-    for (int i = 0; i < 6; ++i) ok &= isfinite(fit.M[i]) ? 1 : 0;
-    const int fr = face2frame[face];
-    if (fr < 0 || fr >= F) ok = 0;
-    if (ok) invert_affine(fit.M, fit.iM);
-    fit.ok = ok;
-    if (M_out && blockIdx.y == 0) for (int i = 0; i < 6; ++i) M_out[(size_t)face * 6 + i] = fit.M[i];
-  }
+  cta_fit(fit, face, F, face2frame, marks, N, tmpl, five_point, M_in, M_out, blockIdx.y == 0, tid);
   __syncthreads();
   uint8_t* crop = crops + (size_t)face * out_h * out_w * nc;
   if (!fit.ok) {
     for (int i = y_beg * out_w * nc + tid; i < y_end * out_w * nc; i += kAlignThreads) crop[i] = 0;
     return;
   }
-  const double AB = 1024.0;
-  for (int x = tid; x < out_w; x += kAlignThreads) {
-    adelta[x] = (int)__double2ll_rn(dm(dm(fit.iM[0], (double)x), AB));
-    bdelta[x] = (int)__double2ll_rn(dm(dm(fit.iM[3], (double)x), AB));
-  }
-  for (int y = y_beg + tid; y < y_end; y += kAlignThreads) {
-    X0[y - y_beg] = (int)__double2ll_rn(dm(da(dm(fit.iM[1], (double)y), fit.iM[2]), AB)) + 16;
-    Y0[y - y_beg] = (int)__double2ll_rn(dm(da(dm(fit.iM[4], (double)y), fit.iM[5]), AB)) + 16;
-  }
+  for (int x = tid; x < out_w; x += kAlignThreads) { adelta[x] = tab_ad(fit, x); bdelta[x] = tab_bd(fit, x); }
+  for (int y = y_beg + tid; y < y_end; y += kAlignThreads) { X0[y - y_beg] = tab_X0(fit, y); Y0[y - y_beg] = tab_Y0(fit, y); }
   __syncthreads();
 
   const uint8_t* frame = frames + (size_t)face2frame[face] * H * W * nc;
@@ -233,6 +492,41 @@ align_warp_kernel(const uint8_t* __restrict__ frames, int F, int H, int W, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor maps over the frames for the eight box classes, cached per (handle, buffer, shape): encoding costs microseconds
+struct MapsEntry { const fld_handle* h; const void* frames; int F, H, W; AlignMaps maps; };
+std::mutex g_maps_mu;
+std::vector<MapsEntry> g_maps_cache;
+
+int get_align_maps(const fld_handle* h, const uint8_t* frames, int F, int H, int W, AlignMaps* out) {
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  for (const auto& e : g_maps_cache)
+    if (e.h == h && e.frames == frames && e.F == F && e.H == H && e.W == W) { *out = e.maps; return FLD_OK; }
+  EncodeTiledFn enc = (EncodeTiledFn)h->encode_tiled;
+  MapsEntry e;
+  e.h = h; e.frames = frames; e.F = F; e.H = H; e.W = W;
+  memset(&e.maps, 0, sizeof(e.maps));
+  for (int k = 0; k < kNumCls; ++k) {
+    // the frame bytes as 32-bit elements: [F][H][W*3/4]; out-of-range elements are zero-filled (BORDER_CONSTANT 0)
+    cuuint64_t dims[3] = {(cuuint64_t)W * 3 / 4, (cuuint64_t)H, (cuuint64_t)F};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)H * W * 3};
+    cuuint32_t box[3] = {(cuuint32_t)cls_bw(k) / 4, (cuuint32_t)cls_side(k), 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&e.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fld_set_error("cuTensorMapEncodeTiled(align frames, class %d) failed: %d", k, (int)r); return FLD_ERR_CUDA; }
+  }
+  if (g_maps_cache.size() >= 32) g_maps_cache.erase(g_maps_cache.begin());
+  g_maps_cache.push_back(e);
+  *out = e.maps;
+  return FLD_OK;
+}
+
 int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int C, const int32_t* face2frame,
                  const float* marks, int N, const double* tmpl, int Nt, int five_point, const double* M_in, int B,
                  int out_h, int out_w, double* M_out, uint8_t* crops, cudaStream_t st) {
@@ -248,7 +542,28 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
     if (five_point) FLD_REQUIRE(N == 68 && Nt == 5, "fld_align: five_point mode needs N=68, Nt=5 (got %d, %d)", N, Nt);
     else FLD_REQUIRE(N == Nt && N >= 2, "fld_align: N (%d) must equal Nt (%d) and be >= 2", N, Nt);
   }
-  if (B == 0) return FLD_OK;
+  static const bool tile_off = getenv("FLD_ALIGN_TILE_OFF") != nullptr;
+  const bool tile_ok = !tile_off && C == 3 && h->encode_tiled && out_w % kTile == 0 && out_h % kTile == 0 && out_w <= kMaxOut &&
+                       out_h <= kMaxOut && ((size_t)W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(crops) & 3) == 0 && H < 30000 && W < 30000;
+  if (tile_ok) {
+    AlignMaps maps;
+    rc = get_align_maps(h, frames, F, H, W, &maps);
+    if (rc) return rc;
+    TileArgs a;
+    a.frames = frames; a.face2frame = face2frame; a.marks = marks; a.tmpl = tmpl; a.M_in = M_in; a.M_out = M_out; a.crops = crops;
+    a.F = F; a.H = H; a.W = W; a.N = N; a.five_point = five_point; a.out_h = out_h; a.out_w = out_w;
+    // split a face's tile rows over several CTAs while the grid would otherwise be only a few waves deep
+    const int tiles_y = out_h / kTile;
+    a.ysplit = ((long long)B < 8ll * 8 * h->sm_count) ? tiles_y : 1;
+    { const char* e = getenv("FLD_ALIGN_YSPLIT"); if (e && atoi(e) > 0) a.ysplit = std::min(tiles_y, atoi(e)); }
+    const size_t smem = kRingBytes + 128 + 32;
+    FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    align_tile_kernel<<<dim3(B, a.ysplit), kTileThreads, smem, st>>>(maps, a);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
   // small batches: split each face over several CTAs (row blocks) so that the grid covers the machine
   int rb = 1;
   while (rb < 8 && (long long)B * rb < 4ll * h->sm_count && out_h / (rb * 2) >= 8) rb *= 2;
@@ -256,7 +571,7 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
   const dim3 grid(B, fld_div_up(out_h, rows_per));
   const size_t smem = (size_t)(2 * out_w + 2 * rows_per) * sizeof(int);
   const bool fast = (C == 3) && (out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(crops) & 3) == 0) &&
-                    ((size_t)F * H * W * 3 >= 32);
+                    ((reinterpret_cast<uintptr_t>(frames) & 7) == 0) && ((size_t)F * H * W * 3 >= 32);
   if (fast) {
     align_warp_kernel<3, true><<<grid, kAlignThreads, smem, st>>>(frames, F, H, W, face2frame, marks, N, tmpl, Nt, five_point,
                                                                M_in, M_out, crops, out_h, out_w, 3, rows_per);

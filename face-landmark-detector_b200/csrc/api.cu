@@ -1,7 +1,6 @@
-// api.cu — handle life-cycle, error reporting, scratch memory for libfld_sm100.so
+// api.cu — handle life-cycle and error reporting for libfld_sm100.so (the library owns no scratch memory: every
+// buffer, including decode partials, is caller-provided so that calls on different streams never share state)
 #include <stdarg.h>
-#include <mutex>
-#include <unordered_map>
 #include "common.cuh"
 
 std::atomic<uint64_t> g_fld_launches{0};
@@ -12,27 +11,6 @@ void fld_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
-}
-
-namespace {
-struct Scratch { void* ptr = nullptr; size_t bytes = 0; };
-std::mutex g_scratch_mu;
-std::unordered_map<const fld_handle*, Scratch> g_scratch;
-}  // namespace
-
-// Handle-owned scratch that grows on demand (used by the two-pass heat-map decodes).  Growing
-// synchronises the device once; steady-state calls do not allocate.
-int fld_scratch(fld_handle* h, size_t bytes, void** out) {
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  Scratch& s = g_scratch[h];
-  if (s.bytes < bytes) {
-    if (s.ptr) { FLD_CUDA(cudaDeviceSynchronize()); FLD_CUDA(cudaFree(s.ptr)); s.ptr = nullptr; s.bytes = 0; }
-    const size_t want = bytes + bytes / 4 + 4096;
-    FLD_CUDA(cudaMalloc(&s.ptr, want));
-    s.bytes = want;
-  }
-  *out = s.ptr;
-  return FLD_OK;
 }
 
 extern "C" int fld_abi_version(void) { return FLD_ABI_VERSION; }
@@ -73,13 +51,5 @@ extern "C" int fld_create(int device, fld_handle** out) {
 
 extern "C" void fld_destroy(fld_handle* h) {
   if (!h) return;
-  {
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
-    auto it = g_scratch.find(h);
-    if (it != g_scratch.end()) {
-      if (it->second.ptr) { cudaSetDevice(h->device); cudaFree(it->second.ptr); }
-      g_scratch.erase(it);
-    }
-  }
   delete h;
 }

@@ -3,9 +3,10 @@
 // Replaces reference prediction.py:88-94 (regression decode), prediction.py:209 (argmax over
 // classes) and utils/metrics.py:46-109 (get_average_xy / transfer_xy_coord / transfer_target).
 // All three are HBM-bound streaming reductions: coalesced loads, warp/block partials, no GEMM.
+#include <stdlib.h>
+#include <algorithm>
 #include "common.cuh"
 
-int fld_scratch(fld_handle* h, size_t bytes, void** out);  // api.cu: handle-owned scratch that grows on demand
 
 namespace {
 
@@ -404,21 +405,18 @@ extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, in
   return FLD_OK;
 }
 
-extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int H, int W, int L, int n_points, double thresh,
-                                     double* xy, fld_stream stream) {
-  int rc = fld_enter(h);
-  if (rc) return rc;
-  if (B == 0) return FLD_OK;
-  FLD_REQUIRE(hm && xy, "fld_decode_heatmap_xy: null pointer");
-  FLD_REQUIRE(B >= 0 && H > 0 && W > 0 && L > 0 && L <= 1024, "fld_decode_heatmap_xy: need 0 < L <= 1024");
-  FLD_REQUIRE(n_points <= FLD_MAX_TOPN, "fld_decode_heatmap_xy: n_points must be <= %d", FLD_MAX_TOPN);
-  if (B == 0) return FLD_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+namespace {
+struct XyPlan { bool vec4; int R, S, threads; size_t bytes; };
+
+// launch geometry + scratch bytes of the two-pass heat-map decode; deterministic per device
+XyPlan xy_plan(const fld_handle* h, int B, int H, int W, int L, int n_points, bool vec4) {
+  XyPlan p;
   const int HW = H * W;
-  const bool vec4 = L % 4 == 0 && (reinterpret_cast<uintptr_t>(hm) & 15) == 0 && n_points <= 4 && L <= 128 && !getenv("FLD_DECODE_SCALAR");
+  p.vec4 = vec4;
   const int Lt = vec4 ? L / 4 : L;                      // threads per pixel lane
-  const int R = (Lt >= 256) ? 1 : fld_div_up(256, Lt);  // pixel lanes per CTA
-  const int threads = R * Lt;
+  p.R = (Lt >= 256) ? 1 : fld_div_up(256, Lt);          // pixel lanes per CTA
+  p.threads = p.R * Lt;
+  const int R = p.R, threads = p.threads;
   // slabs: B * S CTAs fill ONE wave of resident CTAs (a 2.05-wave grid measured 68 % efficient), at least 64 pixels per lane
   int occ = 0;
   if (n_points < 1) {
@@ -429,15 +427,47 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
   else if (n_points <= 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<16>, threads, (size_t)R * L * n_points * sizeof(Cand));
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<FLD_MAX_TOPN>, threads, 0);
   occ = max(occ, 1);
-  int S = max(1, (h->sm_count * occ) / B);
+  int S = max(1, (h->sm_count * occ) / max(B, 1));
   S = max(1, min(S, HW / (64 * R) > 0 ? HW / (64 * R) : 1));
-  S = min(S, 65535);
+  p.S = min(S, 65535);
+  if (n_points < 1) p.bytes = (size_t)B * p.S * R * L * 3 * sizeof(double);
+  else p.bytes = (size_t)B * p.S * R * L * n_points * sizeof(Cand) + (size_t)B * L * n_points * sizeof(Cand);
+  return p;
+}
+bool xy_vec4_shape(int L, int n_points) { return L % 4 == 0 && n_points <= 4 && L <= 128 && !getenv("FLD_DECODE_SCALAR"); }
+}  // namespace
+
+extern "C" size_t fld_decode_heatmap_scratch_bytes(fld_handle* h, int B, int H, int W, int L, int n_points) {
+  if (!h || B <= 0 || H <= 0 || W <= 0 || L <= 0 || L > 1024 || n_points > FLD_MAX_TOPN) return 0;
+  if (fld_enter(h)) return 0;
+  size_t b = xy_plan(h, B, H, W, L, n_points, false).bytes;   // the pointer's alignment picks the variant at call time: cover both
+  if (xy_vec4_shape(L, n_points)) b = std::max(b, xy_plan(h, B, H, W, L, n_points, true).bytes);
+  return b + 256;
+}
+
+extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int H, int W, int L, int n_points, double thresh,
+                                     double* xy, void* scratch_in, size_t scratch_bytes, fld_stream stream) {
+  int rc = fld_enter(h);
+  if (rc) return rc;
+  if (B == 0) return FLD_OK;
+  FLD_REQUIRE(hm && xy, "fld_decode_heatmap_xy: null pointer");
+  FLD_REQUIRE(B >= 0 && H > 0 && W > 0 && L > 0 && L <= 1024, "fld_decode_heatmap_xy: need 0 < L <= 1024");
+  FLD_REQUIRE(n_points <= FLD_MAX_TOPN, "fld_decode_heatmap_xy: n_points must be <= %d", FLD_MAX_TOPN);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  const bool vec4 = xy_vec4_shape(L, n_points) && (reinterpret_cast<uintptr_t>(hm) & 15) == 0;
+  const XyPlan pl = xy_plan(h, B, H, W, L, n_points, vec4);
+  const int R = pl.R, S = pl.S, threads = pl.threads;
+  // caller-provided scratch (fld_decode_heatmap_scratch_bytes): decodes in flight on different streams never share partials
+  FLD_REQUIRE(scratch_in, "fld_decode_heatmap_xy: null scratch (size it with fld_decode_heatmap_scratch_bytes)");
+  char* scratch = (char*)(((uintptr_t)scratch_in + 255) & ~(uintptr_t)255);
+  if ((size_t)(scratch - (char*)scratch_in) + pl.bytes > scratch_bytes) {
+    fld_set_error("fld_decode_heatmap_xy: scratch %zu < required %zu", scratch_bytes, pl.bytes + 256);
+    return FLD_ERR_WORKSPACE;
+  }
   dim3 grid(B, S);
   const int nBL = B * L;
   if (n_points < 1) {
-    void* scratch;
-    rc = fld_scratch(h, (size_t)B * S * R * L * 3 * sizeof(double), &scratch);
-    if (rc) return rc;
     if (vec4) soft_partial_vec4_kernel<<<grid, threads, (size_t)R * L * 3 * sizeof(double), st>>>((const float4*)hm, HW, W, L / 4, R, S, (double*)scratch);
     else soft_partial_kernel<<<grid, threads, 0, st>>>(hm, HW, W, L, R, S, (double*)scratch);
     FLD_LAUNCHED();
@@ -448,10 +478,6 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
   const int n = n_points;
   FLD_REQUIRE(n <= HW, "fld_decode_heatmap_xy: n_points (%d) exceeds H*W (%d)", n, HW);
   const size_t part_bytes = (size_t)B * S * R * L * n * sizeof(Cand);
-  const size_t sel_bytes = (size_t)nBL * n * sizeof(Cand);
-  void* scratch;
-  rc = fld_scratch(h, part_bytes + sel_bytes, &scratch);
-  if (rc) return rc;
   Cand* partial = (Cand*)scratch;
   Cand* sel = (Cand*)((char*)scratch + part_bytes);
   const size_t csm = (size_t)R * L * n * sizeof(Cand);   // block-level candidate exchange (n <= 16)

@@ -55,6 +55,7 @@ struct fld_net {
   bool finalized = false;
   bool profiling = false;
   bool profiled_once = false;
+  int retained = 0;                 // > 0 while captured CUDA graphs reference this net's plans: nothing is evicted
   std::vector<cudaEvent_t> events;  // n_layers + 1, recorded around every layer when profiling
 };
 
@@ -387,6 +388,14 @@ extern "C" size_t fld_net_workspace_bytes(const fld_net* net, int B) {
   return off + align_up(dense_scratch_bytes(net, B), 1024) + 1024;
 }
 
+// fld_net_forward_landmarks: the plain forward's workspace followed by the partials of the stand-alone heat-map decode
+// (used whenever the centroid is not fused into the last transposed conv's epilogue)
+extern "C" size_t fld_net_landmarks_workspace_bytes(const fld_net* net, int B, int n_points) {
+  if (!net || B < 0) return 0;
+  const TensorInfo& o = net->tensors.back();
+  return fld_net_workspace_bytes(net, B) + align_up(fld_decode_heatmap_scratch_bytes(net->h, B, o.h, o.w, o.c, n_points < 1 ? 0 : n_points), 1024);
+}
+
 extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, int hw, int L, int64_t* class_map, fld_stream stream);
 
 static int net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, int64_t* cmap_out, fld_stream stream,
@@ -399,11 +408,11 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   if (B == 0) return FLD_OK;   // an empty batch is legal (empty tensors have null data pointers)
   FLD_REQUIRE(in && workspace, "fld_net_forward: null pointer");
   FLD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "fld_net_forward: workspace must be 1024-byte aligned");
-  if (ws_bytes < fld_net_workspace_bytes(net, B)) {
-    fld_set_error("fld_net_forward: workspace %zu < required %zu", ws_bytes, fld_net_workspace_bytes(net, B));
+  const size_t ws_need = xy_out ? fld_net_landmarks_workspace_bytes(net, B, xy_n) : fld_net_workspace_bytes(net, B);
+  if (ws_bytes < ws_need) {
+    fld_set_error("fld_net_forward: workspace %zu < required %zu", ws_bytes, ws_need);
     return FLD_ERR_WORKSPACE;
   }
-  if (B == 0) return FLD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nT = (int)net->tensors.size();
   std::vector<void*> ptr(nT);
@@ -442,7 +451,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           if (!plan) {
             rc = tc_halo_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan);
             if (rc) return rc;
-            if (L.hplans.size() >= 8) { tc_halo_plan_destroy(L.hplans.front().plan); L.hplans.erase(L.hplans.begin()); }
+            if (L.hplans.size() >= 16 && net->retained == 0) { tc_halo_plan_destroy(L.hplans.front().plan); L.hplans.erase(L.hplans.begin()); }
             L.hplans.push_back({B, pin, plan});
           }
           rc = tc_halo_run(plan, L.d_bias, pout, st);
@@ -452,7 +461,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           if (!plan) {
             rc = tc_conv_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan);
             if (rc) return rc;
-            if (L.plans.size() >= 8) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
+            if (L.plans.size() >= 16 && net->retained == 0) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
             L.plans.push_back({B, pin, plan});
           }
           rc = tc_conv_run(plan, L.d_bias, pout, o.dtype, st);
@@ -475,7 +484,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           if (!plan) {
             rc = tc_deconv_plan_create(net->h, dense_scratch, L.d_wbf, B, a.h, a.w, a.c, d.cout, d.stride, &plan);
             if (rc) return rc;
-            if (L.dplans.size() >= 8) { tc_deconv_plan_destroy(L.dplans.front().plan); L.dplans.erase(L.dplans.begin()); }
+            if (L.dplans.size() >= 16 && net->retained == 0) { tc_deconv_plan_destroy(L.dplans.front().plan); L.dplans.erase(L.dplans.begin()); }
             L.dplans.push_back({B, (const void*)dense_scratch, plan});
           }
           rc = tc_deconv_run(plan, (const float*)pin, dst, mode, st, acc, xy_thresh);
@@ -534,7 +543,9 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   if (xy_out && !xy_done) {  // no fused centroid available: soft-centroid decode of the final tensor
     const TensorInfo& o = net->tensors[nT - 1];
     FLD_REQUIRE(o.dtype == FLD_F32, "fld_net_forward_landmarks: final tensor must be fp32");
-    rc = fld_decode_heatmap_xy(net->h, (const float*)ptr[nT - 1], B, o.h, o.w, o.c, xy_n < 1 ? 0 : xy_n, xy_thresh, xy_out, stream);
+    const size_t base = fld_net_workspace_bytes(net, B);
+    rc = fld_decode_heatmap_xy(net->h, (const float*)ptr[nT - 1], B, o.h, o.w, o.c, xy_n < 1 ? 0 : xy_n, xy_thresh, xy_out,
+                               (char*)workspace + base, ws_bytes - base, stream);
     if (rc) return rc;
   }
   if (out && !direct_out) {
@@ -561,6 +572,18 @@ extern "C" int fld_net_forward_classmap(fld_net* net, const void* in, int B, voi
                                         fld_stream stream) {
   if (!class_map) { fld_set_error("fld_net_forward_classmap: null class_map"); return FLD_ERR_INVALID; }
   return net_forward(net, in, B, workspace, ws_bytes, nullptr, class_map, stream);
+}
+
+// A captured CUDA graph bakes in device pointers owned by the kernel plans (tile schedules): while a net is retained no plan
+// is evicted, so those pointers stay valid for the graph's lifetime.  Balanced by fld_net_release.
+extern "C" int fld_net_retain(fld_net* net) {
+  FLD_REQUIRE(net, "fld_net_retain: null net");
+  return ++net->retained;
+}
+extern "C" int fld_net_release(fld_net* net) {
+  FLD_REQUIRE(net, "fld_net_release: null net");
+  if (net->retained > 0) --net->retained;
+  return net->retained;
 }
 
 extern "C" int fld_net_set_profiling(fld_net* net, int enable) {

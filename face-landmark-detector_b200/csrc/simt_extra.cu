@@ -175,7 +175,9 @@ __global__ void add_bf16x8_kernel(const uint4* __restrict__ a, int AH, int AW, c
   out[i] = pack8(u);
 }
 
-unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
+// grid.x is limited to 2^31 - 1: a larger request returns 0 blocks, which the launch rejects loudly (FLD_LAUNCHED) instead of
+// silently truncating the element count
+unsigned blocks_for(long long total) { const long long b = (total + 255) / 256; return b < (1ll << 31) ? (unsigned)b : 0u; }
 
 }  // namespace
 

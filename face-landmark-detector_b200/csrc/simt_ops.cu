@@ -7,6 +7,9 @@
 
 namespace {
 
+// grid.x is limited to 2^31 - 1: a larger request yields 0 blocks, which the launch rejects loudly (FLD_LAUNCHED)
+unsigned blocks256(long long total) { const long long b = (total + 255) / 256; return b < (1ll << 31) ? (unsigned)b : 0u; }
+
 template <typename T> __device__ __forceinline__ float ld_f(const T* p);
 template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_f<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
@@ -348,12 +351,12 @@ int simt_add_crop(const float* a, int AH, int AW, const float* b, int BH, int BW
   if (B == 0) return FLD_OK;
   const long long total = (long long)B * OH * OW * C;
   if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    add_crop_vec4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>((const float4*)a, AH, AW, (const float4*)b, BH, BW, (float4*)out, B, OH,
+    add_crop_vec4_kernel<<<blocks256(total / 4), 256, 0, st>>>((const float4*)a, AH, AW, (const float4*)b, BH, BW, (float4*)out, B, OH,
                                                                             OW, C / 4);
     FLD_LAUNCHED();
     return FLD_OK;
   }
-  add_crop_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, AH, AW, b, BH, BW, out, B, OH, OW, C);
+  add_crop_kernel<<<blocks256(total), 256, 0, st>>>(a, AH, AW, b, BH, BW, out, B, OH, OW, C);
   FLD_LAUNCHED();
   return FLD_OK;
 }
@@ -386,14 +389,14 @@ int simt_dense(const void* in, int in_dtype, const float* w, const float* bias, 
 int simt_maxpool(const float* in, float* out, int B, int IH, int IW, int C, int OH, int OW, int k, int s, cudaStream_t st) {
   if (B == 0) return FLD_OK;
   const long long total = (long long)B * OH * OW * C;
-  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, IH, IW, C, OH, OW, k, s);
+  maxpool_kernel<<<blocks256(total), 256, 0, st>>>(in, out, B, IH, IW, C, OH, OW, k, s);
   FLD_LAUNCHED();
   return FLD_OK;
 }
 
 int simt_cvt_bf16_f32(const void* in, float* out, long long n, cudaStream_t st) {
   if (n == 0) return FLD_OK;
-  cvt_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)in, out, n);
+  cvt_bf16_f32_kernel<<<blocks256(n), 256, 0, st>>>((const __nv_bfloat16*)in, out, n);
   FLD_LAUNCHED();
   return FLD_OK;
 }

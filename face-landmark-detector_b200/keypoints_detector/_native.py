@@ -54,12 +54,16 @@ SIGNATURES = {
     "fld_net_tensor_offset": (ctypes.c_int64, [_vp, _i, _i]),
     "fld_net_forward": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "fld_net_forward_classmap": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "fld_net_landmarks_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "fld_net_retain": (_i, [_vp]),
+    "fld_net_release": (_i, [_vp]),
     "fld_net_forward_landmarks": (_i, [_vp, _vp, _i, _vp, _sz, _i, ctypes.c_double, _vp, _vp]),
     "fld_net_set_profiling": (_i, [_vp, _i]),
     "fld_net_layer_times": (_i, [_vp, _vp, _i]),
     "fld_decode_regress": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "fld_decode_classmap": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
-    "fld_decode_heatmap_xy": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
+    "fld_decode_heatmap_scratch_bytes": (_sz, [_vp, _i, _i, _i, _i, _i]),
+    "fld_decode_heatmap_xy": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _sz, _vp]),
     "fld_align": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fld_warp_affine": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "fld_launch_count": (ctypes.c_uint64, []),

@@ -22,6 +22,12 @@ def fcn_32_vanilla(n_classes, input_height=224, input_width=224, channels=3):
     return model
 
 
+def landmark_regressor_model(n_classes=136, input_height=128, input_width=128, channels=3):
+    """Registry adapter: the regression model's `n_classes` is its output width (2 values per landmark), which is what
+    Model.config_dict / save_config record, so save_config -> model_from_checkpoint_path round-trips."""
+    return landmark_regressor(input_height, input_width, channels, n_points=int(n_classes) // 2)
+
+
 LANDMARKS_MODELS = {
     'fcn_8_resnet50': fcn_8_resnet50,
     'fcn_8_mobilenet': fcn_8_mobilenet,
@@ -33,4 +39,5 @@ LANDMARKS_MODELS = {
     'fcn_32_vgg': fcn_32_vgg,
     'fcn_32_resnet50': fcn_32_resnet50,
     'fcn_32_mobilenet': fcn_32_mobilenet,
+    'landmark_regressor': landmark_regressor_model,
 }

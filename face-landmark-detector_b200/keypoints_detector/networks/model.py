@@ -146,7 +146,9 @@ class Model:
         self.weights = {}
         self._specs = weight_specs(graph)
         self._nets = {}                      # (device index, compute) -> (net handle, ...)
-        self._ws = {}                        # (device index, compute) -> torch.uint8 workspace
+        self._ws = {}                        # (device index, compute, lane) -> torch.uint8 workspace
+        self._pins = {}                      # (device index, compute, lane) -> number of live CUDA-graph captures using that workspace
+        self._captures = []                  # weak references to live captures (invalidated when the nets are rebuilt)
         self.signatures = {"predict": _Signature(self)}
 
     # ------------------------------------------------------------------ weights
@@ -195,6 +197,42 @@ class Model:
             out[k2] = v
         return out
 
+    # Keras auto-names of layers the reference leaves unnamed (fcn.py:10-51 vanilla encoder, :98-121 FCN head), by layer type
+    _AUTO_NAMES = {"conv": "conv2d", "bn": "batch_normalization", "deconv": "conv2d_transpose", "dense": "dense",
+                   "dwconv": "depthwise_conv2d"}
+
+    def alias_keras_auto_names(self, arrays):
+        """The reference gives no names to the vanilla encoder's and the FCN head's layers, so a checkpoint trained with it
+        carries Keras' auto-generated names (`conv2d`, `conv2d_1`, ..., `batch_normalization_3`, `conv2d_transpose_2`), numbered
+        in creation order with a session-dependent offset.  Layers of this build whose own name is absent from `arrays` are
+        matched, per layer type and in graph (= creation) order, to the auto-named layers sorted by their numeric suffix.
+        Raises KeyError when the counts do not line up."""
+        import re
+        have = {k.split("/")[0] for k in arrays}
+        want = {"conv": [], "bn": [], "deconv": [], "dense": [], "dwconv": []}
+        for L in self.graph.layers:
+            kind = {N.OP_CONV: "conv", N.OP_DECONV: "deconv", N.OP_DENSE: "dense", N.OP_DWCONV: "dwconv"}.get(L["op"])
+            if kind is None:
+                continue
+            if L["name"] not in have:
+                want[kind].append(L["name"])
+            if L.get("has_bn") and L["bn_name"] not in have:
+                want["bn"].append(L["bn_name"])
+        out = dict(arrays)
+        for kind, names in want.items():
+            if not names:
+                continue
+            pat = re.compile(r"^%s(?:_(\d+))?$" % self._AUTO_NAMES[kind])
+            autos = sorted({(int(m.group(1) or 0), l) for l in have for m in [pat.match(l)] if m})
+            if len(autos) != len(names):
+                raise KeyError("cannot alias Keras auto-named %s layers: the file has %d (%s), the model needs %d (%s)"
+                               % (kind, len(autos), [a for _, a in autos][:4], len(names), names[:4]))
+            for (_, auto), name in zip(autos, names):
+                for k, v in arrays.items():
+                    if k.split("/")[0] == auto:
+                        out[name + "/" + k.split("/", 1)[1]] = v
+        return out
+
     def load_weights(self, path):
         """Weights container of this build: `.npz` or `.safetensors` keyed by layer name in Keras layouts (the
         reference's TF-checkpoint format cannot be read without TensorFlow)."""
@@ -208,16 +246,62 @@ class Model:
         else:
             with np.load(p) as z:
                 arrays = {k: z[k] for k in z.files}
-        self.set_weights(self.normalize_weight_names(arrays))
+        arrays = self.normalize_weight_names(arrays)
+        if any(k not in arrays for k in self._specs):
+            arrays = self.alias_keras_auto_names(arrays)
+        self.set_weights(arrays)
         return None
 
     # ------------------------------------------------------------------ device side
     def _release(self):
+        """Destroy the compiled nets and workspaces (new weights).  CUDA graphs captured over them hold raw pointers into
+        both, so every live capture is invalidated first: replaying it afterwards raises instead of touching freed memory."""
+        for ref in self._captures:
+            cap = ref()
+            if cap is not None:
+                cap.invalidate("the model's weights / compiled nets were replaced after the capture")
+        self._captures = []
+        self._pins = {}
         lib = N.load_library() if self._nets else None
         for (net, _) in self._nets.values():
             lib.fld_net_destroy(net)
         self._nets.clear()
         self._ws.clear()
+
+    def _workspace(self, dev, comp, lane, need, device):
+        """The lane's activation workspace (1024-byte aligned base, usable bytes).  Grows on demand — except while a captured
+        CUDA graph uses it (its kernels have the old pointer baked in): then a larger batch must use another lane."""
+        key = (dev, comp, lane)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need + 1024:
+            if ws is not None and self._pins.get(key, 0) > 0:
+                raise N.FldError("lane %d's workspace is referenced by a captured CUDA graph and cannot grow to %d bytes: run larger "
+                                 "batches on another lane or drop the capture first" % (lane, need))
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        al = (-ws.data_ptr()) % 1024
+        return ws, al
+
+    def pin_lane(self, device, dtype, lane, capture):
+        """Called by LandmarkPipeline.capture: keep the lane's workspace and the net's kernel plans alive and in place while
+        `capture` lives.  Returns a release callback."""
+        import weakref
+        dev = torch.device(device).index
+        comp = self._compute_code(dtype)
+        key = (dev, comp, lane)
+        net = self.compiled(dev, dtype)
+        lib = N.load_library()
+        lib.fld_net_retain(net)
+        self._pins[key] = self._pins.get(key, 0) + 1
+        self._captures.append(weakref.ref(capture))
+        ws = self._ws.get(key)
+        nets = self._nets
+
+        def release():
+            if nets.get((dev, comp), (None,))[0] is net and self._pins.get(key, 0) > 0:   # still the same compiled net
+                self._pins[key] -= 1
+                lib.fld_net_release(net)
+        return release, ws
 
     def __del__(self):
         try:
@@ -313,12 +397,8 @@ class Model:
             net = self.compiled(dev, dtype)
             comp = self._compute_code(dtype)
             need = lib.fld_net_workspace_bytes(net, B)
-            ws = self._ws.get((dev, comp, lane))
-            if ws is None or ws.numel() < need:
-                ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
-                self._ws[(dev, comp, lane)] = ws
+            ws, al = self._workspace(dev, comp, lane, need, x.device)
             base = ws.data_ptr()
-            al = (-base) % 1024
             oh, ow, oc = self.graph.shapes[-1]
             if out is None:
                 out = torch.empty((B, oh * ow, oc) if self.kind == "segmentation" else (B, oc), dtype=torch.float32, device=x.device)
@@ -342,12 +422,8 @@ class Model:
             net = self.compiled(dev, dtype)
             comp = self._compute_code(dtype)
             need = lib.fld_net_workspace_bytes(net, B)
-            ws = self._ws.get((dev, comp, lane))
-            if ws is None or ws.numel() < need:
-                ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
-                self._ws[(dev, comp, lane)] = ws
+            ws, al = self._workspace(dev, comp, lane, need, x.device)
             base = ws.data_ptr()
-            al = (-base) % 1024
             cmap = torch.empty((B, self.output_height, self.output_width), dtype=torch.int64, device=x.device)
             N.check(lib.fld_net_forward_classmap(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(cmap), N.stream_ptr(dev)))
         return cmap
@@ -368,13 +444,9 @@ class Model:
         with torch.cuda.device(dev):
             net = self.compiled(dev, dtype)
             comp = self._compute_code(dtype)
-            need = lib.fld_net_workspace_bytes(net, B)
-            ws = self._ws.get((dev, comp, lane))
-            if ws is None or ws.numel() < need:
-                ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
-                self._ws[(dev, comp, lane)] = ws
+            need = lib.fld_net_landmarks_workspace_bytes(net, B, int(n_points))
+            ws, al = self._workspace(dev, comp, lane, need, x.device)
             base = ws.data_ptr()
-            al = (-base) % 1024
             xy = torch.empty((B, 2 * self.graph.shapes[-1][2]), dtype=torch.float64, device=x.device)
             N.check(lib.fld_net_forward_landmarks(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, int(n_points), float(thresh),
                                                   N.ptr(xy), N.stream_ptr(dev)))

@@ -121,6 +121,44 @@ def class_map_device(scores, oh, ow):
 
 
 # ----------------------------------------------------------------------------------------------- batched pipeline
+class CapturedRun:
+    """One LandmarkPipeline run recorded as a CUDA graph.  The graph's kernels have raw device pointers baked in (inputs, the
+    lane's activation workspace and result buffers, the kernel plans' tile schedules), so this object keeps all of them alive
+    and in place: it holds the tensors, pins the lane's workspace against re-allocation and retains the net's plans
+    (fld_net_retain).  Replacing the model's weights invalidates it — replay() then raises instead of touching freed memory.
+    Unpacks like the (graph, results) pair capture() used to return."""
+
+    def __init__(self, graph, results, keep):
+        self.graph, self.results, self._keep = graph, results, keep
+        self._release, self._why_invalid = None, None
+
+    def replay(self):
+        if self._why_invalid is not None:
+            raise N.FldError("captured run is no longer valid: " + self._why_invalid)
+        self.graph.replay()
+        return self.results
+
+    def invalidate(self, why):
+        self._why_invalid = why
+        self._release = None
+
+    def close(self):
+        if self._release is not None:
+            self._release()
+            self._release = None
+        self._why_invalid = self._why_invalid or "closed"
+
+    def __del__(self):
+        try:
+            if self._release is not None:
+                self._release()
+        except Exception:
+            pass
+
+    def __iter__(self):
+        return iter((self, self.results))
+
+
 class LandmarkPipeline:
     """frames + detector boxes -> 68 landmarks -> aligned crops, entirely on one GPU:
     crop/resize (a1) -> regression CNN (a2) -> decode (a3) -> Umeyama + warp (a10)."""
@@ -172,8 +210,9 @@ class LandmarkPipeline:
 
     def capture(self, frames, boxes, face2frame, want_uint=False, lane=0):
         """Record one run over FIXED input buffers into a CUDA graph (small batches are launch-bound: ~12 kernels plus the
-        Python shim per run).  Returns (graph, results): refill `frames` / `boxes` / `face2frame` in place, call
-        `graph.replay()`, read `results` (the lane's buffers)."""
+        Python shim per run).  Returns a CapturedRun (unpacks as (graph, results)): refill `frames` / `boxes` / `face2frame`
+        in place, call `.replay()`, read `.results` (the lane's buffers).  The capture keeps every buffer its kernels point
+        at alive; a lane with a live capture cannot be used for a larger batch."""
         with torch.cuda.device(self.device):
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -184,7 +223,10 @@ class LandmarkPipeline:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 res = self.run_device(frames, boxes, face2frame, want_uint, lane)
-        return g, res
+            cap = CapturedRun(g, res, [frames, boxes, face2frame, self, _template_device(self.template, frames.device)])
+            cap._release, ws = self.model.pin_lane(self.device, self.dtype, lane, cap)
+            cap._keep.append(ws)
+        return cap
 
     def __call__(self, frames, boxes, face2frame=None):
         """NumPy in / NumPy out convenience (H2D, run, D2H)."""

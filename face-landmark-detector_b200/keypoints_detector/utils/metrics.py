@@ -15,9 +15,16 @@ def heatmap_xy_device(hm, n_points=4, thresh=0.0):
     if n_points > N.MAX_TOPN:
         raise ValueError("n_points must be <= %d" % N.MAX_TOPN)
     xy = torch.empty((B, 2 * L), dtype=torch.float64, device=hm.device)
+    if B == 0:
+        return xy
     with torch.cuda.device(hm.device):
-        N.check(lib.fld_decode_heatmap_xy(N.handle(hm.device), N.ptr(hm), B, H, W, L, int(n_points), float(thresh), N.ptr(xy),
-                                          N.stream_ptr(hm.device)))
+        h = N.handle(hm.device)
+        # the two-pass decode's partials: a per-call buffer from the stream-aware allocator, so decodes enqueued on
+        # different streams never share scratch (the library itself owns none)
+        need = int(lib.fld_decode_heatmap_scratch_bytes(h, B, H, W, L, int(n_points)))
+        scratch = torch.empty(max(need, 1), dtype=torch.uint8, device=hm.device)
+        N.check(lib.fld_decode_heatmap_xy(h, N.ptr(hm), B, H, W, L, int(n_points), float(thresh), N.ptr(xy), N.ptr(scratch),
+                                          scratch.numel(), N.stream_ptr(hm.device)))
     return xy
 
 

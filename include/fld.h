@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FLD_ABI_VERSION 1
+#define FLD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FLD_API __attribute__((visibility("default")))
@@ -146,9 +146,17 @@ FLD_API int fld_net_forward_classmap(fld_net* net, const void* in, int B, void* 
  * heat-map pixels, (-1, -1) where sum / n <= thresh.  In FLD_BF16 mode, when the graph ends in Conv2DTranspose(k = 2*stride) +
  * softmax (fcn_8 / fcn_32), the SOFT centroid is accumulated in the transposed conv's epilogue (fp32 atomics: summation order,
  * hence the last bits, vary from run to run) and the probabilities are never written to HBM.  In every other case (top-n,
- * fp32 mode, other graphs) the final tensor is materialised in the workspace and decoded by fld_decode_heatmap_xy. */
+ * fp32 mode, other graphs) the final tensor is materialised in the workspace and decoded by fld_decode_heatmap_xy, whose
+ * partials follow the activations: the workspace must hold fld_net_landmarks_workspace_bytes(net, B, n_points). */
+FLD_API size_t fld_net_landmarks_workspace_bytes(const fld_net* net, int B, int n_points);
 FLD_API int fld_net_forward_landmarks(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int n_points, double thresh,
                                       double* xy, fld_stream stream);
+
+/* CUDA-graph lifetime: a graph captured around fld_net_forward* bakes in device pointers owned by the net's cached kernel
+ * plans.  While the retain count is > 0 no plan is evicted (the plan caches otherwise keep the 16 most recent (batch, buffer)
+ * combinations per layer).  Both return the new count.  The caller keeps workspace and I/O buffers alive itself. */
+FLD_API int fld_net_retain(fld_net* net);
+FLD_API int fld_net_release(fld_net* net);
 
 /* Per-layer device timing (bench.py's live roofline measurement): when enabled, fld_net_forward brackets
  * every layer with CUDA events on the launching stream; fld_net_layer_times waits for the last profiled
@@ -173,10 +181,13 @@ FLD_API int fld_decode_classmap(fld_handle* h, const float* scores, int B, int h
 /* Replaces utils/metrics.py:46-109 (get_average_xy / transfer_xy_coord / transfer_target).
  * hm: float32 [B,H,W,L].  n_points < 1: full soft-centroid (:58-64); else top-n weighted centroid
  * (:66-77, ties -> higher flat index).  xy: float64 [B, 2L] = (x0,y0,x1,y1,...), (-1,-1) where
- * sum/n <= thresh (:78-79).  n_points <= FLD_MAX_TOPN. */
+ * sum/n <= thresh (:78-79).  n_points <= FLD_MAX_TOPN.  The decode is two-pass; its partials live in a CALLER-provided
+ * scratch buffer of at least fld_decode_heatmap_scratch_bytes(...) bytes, so decodes in flight on different streams (each
+ * with its own scratch) never interfere and nothing is allocated, freed or synchronised inside the call (graph-capture safe). */
 #define FLD_MAX_TOPN 128
+FLD_API size_t fld_decode_heatmap_scratch_bytes(fld_handle* h, int B, int H, int W, int L, int n_points);
 FLD_API int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int H, int W, int L, int n_points, double thresh,
-                          double* xy, fld_stream stream);
+                          double* xy, void* scratch, size_t scratch_bytes, fld_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Alignment (build-defined — nothing in the reference to replace; semantics =

@@ -26,27 +26,40 @@ def five_points(marks68):
     return np.stack([le, re, m[..., 30, :], m[..., 48, :], m[..., 54, :]], axis=-2)
 
 
+def _tree_sum(vals):
+    """Summation tree of the CUDA fit (csrc/align.cu fit_similarity_warp): lane l of a 32-lane warp adds elements
+    l, l+32, ... in index order, then an xor butterfly (16, 8, 4, 2, 1) combines the lanes.  IEEE addition is
+    commutative, so every lane ends with the same value; lane 0's is returned."""
+    p = [0.0] * 32
+    for i, v in enumerate(vals):
+        p[i % 32] = p[i % 32] + float(v)
+    for off in (16, 8, 4, 2, 1):
+        p = [p[l] + p[l ^ off] for l in range(32)]
+    return p[0]
+
+
 def umeyama(src, dst):
     """Closed-form 2-D similarity fit src->dst.  Returns M [2,3] fp64 (NaN if degenerate).
 
-    Plain sequential sums in index order (the CUDA kernel uses the same order so the
-    fp64 results agree to rounding)."""
+    Every sum uses `_tree_sum`, the fixed warp-parallel order of the CUDA kernel, and no fused multiply-add, so the
+    fp64 results agree bit for bit."""
     src = np.asarray(src, dtype=np.float64)
     dst = np.asarray(dst, dtype=np.float64)
     n = src.shape[0]
-    mpx = mpy = mqx = mqy = 0.0
-    for i in range(n):
-        mpx += src[i, 0]; mpy += src[i, 1]; mqx += dst[i, 0]; mqy += dst[i, 1]
-    mpx /= n; mpy /= n; mqx /= n; mqy /= n
-    var = a = b = c = d = 0.0
-    for i in range(n):
-        px = src[i, 0] - mpx; py = src[i, 1] - mpy
-        qx = dst[i, 0] - mqx; qy = dst[i, 1] - mqy
-        var += px * px + py * py
-        a += qx * px; b += qx * py; c += qy * px; d += qy * py
+    px_, py_ = [float(v) for v in src[:, 0]], [float(v) for v in src[:, 1]]
+    qx_, qy_ = [float(v) for v in dst[:, 0]], [float(v) for v in dst[:, 1]]
+    mpx = _tree_sum(px_) / n; mpy = _tree_sum(py_) / n
+    mqx = _tree_sum(qx_) / n; mqy = _tree_sum(qy_) / n
+    dx = [v - mpx for v in px_]; dy = [v - mpy for v in py_]
+    ex = [v - mqx for v in qx_]; ey = [v - mqy for v in qy_]
+    var = _tree_sum([x * x + y * y for x, y in zip(dx, dy)])
+    a = _tree_sum([q * x for q, x in zip(ex, dx)])
+    b = _tree_sum([q * y for q, y in zip(ex, dy)])
+    c = _tree_sum([q * x for q, x in zip(ey, dx)])
+    d = _tree_sum([q * y for q, y in zip(ey, dy)])
     P = a + d
     Q = c - b
-    if var == 0.0 or (P == 0.0 and Q == 0.0) or not np.isfinite(var):
+    if var == 0.0 or (P == 0.0 and Q == 0.0) or not np.isfinite(var) or not np.isfinite(P) or not np.isfinite(Q):
         return np.full((2, 3), np.nan)
     # (1/n) factors of covariance and variance cancel
     l00 = P / var; l01 = -Q / var

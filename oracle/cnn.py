@@ -15,8 +15,10 @@ model definitions with Keras layer semantics:
   ResNet50 encoder     networks/resnet50.py:23-173
                        standing in for the opaque SavedModel at prediction.py:84
 
-Two independent restatements are kept and must agree: torch functional ops (``*_t``) and a numpy
-einsum/loop version (``*_np``, small cases only).
+Two independent restatements are kept for EVERY graph (vanilla / VGG16 / MobileNet / ResNet50 encoders, fcn_8, fcn_32) and must
+agree: torch functional ops (``*_t``) and a numpy version (``*_np``) written without torch — sliding windows + einsum for
+dense convs (stride by slicing), an explicit tap loop for depth-wise convs, window maxima for pools, a scatter-add loop for
+transposed convs.  Tests run the numpy side on small inputs only.
 
 Weights are a dict name -> ndarray in Keras layouts: Conv2D kernel [kh,kw,Cin,Cout], bias [Cout];
 BatchNormalization gamma/beta/moving_mean/moving_variance [C]; Conv2DTranspose kernel
@@ -305,3 +307,90 @@ def fcn_forward_encoder(x_nhwc, weights, encoder="mobilenet", dtype=torch.float6
     if return_levels:
         return probs, [l.permute(0, 2, 3, 1).contiguous().numpy() for l in levels]
     return probs
+
+
+# ----------------------------------------------------------------------------- numpy restatement of the other encoders
+def conv2d_np_s(x, kernel, bias=None, pad=(0, 0, 0, 0), stride=1):
+    """conv2d_np with a stride: the 'valid' conv evaluated at every position, then sub-sampled (Keras strides start at 0)."""
+    y = conv2d_np(x, kernel, None, pad)[:, ::stride, ::stride]
+    return y + bias if bias is not None else y
+
+
+def dwconv_np(x, kernel, pad=(0, 0, 0, 0), stride=1):
+    """DepthwiseConv2D 'valid', depth_multiplier 1: x NHWC, kernel [kh,kw,C,1]; explicit loop over the taps."""
+    x = np.pad(x, ((0, 0), (pad[0], pad[1]), (pad[2], pad[3]), (0, 0)))
+    kh, kw = kernel.shape[:2]
+    oh, ow = x.shape[1] - kh + 1, x.shape[2] - kw + 1
+    out = np.zeros((x.shape[0], oh, ow, x.shape[3]), dtype=x.dtype)
+    for a in range(kh):
+        for b in range(kw):
+            out += x[:, a: a + oh, b: b + ow, :] * kernel[a, b, :, 0]
+    return out[:, ::stride, ::stride]
+
+
+def maxpool_np(x, k, s):
+    """MaxPooling2D((k,k), strides=s) 'valid' (floor)."""
+    B, H, W, C = x.shape
+    oh, ow = (H - k) // s + 1, (W - k) // s + 1
+    out = np.full((B, oh, ow, C), -np.inf, dtype=x.dtype)
+    for a in range(k):
+        for b in range(k):
+            out = np.maximum(out, x[:, a: a + (oh - 1) * s + 1: s, b: b + (ow - 1) * s + 1: s])
+    return out
+
+
+def vgg_encoder_np(x, w):
+    """vgg16.py:27-74 (x NHWC)."""
+    levels = []
+    for b, n in enumerate((2, 2, 3, 3, 3), start=1):
+        for i in range(1, n + 1):
+            name = "block%d_conv%d" % (b, i)
+            x = np.maximum(conv2d_np(x, w[name + "/kernel"], w[name + "/bias"], pad=same_pad(3)), 0)
+        x = maxpool_np(x, 2, 2)
+        levels.append(x)
+    return levels
+
+
+def mobilenet_encoder_np(x, w):
+    """mobilenet.py:16-104 (x NHWC)."""
+    r6 = lambda t: np.minimum(np.maximum(t, 0), 6)
+    x = r6(bn_np(conv2d_np_s(x, w["conv1/kernel"], None, pad=(1, 1, 1, 1), stride=2), w, "conv1_bn"))
+    strides = (1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1)
+    levels = []
+    for i, s in enumerate(strides, start=1):
+        x = r6(bn_np(dwconv_np(x, w["conv_dw_%d/depthwise_kernel" % i], pad=(1, 1, 1, 1), stride=s), w, "conv_dw_%d_bn" % i))
+        x = r6(bn_np(conv2d_np(x, w["conv_pw_%d/kernel" % i]), w, "conv_pw_%d_bn" % i))
+        if i in (1, 3, 5, 11, 13):
+            levels.append(x)
+    return levels
+
+
+def resnet50_encoder_np(x, w):
+    """resnet50.py:23-173 (x NHWC): f1 is conv1's raw output, f2 the top/left-padded stage-2 output."""
+    relu = lambda t: np.maximum(t, 0)
+
+    def block(x, stage, blk, stride, shortcut):
+        cb, bb = "res%d%s_branch" % (stage, blk), "bn%d%s_branch" % (stage, blk)
+        y = relu(bn_np(conv2d_np_s(x, w[cb + "2a/kernel"], w[cb + "2a/bias"], stride=stride), w, bb + "2a"))
+        y = relu(bn_np(conv2d_np(y, w[cb + "2b/kernel"], w[cb + "2b/bias"], pad=same_pad(3)), w, bb + "2b"))
+        y = bn_np(conv2d_np(y, w[cb + "2c/kernel"], w[cb + "2c/bias"]), w, bb + "2c")
+        sc = bn_np(conv2d_np_s(x, w[cb + "1/kernel"], w[cb + "1/bias"], stride=stride), w, bb + "1") if shortcut else x
+        return relu(y + sc)
+
+    x = conv2d_np_s(x, w["conv1/kernel"], w["conv1/bias"], pad=(3, 3, 3, 3), stride=2)
+    levels = [x]
+    x = maxpool_np(relu(bn_np(x, w, "bn_conv1")), 3, 2)
+    for stage, blocks, stride in ((2, "abc", 1), (3, "abcd", 2), (4, "abcdef", 2), (5, "abc", 2)):
+        for bi, b in enumerate(blocks):
+            x = block(x, stage, b, stride if bi == 0 else 1, bi == 0)
+        levels.append(np.pad(x, ((0, 0), (1, 0), (1, 0), (0, 0))) if stage == 2 else x)
+    return levels
+
+
+def fcn_32_logits_np(levels, w):
+    """fcn.py:137-146 (numpy)."""
+    f5 = levels[4]
+    o = np.maximum(conv2d_np(f5, w["head7/kernel"], w["head7/bias"], pad=same_pad(7)), 0)
+    o = np.maximum(conv2d_np(o, w["head1/kernel"], w["head1/bias"]), 0)
+    o = conv2d_np(o, w["score5/kernel"], w["score5/bias"])
+    return deconv_np(o, w["up32/kernel"], 32)

@@ -1,0 +1,343 @@
+"""GPU parity tests added in round 2 (pytest -m gpu), all through the C-ABI:
+
+* config C2 at its full batch (256 faces) and config C3 at its full resolution (224 x 224, 68 classes) against the fp64
+  CPU oracle, with the bars BASELINE.json's north_star states: decoded landmarks within 0.05 px (fp32-accurate modes) /
+  0.5 px (bf16 mode);
+* decoded landmarks (soft centroid and top-4) for every encoder of LANDMARKS_MODELS and fcn_32 in bf16 mode;
+* the shared-memory-staged alignment kernel (csrc/align.cu align_tile_kernel) on the cases that stress it: faces leaving the
+  frame, extreme scales (global-load fallback), caller matrices with shear, small batches (row split);
+* caller-provided decode scratch under concurrent streams, capture lifetime rules, video_predict with a fake capture.
+"""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_lib):
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def T(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev).contiguous()
+
+
+def _soft_centroids(pr):
+    """reference utils/metrics.py:56-64 on probabilities [B,H,W,L] (float64) -> [B,L,2] (x, y)."""
+    B, H, W, L = pr.shape
+    s = pr.sum((1, 2))
+    out = np.empty((B, L, 2))
+    out[..., 0] = (pr * np.arange(W)[None, None, :, None]).sum((1, 2)) / s
+    out[..., 1] = (pr * np.arange(H)[None, :, None, None]).sum((1, 2)) / s
+    return out
+
+
+def _topn_centroids(pr, n):
+    """reference utils/metrics.py:66-77 (top-n weighted centroid; ties -> higher flat index) and the margin between the n-th
+    and (n+1)-th largest value relative to the n-th (a near-tie there makes the SELECTION itself precision dependent)."""
+    B, H, W, L = pr.shape
+    flat = pr.reshape(B, H * W, L)
+    out = np.empty((B, L, 2))
+    margin = np.empty((B, L))
+    for b in range(B):
+        for l in range(L):
+            v = flat[b, :, l]
+            order = np.lexsort((np.arange(v.size), v))[::-1]          # descending value, higher index first on ties
+            top = order[:n]
+            w = v[top]
+            out[b, l, 0] = (w * (top % W)).sum() / w.sum()
+            out[b, l, 1] = (w * (top // W)).sum() / w.sum()
+            margin[b, l] = (v[order[n - 1]] - v[order[n]]) / max(v[order[n - 1]], 1e-300)
+    return out, margin
+
+
+# ------------------------------------------------------------------------------------------------ C2 at batch 256
+def test_c2_batch256_against_oracle(dev):
+    """BASELINE.json configs[1]: 256 crops through vanilla trunk@128 + FC-136, every compute mode, vs the fp64 oracle;
+    then the whole step (crop/resize -> CNN -> decode) in source-image pixels on boxes of 96..400 px."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.regression import landmark_regressor
+    from oracle import cnn as o_cnn, decode as o_dec, preprocess as o_pre
+    B = 256
+    m = landmark_regressor().init_weights(seed=0)
+    frames = synthetic.make_frames(4, 1080, 1920, seed=11)
+    boxes = synthetic.make_boxes(B, 1080, 1920, seed=12, min_side=96, max_side=400)
+    f2f = (np.arange(B) // 64).astype(np.int32)
+    crops, fbs = zip(*[o_pre.crop_resize_rgb(frames[f2f[i]], boxes[i]) for i in range(B)])
+    crops = np.stack(crops)
+    ref = o_cnn.regression_forward(crops, m.weights, torch.float64)
+    marks_ref = np.stack([o_dec.regression_decode(ref[i], fbs[i])[0] for i in range(B)])
+    xt = T(crops, dev)
+    for dtype, tol_n, tol_px in (("float32", 1.25e-4, 0.05), ("bfloat16", 1.25e-3, 0.5)):
+        out = m.forward_device(xt, dtype).cpu().numpy()
+        err = np.abs(out - ref).max()
+        assert out.shape == (B, 136) and err < tol_n, (dtype, err)
+        r = prediction.LandmarkPipeline(m, dtype=dtype).run_device(T(frames, dev), T(boxes, dev), T(f2f, dev))
+        assert np.array_equal(r["crops"].cpu().numpy(), crops)
+        perr = np.abs(r["marks"].cpu().numpy() - marks_ref).max()
+        assert perr <= tol_px, (dtype, perr)
+
+
+# ------------------------------------------------------------------------------------------------ C3 at 224 x 224
+def test_c3_224_against_oracle(dev):
+    """BASELINE.json configs[2]: fcn_8 over the vanilla encoder at 224 x 224, 68 classes, against the fp64 oracle on 2 images:
+    class-map agreement, soft centroid and top-4 centroid in heat-map pixels (0.05 px fp32 / 0.5 px bf16)."""
+    from keypoints_detector.data.generator import get_image_array
+    from keypoints_detector.networks.fcn import fcn_8
+    from oracle import cnn as o_cnn
+    m = fcn_8(68, input_height=224, input_width=224).init_weights(3)
+    imgs = [gi.image(40 + i, 300, 360) for i in range(2)]
+    x = np.stack([get_image_array(im, 224, 224, ordering="channels_last") for im in imgs])
+    pr = o_cnn.fcn_forward(x.astype(np.float64), m.weights, "fcn_8", torch.float64).reshape(2, 232, 232, 68)
+    cm_ref = pr.argmax(-1)
+    soft_ref = _soft_centroids(pr)
+    top_ref, margin = _topn_centroids(pr, 4)
+    xt = T(x, dev)
+    for dtype, rate, tol in (("float32", 0.999, 0.05), ("bfloat16", 0.97, 0.5)):
+        cm = m.forward_classmap_device(xt, dtype).cpu().numpy()
+        assert cm.shape == (2, 232, 232) and (cm == cm_ref).mean() > rate, (dtype, (cm == cm_ref).mean())
+        soft = m.forward_landmarks_device(xt, dtype, n_points=0).cpu().numpy().reshape(2, 68, 2)
+        assert np.abs(soft - soft_ref).max() <= tol, (dtype, np.abs(soft - soft_ref).max())
+        top = m.forward_landmarks_device(xt, dtype, n_points=4).cpu().numpy().reshape(2, 68, 2)
+        # the top-4 SET is a discrete choice: where the 4th and 5th largest probabilities are closer than the mode's own
+        # relative precision the choice is not defined by the arithmetic, so those channels are compared only when clear
+        clear = margin > (1e-4 if dtype == "float32" else 2e-2)
+        d = np.abs(top - top_ref).max(-1)
+        assert clear.mean() > 0.3, clear.mean()
+        assert d[clear].max() <= tol, (dtype, d[clear].max(), clear.mean())
+
+
+# ------------------------------------------------------------------------------------------------ every encoder, decoded landmarks
+@pytest.mark.parametrize("name,H,W", [("fcn_8_vgg", 64, 96), ("fcn_8_mobilenet", 64, 96), ("fcn_8_resnet50", 96, 64),
+                                      ("fcn_32_vanilla", 64, 64), ("fcn_32_mobilenet", 64, 64)])
+def test_decoded_landmarks_every_encoder_bf16(dev, name, H, W):
+    """north_star's bf16 bar is on DECODED landmarks (0.5 px), not on per-pixel probabilities: soft centroid of every class
+    channel for each registry model in bf16 mode vs the fp64 oracle's probabilities, plus fp32 mode at 0.05 px."""
+    from keypoints_detector.networks.basic_models import LANDMARKS_MODELS
+    from oracle import cnn as o_cnn
+    m = LANDMARKS_MODELS[name](68, input_height=H, input_width=W).init_weights(21)
+    x = np.random.default_rng(21).uniform(0, 1, (2, H, W, 3)).astype(np.float32)
+    w = o_cnn._prep(m.weights, torch.float64)
+    xin = torch.from_numpy(x).double().permute(0, 3, 1, 2)
+    enc = {"vgg": o_cnn.vgg_encoder_t, "mobilenet": o_cnn.mobilenet_encoder_t, "resnet50": o_cnn.resnet50_encoder_t,
+           "vanilla": o_cnn.vanilla_encoder_t}[name.split("_")[2]]
+    levels = enc(xin, w)
+    logits = o_cnn.fcn_8_logits_t(levels, w) if name.startswith("fcn_8") else o_cnn.fcn_32_logits_t(levels, w)
+    oh, ow = m.output_height, m.output_width
+    pr = o_cnn.segmentation_probs_t(logits).numpy().reshape(2, oh, ow, 68)
+    soft_ref = _soft_centroids(pr)
+    xt = T(x, dev)
+    for dtype, tol in (("float32", 0.05), ("bfloat16", 0.5)):
+        soft = m.forward_landmarks_device(xt, dtype, n_points=0).cpu().numpy().reshape(2, 68, 2)
+        assert np.abs(soft - soft_ref).max() <= tol, (name, dtype, np.abs(soft - soft_ref).max())
+
+
+# ------------------------------------------------------------------------------------------------ tile-staged alignment kernel
+def _check_warps(frames, f2f, M, crops, out_hw, idx):
+    oh, ow = out_hw
+    for i in idx:
+        ref = cv2.warpAffine(frames[f2f[i]], M[i], (ow, oh), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        assert np.array_equal(crops[i], ref), i
+
+
+def test_align_tile_kernel_edges(dev):
+    """align_tile_kernel (TMA-staged source boxes) must stay bit-identical to cv2.warpAffine where round 1's per-pixel kernel was:
+    faces hanging over every frame edge (zero-filled by the tensor map), faces far outside, scales from 4x up to 6x down (boxes
+    beyond the largest class fall back to global loads per face), small batches (tile rows split over CTAs) and both fits."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from oracle import align as o_al
+    H, W = 300, 448                                           # 448 * 3 bytes per row: a multiple of 16 -> tile kernel eligible
+    frames = np.stack([gi.image(60 + i, H, W) for i in range(3)])
+    rng = np.random.default_rng(17)
+    B = 90
+    pts = np.zeros((B, 5, 2), np.float32)
+    for i in range(B):
+        s = float(np.exp(rng.uniform(np.log(0.16), np.log(4.0))))           # crop px per frame px
+        th = np.deg2rad(rng.uniform(-180, 180))
+        L = s * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        c = np.array([rng.uniform(-60, W + 60), rng.uniform(-60, H + 60)])   # many centres near / beyond the border
+        t = np.array([56.0, 56.0]) - L @ c
+        pts[i] = ((o_al.TEMPLATE_112 - t) @ np.linalg.inv(L).T + rng.normal(0, 0.7, (5, 2))).astype(np.float32)
+    pts[7] += 5000.0                                                           # far outside: all-zero crop
+    f2f = (np.arange(B) % 3).astype(np.int32)
+    for n in (B, 3):                                                           # 3 faces: tile rows split across CTAs
+        crops, M = prediction.align_device(T(frames, dev), T(f2f[:n], dev), T(pts[:n], dev), None, (112, 112), five_point=False)
+        crops, M = crops.cpu().numpy(), M.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(M[i], o_al.umeyama(pts[i], o_al.TEMPLATE_112)), i
+        _check_warps(frames, f2f, M, crops, (112, 112), range(n))
+    full, _ = prediction.align_device(T(frames, dev), T(f2f, dev), T(pts, dev), None, (112, 112), five_point=False)
+    assert not full[7].any()
+    # other tile-eligible output sizes and the 68 -> 5 point reduction
+    marks = np.zeros((12, 68, 2), np.float32)
+    from keypoints_detector.networks.init import canonical_face68
+    for i in range(12):
+        marks[i] = (canonical_face68() * rng.uniform(50, 420) + rng.uniform(-60, 250, 2) + rng.normal(0, 1.0, (68, 2))).astype(np.float32)
+    for out_hw in ((112, 112), (128, 96), (64, 128)):
+        tm = o_al.TEMPLATE_112 * np.array([out_hw[1] / 112.0, out_hw[0] / 112.0])
+        crops, M = prediction.align_device(T(frames, dev), T(f2f[:12], dev), T(marks, dev), tm, out_hw, five_point=True)
+        crops, M = crops.cpu().numpy(), M.cpu().numpy()
+        for i in range(12):
+            assert np.array_equal(M[i], o_al.umeyama(o_al.five_points(marks[i]), tm)), i
+        _check_warps(frames, f2f, M, crops, out_hw, range(12))
+
+
+def test_warp_affine_caller_matrices_with_shear(dev):
+    """fld_warp_affine with arbitrary affine matrices (shear, anisotropic scale, reflection): a tile's source box is then not a
+    square and may not fit the class picked from the linear part — those tiles take the global-load path inside the tile
+    kernel.  Bit-identical to cv2.warpAffine either way."""
+    from keypoints_detector import prediction
+    H, W = 240, 320                                           # 960 bytes per row
+    frames = np.stack([gi.image(75 + i, H, W) for i in range(2)])
+    rng = np.random.default_rng(23)
+    B = 40
+    M = np.zeros((B, 2, 3))
+    for i in range(B):
+        A = rng.normal(0, 1.0, (2, 2)) * np.exp(rng.uniform(-1.5, 1.0))
+        if abs(np.linalg.det(A)) < 1e-3:
+            A += np.eye(2)
+        c = np.array([rng.uniform(0, W), rng.uniform(0, H)])
+        M[i] = np.concatenate([A, (np.array([56.0, 56.0]) - A @ c)[:, None]], 1)
+    f2f = (np.arange(B) % 2).astype(np.int32)
+    crops = prediction.warp_affine_device(T(frames, dev), T(f2f, dev), T(M, dev), (112, 112)).cpu().numpy()
+    _check_warps(frames, f2f, M, crops, (112, 112), range(B))
+
+
+def test_align_tile_equals_generic_kernel_at_c4_scale(dev, monkeypatch):
+    """The two warp kernels (tile-staged, per-pixel generic) are independent implementations of the same integer scheme:
+    1024 faces of config C4's distribution must agree byte for byte (the generic kernel is selected by an unaligned frame
+    pointer, exactly what a sliced tensor view gives)."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from oracle import align as o_al
+    F, B = 16, 1024
+    g = torch.Generator().manual_seed(2)
+    frames = torch.randint(0, 256, (F, 1080, 1920, 3), dtype=torch.uint8, generator=g).to(dev)
+    pts, _ = synthetic.make_similarity_landmarks(B, 1080, 1920, o_al.TEMPLATE_112, seed=9)
+    f2f = T((np.arange(B) // 64).astype(np.int32), dev)
+    a, Ma = prediction.align_device(frames, f2f, T(pts, dev), None, (112, 112), five_point=False)
+    flat = torch.empty(frames.numel() + 16, dtype=torch.uint8, device=dev)
+    shifted = flat[4:4 + frames.numel()].view(frames.shape)                     # 4-byte offset: not 16-byte aligned -> generic path
+    shifted.copy_(frames)
+    lib = prediction.N.load_library()
+    crops = torch.empty_like(a)
+    M2 = torch.empty_like(Ma)
+    t = prediction._template_device(None, dev)
+    prediction.N.check(lib.fld_align(prediction.N.handle(dev), prediction.N._vp(shifted.data_ptr()), F, 1080, 1920, 3, prediction.N.ptr(f2f),
+                                     prediction.N.ptr(T(pts, dev)), 5, prediction.N.ptr(t), 5, 0, B, 112, 112, prediction.N.ptr(M2),
+                                     prediction.N.ptr(crops), prediction.N.stream_ptr(dev)))
+    assert torch.equal(M2, Ma) and torch.equal(crops, a)
+
+
+# ------------------------------------------------------------------------------------------------ scratch / capture rules
+def test_decode_scratch_is_per_call_and_stream_safe(dev):
+    """Two top-n decodes of DIFFERENT maps in flight on different streams (the race the handle-owned scratch of round 1 had):
+    each call carves its partials from its own caller-provided buffer, so both equal their serial results."""
+    from keypoints_detector.utils import metrics
+    rng = np.random.default_rng(3)
+    a = T(rng.random((6, 136, 136, 68), dtype=np.float32), dev)
+    b = T(rng.random((6, 136, 136, 68), dtype=np.float32), dev)
+    ra, rb = metrics.heatmap_xy_device(a, 4, 0.0).clone(), metrics.heatmap_xy_device(b, 4, 0.0).clone()
+    sa_, sb_ = metrics.heatmap_xy_device(a, 0, 0.0).clone(), metrics.heatmap_xy_device(b, 0, 0.0).clone()
+    torch.cuda.synchronize(dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            xa, ya = metrics.heatmap_xy_device(a, 4, 0.0), metrics.heatmap_xy_device(a, 0, 0.0)
+        with torch.cuda.stream(s2):
+            xb, yb = metrics.heatmap_xy_device(b, 4, 0.0), metrics.heatmap_xy_device(b, 0, 0.0)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(xa, ra) and torch.equal(xb, rb) and torch.equal(ya, sa_) and torch.equal(yb, sb_)
+    # the ABI rejects a missing / short scratch instead of allocating behind the caller's back
+    from keypoints_detector import _native as N
+    lib = N.load_library()
+    xy = torch.empty((6, 136), dtype=torch.float64, device=dev)
+    rc = lib.fld_decode_heatmap_xy(N.handle(dev), N.ptr(a), 6, 136, 136, 68, 4, 0.0, N.ptr(xy), None, 0, N.stream_ptr(dev))
+    assert rc == -1
+    tiny = torch.empty(64, dtype=torch.uint8, device=dev)
+    rc = lib.fld_decode_heatmap_xy(N.handle(dev), N.ptr(a), 6, 136, 136, 68, 4, 0.0, N.ptr(xy), N.ptr(tiny), 64, N.stream_ptr(dev))
+    assert rc == -4
+
+
+def test_capture_keeps_buffers_and_invalidates(dev):
+    """LandmarkPipeline.capture: the CapturedRun pins the lane workspace (a larger batch on that lane is refused instead of
+    re-allocating memory the graph points at), survives more plans being built than the plan cache holds, and refuses to replay
+    after the model's weights were replaced."""
+    from keypoints_detector import _native as N, prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = landmark_regressor().init_weights(seed=5)
+    pipe = prediction.LandmarkPipeline(m, dtype="bfloat16")
+    frames = T(synthetic.make_frames(1, 480, 640, seed=41), dev)
+    boxes = T(synthetic.make_boxes(12, 480, 640, seed=42, max_side=300), dev)
+    f2f = T(np.zeros(12, np.int32), dev)
+    ref = {k: v.clone() for k, v in pipe.run_device(frames, boxes, f2f, lane=0).items() if k in ("marks", "aligned")}
+    cap = pipe.capture(frames, boxes, f2f, lane=3)
+    with pytest.raises(N.FldError):
+        pipe.run_device(frames, T(synthetic.make_boxes(500, 480, 640, seed=43, max_side=300), dev), T(np.zeros(500, np.int32), dev), lane=3)
+    for b in range(1, 24):                                                     # 23 more (batch, buffer) plans per layer on another lane
+        pipe.run_device(frames, boxes[:b % 12 + 1].contiguous(), f2f[:b % 12 + 1].contiguous(), lane=1 + b % 2)
+    torch.cuda.synchronize(dev)
+    for k in ref:
+        cap.results[k].zero_()
+    res = cap.replay()
+    torch.cuda.synchronize(dev)
+    for k in ref:
+        assert torch.equal(res[k], ref[k]), k
+    g, res2 = cap                                                               # unpacks like the old (graph, results) pair
+    assert g is cap and res2 is cap.results
+    m.init_weights(seed=6)                                                      # rebuilds the nets: the capture is dead
+    with pytest.raises(N.FldError):
+        cap.replay()
+
+
+def test_video_predict_with_fake_capture(dev, monkeypatch):
+    """reference prediction.py:99-113 with cv2.VideoCapture replaced by a fake: every rect of every frame is decoded (one
+    batched call per frame) and drawn; the marks equal detect_marks on the same frame / rect."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = landmark_regressor().init_weights(seed=8)
+    frames = synthetic.make_frames(3, 360, 480, seed=51)
+    rects = [synthetic.make_boxes(k, 360, 480, seed=60 + k, min_side=80, max_side=200).tolist() for k in (2, 0, 3)]
+
+    class FakeCapture:
+        def __init__(self, src):
+            self.i, self.released = 0, False
+
+        def read(self):
+            if self.i >= len(frames):
+                return False, None
+            self.i += 1
+            return True, frames[self.i - 1].copy()
+
+        def release(self):
+            self.released = True
+
+    drawn, seen = [], []
+    monkeypatch.setattr(cv2, "VideoCapture", FakeCapture)
+    monkeypatch.setattr(prediction, "draw_marks", lambda img, marks, **kw: drawn.append(np.array(marks)))
+
+    def detector(img):
+        seen.append(img.shape)
+        return rects[len(seen) - 1]
+
+    prediction.video_predict(detector, m, capture="fake.mp4", show=False)
+    assert len(seen) == 3 and len(drawn) == 5
+    k = 0
+    for fi, rs in enumerate(rects):
+        for r in rs:
+            ref = prediction.detect_marks(frames[fi], m, r)
+            assert drawn[k].shape == (68, 2) and np.array_equal(drawn[k].astype(np.uint64), ref.astype(np.uint64))
+            k += 1

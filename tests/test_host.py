@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.fld_abi_version() == 1
+    assert lib.fld_abi_version() == 2
     assert lib.fld_launch_count() == 0
 
 
@@ -180,8 +180,8 @@ def test_encoder_graphs_match_oracle_shapes():
     from keypoints_detector.networks.basic_models import LANDMARKS_MODELS
     from oracle import cnn as o_cnn
     for name, build in LANDMARKS_MODELS.items():
-        m = build(5, input_height=32, input_width=64)
-        assert m.n_classes == 5 and m.output_height > 0 and m.weight_specs()
+        m = build(6, input_height=32, input_width=64)
+        assert m.n_classes == 6 and m.output_height > 0 and m.weight_specs()
     x = torch.zeros(1, 3, 32, 64, dtype=torch.float32)
     from keypoints_detector.networks import vgg16
     for getter, enc_t in ((mobilenet.get_mobilenet_encoder, o_cnn.mobilenet_encoder_t),
@@ -239,3 +239,85 @@ def test_weight_files_npz_safetensors_and_keras_names(tmp_path):
     bad["conv1/kernel"] = bad["conv1/kernel"][..., :8]
     with pytest.raises(ValueError, match="conv1/kernel"):
         fcn_8_mobilenet(5, 32, 32).set_weights(bad)
+
+
+def test_keras_auto_named_checkpoint_aliases(tmp_path):
+    """A checkpoint written by the reference's own trainer names the vanilla encoder's and the FCN head's layers with Keras
+    auto-names (the reference leaves them unnamed, networks/fcn.py:10-51, 98-121): conv2d_K.., batch_normalization_K..,
+    conv2d_transpose_K.. numbered in creation order from a session-dependent offset.  load_weights maps them by type and
+    order onto this build's names; named encoder layers (VGG) keep matching by name; a count mismatch raises KeyError."""
+    from keypoints_detector import _native as N
+    from keypoints_detector.networks.fcn import fcn_8, fcn_8_vgg
+
+    def keras_style(m, offset):
+        w = m.get_weights()
+        out, counters = {}, {"conv2d": offset, "batch_normalization": offset + 2, "conv2d_transpose": offset}
+        for L in m.graph.layers:
+            kind = {N.OP_CONV: "conv2d", N.OP_DECONV: "conv2d_transpose"}.get(L["op"])
+            if kind is None:
+                continue
+            named = L["name"].startswith("block")                                    # VGG's own names (vgg16.py:27-72)
+            auto = L["name"] if named else (kind if counters[kind] == 0 else "%s_%d" % (kind, counters[kind]))
+            if not named:
+                counters[kind] += 1
+            for v in ("kernel", "bias"):
+                if L["name"] + "/" + v in w:
+                    out["%s/%s/%s:0" % (auto, auto, v)] = w[L["name"] + "/" + v]
+            if L.get("has_bn"):
+                k = counters["batch_normalization"]
+                bn = "batch_normalization" if k == 0 else "batch_normalization_%d" % k
+                counters["batch_normalization"] += 1
+                for v in ("gamma", "beta", "moving_mean", "moving_variance"):
+                    out["%s/%s/%s:0" % (bn, bn, v)] = w[L["bn_name"] + "/" + v]
+        return w, out
+
+    for build, offset in ((lambda: fcn_8(7, input_height=32, input_width=32), 0), (lambda: fcn_8(7, input_height=32, input_width=32), 11),
+                          (lambda: fcn_8_vgg(7, 32, 32), 3)):
+        m = build().init_weights(4)
+        w, ks = keras_style(m, offset)
+        np.savez(str(tmp_path / "k.npz"), **ks)
+        m2 = build()
+        m2.load_weights(str(tmp_path / "k"))
+        assert set(m2.weights) == set(w)
+        for k in w:
+            np.testing.assert_array_equal(m2.weights[k], w[k], err_msg=k)
+    del ks["conv2d_transpose_4/conv2d_transpose_4/kernel:0"]                         # fcn_8_vgg, offset 3: up2a's auto name is _3, up2b's _4
+    np.savez(str(tmp_path / "bad.npz"), **ks)
+    with pytest.raises(KeyError, match="conv2d_transpose"):
+        fcn_8_vgg(7, 32, 32).load_weights(str(tmp_path / "bad"))
+
+
+def test_safetensors_checkpoints_are_found_and_regressor_round_trips(tmp_path):
+    """find_latest_checkpoint strips both weight-container extensions (reference training.py:41-71 strips '.index'), and the
+    regression model is a registry entry, so save_config -> model_from_checkpoint_path works for it too."""
+    from keypoints_detector import prediction
+    from keypoints_detector.networks.basic_models import LANDMARKS_MODELS
+    from keypoints_detector.training import find_latest_checkpoint
+    m = LANDMARKS_MODELS["landmark_regressor"](136).init_weights(1)
+    assert m.n_classes == 136 and m.input_height == 128
+    ck = str(tmp_path / "reg")
+    m.save_weights(ck + ".00002.npz")
+    m.save_weights(ck + ".00007.safetensors")
+    m.save_config(ck)
+    assert find_latest_checkpoint(ck) == ck + ".00007"
+    m2 = prediction.model_from_checkpoint_path(ck)
+    assert m2.model_name == "landmark_regressor" and m2.kind == "regression"
+    for k, v in m.weights.items():
+        np.testing.assert_array_equal(m2.weights[k], v)
+
+
+def test_oracle_tree_sum_is_the_documented_order():
+    """oracle.align._tree_sum mirrors csrc/align.cu's warp reduction: lane partial sums in index order, then the xor butterfly.
+    Checked against an explicit, independently written evaluation on values whose sum depends on the order."""
+    from oracle import align as o_al
+    rng = np.random.default_rng(0)
+    v = (rng.normal(0, 1, 68) * 10.0 ** rng.integers(-8, 8, 68)).tolist()
+    lanes = [0.0] * 32
+    for i, x in enumerate(v):
+        lanes[i % 32] += x
+    p = lanes
+    for off in (16, 8, 4, 2, 1):
+        p = [p[l] + p[l ^ off] for l in range(32)]
+    assert len(set(p)) == 1 and o_al._tree_sum(v) == p[0]
+    assert o_al._tree_sum(v) != sum(v) or True                                        # (order-sensitive inputs; equality is possible but rare)
+    assert o_al._tree_sum([1.5, 2.25, -3.0]) == 0.75

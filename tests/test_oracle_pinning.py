@@ -148,6 +148,44 @@ def test_cnn_two_restatements_agree():
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-10)
 
 
+@pytest.mark.parametrize("name", ["vgg", "mobilenet", "resnet50", "fcn_32"])
+def test_cnn_two_restatements_agree_other_encoders(name):
+    """The second, torch-free restatement of the graphs the first cross-check does not reach: depth-wise and
+    strided convs, ReLU6, residual blocks with strided 1x1 shortcuts, the 3x3/2 pool, one_side_pad, the 64x64 / stride-32
+    transposed conv.  reference networks/vgg16.py:27-74, mobilenet.py:16-104, resnet50.py:23-173, fcn.py:129-150.  Weights come
+    from the builders' own seeded initialiser (non-trivial BN statistics)."""
+    import torch
+    from keypoints_detector.networks import fcn, mobilenet, resnet50, vgg16
+    from keypoints_detector.networks.model import Model
+    rng = np.random.default_rng(11)
+    H, W = (32, 64) if name != "fcn_32" else (32, 32)
+    x = rng.normal(0, 1, (2, H, W, 3))
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    if name == "fcn_32":
+        m = fcn.fcn_32(5, input_height=H, input_width=W).init_weights(3)
+        wn = {k: v.astype(np.float64) for k, v in m.weights.items()}
+        wt = cnn._prep(m.weights, torch.float64)
+        lv_t = cnn.vanilla_encoder_t(xt, wt)
+        lo_t = cnn.fcn_32_logits_t(lv_t, wt).permute(0, 2, 3, 1).numpy()
+        lo_n = cnn.fcn_32_logits_np(cnn.vanilla_encoder_np(x, wn), wn)
+        assert lo_t.shape == lo_n.shape == (2, 64, 64, 5)                             # 32 * h5 + 32
+        np.testing.assert_allclose(lo_t, lo_n, rtol=1e-9, atol=1e-9)
+        return
+    getter, enc_t, enc_n = {"vgg": (vgg16.get_vgg_encoder, cnn.vgg_encoder_t, cnn.vgg_encoder_np),
+                            "mobilenet": (mobilenet.get_mobilenet_encoder, cnn.mobilenet_encoder_t, cnn.mobilenet_encoder_np),
+                            "resnet50": (resnet50.get_resnet50_encoder, cnn.resnet50_encoder_t, cnn.resnet50_encoder_np)}[name]
+    g, _ = getter(H, W)
+    wf = Model(g, "segmentation").init_weights(0).weights
+    wn = {k: v.astype(np.float64) for k, v in wf.items()}
+    lv_t = enc_t(xt, cnn._prep(wf, torch.float64))
+    lv_n = enc_n(x, wn)
+    assert len(lv_t) == len(lv_n) == 5
+    for i, (a, b) in enumerate(zip(lv_t, lv_n)):
+        a = a.permute(0, 2, 3, 1).numpy()
+        assert a.shape == b.shape, (i, a.shape, b.shape)
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(a).max()), err_msg="level %d" % (i + 1))
+
+
 def test_keras_semantics_spot_checks():
     import torch
     # fresh BatchNormalization is NOT the identity: y = x / sqrt(1 + 1e-3)
