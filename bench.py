@@ -294,7 +294,7 @@ def run_gpu(args, rank, world, local_rank):
     all_cpus = os.sched_getaffinity(0)
     bound_cpus = bind_to_gpu_numa_node(local_rank)
     B = args.batch
-    dtype = "bfloat16" if args.dtype == "bf16" else "float32"
+    dtype = {"bf16": "bfloat16", "fp32": "float32", "bf16x3": "bf16x3"}[args.dtype]
     model = landmark_regressor().init_weights(seed=0)
     pipe = prediction.LandmarkPipeline(model, dtype=dtype, device=dev)
 
@@ -492,7 +492,7 @@ def run_gpu(args, rank, world, local_rank):
                              "graph (TensorFlow not installable), numpy decode, fp64 Umeyama, cv2.warpAffine"}
         line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if dtype == "bfloat16" else "f32", "data": "synthetic",
+                "dtype": {"bfloat16": "bf16", "float32": "f32", "bf16x3": "bf16x3 (fp32-accurate split)"}[dtype], "data": "synthetic",
                 "config": {"workload": "configs[1]: batch-%d crops/GPU from %d 1080p frames, vanilla trunk@128 + FC-136 head, "
                                        "+ decode + 5-point align warp to 112x112" % (B, -(-B // FACES_PER_FRAME)),
                            "batch_per_gpu": B, "global_batch": int(total_faces), "parallelism": "faces sharded, no collective",
@@ -517,7 +517,7 @@ def main():
     ap.add_argument("--sets", type=int, default=6)
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--lanes", type=int, default=3, help="independent batches in flight (streams with their own workspace)")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -16,7 +16,7 @@ struct TensorInfo {
   int h = 0, w = 0, c = 0;
   int dtype = FLD_F32;
   size_t elems() const { return (size_t)h * w * c; }
-  size_t esz() const { return dtype == FLD_U8 ? 1 : dtype == FLD_BF16 ? 2 : 4; }
+  size_t esz() const { return dtype == FLD_U8 ? 1 : dtype == FLD_BF16 ? 2 : 4; }   // FLD_BF16X3 = SPLIT: 2 x bf16 per element
 };
 
 enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
@@ -30,6 +30,7 @@ struct LayerRt {
   ConvGeom g{};
   int path = PATH_SIMT;
   int cout_pad = 0;
+  bool x3 = false;              // FLD_BF16X3 tensor-core conv: SPLIT input, weights packed [w_hi | w_hi | w_lo]
   bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
   bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
   bool needs_weights = false, has_weights = false;
@@ -166,6 +167,36 @@ int infer_shapes(fld_net* net) {
       N2.skip = true;
     }
   }
+  // fp32-accurate tensor-core mode: SPLIT tensors between tensor-core convs, the fp32 kernels everywhere else
+  if (net->compute == FLD_BF16X3) {
+    std::vector<std::vector<int>> consumers(net->tensors.size());
+    for (int i = 0; i < nL; ++i) {
+      consumers[net->layers[i].d.in0].push_back(i);
+      if (net->layers[i].d.op == FLD_OP_ADD) consumers[net->layers[i].d.in1].push_back(i);
+    }
+    // out_split[i]: layer i (a conv) stores a SPLIT tensor — possible when every consumer is a tensor-core-capable conv or a
+    // dense layer.  geom_ok[i]: conv i can run on the tensor cores given a SPLIT input (a fused pool needs a SPLIT output).
+    // Consumers have larger indices, so decide back to front.
+    std::vector<char> out_split(nL, 0), geom_ok(nL, 0);
+    for (int i = nL - 1; i >= 0; --i) {
+      const LayerRt& L = net->layers[i];
+      if (L.d.op == FLD_OP_CONV && L.g.Cout % 8 == 0 && i + 1 != nL && !consumers[i + 1].empty() && !getenv("FLD_X3_OFF")) {
+        bool all = true;
+        for (int j : consumers[i + 1]) all = all && (geom_ok[j] || net->layers[j].d.op == FLD_OP_DENSE);
+        out_split[i] = all;
+      }
+      geom_ok[i] = L.d.op == FLD_OP_CONV && tc_conv_supported(L.g) && (out_split[i] || !L.g.pool);
+    }
+    for (int i = 0; i < nL; ++i) {
+      LayerRt& L = net->layers[i];
+      net->tensors[i + 1].dtype = out_split[i] ? FLD_BF16X3 : FLD_F32;
+      if (L.d.op == FLD_OP_CONV && geom_ok[i] && net->tensors[L.d.in0].dtype == FLD_BF16X3) {
+        L.path = PATH_TC_TMA;
+        L.x3 = true;
+        L.cout_pad = (int)align_up(L.g.Cout, L.g.Cout > 256 ? 128 : 16);
+      }
+    }
+  }
   return FLD_OK;
 }
 
@@ -205,7 +236,7 @@ extern "C" int fld_net_create(fld_handle* h, const fld_layer_desc* layers_h, int
   FLD_REQUIRE(layers_h && out && n_layers > 0, "fld_net_create: null/empty layer list");
   FLD_REQUIRE(in_h > 0 && in_w > 0 && in_c > 0, "fld_net_create: bad input shape");
   FLD_REQUIRE(in_dtype == FLD_U8 || in_dtype == FLD_F32, "fld_net_create: input dtype must be FLD_U8 or FLD_F32");
-  FLD_REQUIRE(compute == FLD_F32 || compute == FLD_BF16, "fld_net_create: compute must be FLD_F32 or FLD_BF16");
+  FLD_REQUIRE(compute == FLD_F32 || compute == FLD_BF16 || compute == FLD_BF16X3, "fld_net_create: compute must be FLD_F32, FLD_BF16 or FLD_BF16X3");
   fld_net* net = new fld_net();
   net->h = h;
   net->compute = compute;
@@ -339,6 +370,23 @@ extern "C" int fld_net_finalize(fld_net* net) {
       tc_conv_first_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data());
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (L.x3) {
+      // FLD_BF16X3: [tap][cout_pad][3 Cin] = [w_hi | w_hi | w_lo] against the activation chunks [x_hi | x_lo | x_hi]
+      const int taps = L.d.kh * L.d.kw, Cin = a.c, cp = L.cout_pad;
+      std::vector<uint16_t> pk((size_t)taps * cp * 3 * Cin, 0);
+      for (int t = 0; t < taps; ++t)
+        for (int c = 0; c < Cin; ++c)
+          for (int o = 0; o < Cout; ++o) {
+            const float w = L.w_host[((size_t)t * Cin + c) * Cout + o];
+            const uint16_t hb = f2bf(w);
+            const uint32_t hu = (uint32_t)hb << 16;
+            float hf;
+            memcpy(&hf, &hu, 4);
+            uint16_t* row = &pk[((size_t)t * cp + o) * 3 * Cin];
+            row[c] = hb; row[Cin + c] = hb; row[2 * Cin + c] = f2bf(w - hf);
+          }
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else {
       // [tap][cout_pad][Cin]  <-  w[(tap*Cin + c)][cout]
       const int taps = L.d.kh * L.d.kw, Cin = a.c, cp = L.cout_pad;
@@ -445,11 +493,11 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           rc = tc_conv_stem(net->h, pin, a.dtype, L.d_wbf, (__nv_bfloat16*)pout, L.g, B, st);
         } else if (L.path == PATH_TC_FIRST) {
           rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st);
-        } else if (L.path == PATH_TC_TMA && o.dtype == FLD_BF16 && tc_halo_supported(L.g, L.cout_pad)) {
+        } else if (L.path == PATH_TC_TMA && (o.dtype == FLD_BF16 || o.dtype == FLD_BF16X3) && tc_halo_supported(L.g, L.cout_pad)) {
           TcHaloPlan* plan = nullptr;
           for (auto& pe : L.hplans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }
           if (!plan) {
-            rc = tc_halo_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan);
+            rc = tc_halo_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan, L.x3 ? 1 : 0, o.dtype == FLD_BF16X3 ? 1 : 0);
             if (rc) return rc;
             if (L.hplans.size() >= 16 && net->retained == 0) { tc_halo_plan_destroy(L.hplans.front().plan); L.hplans.erase(L.hplans.begin()); }
             L.hplans.push_back({B, pin, plan});
@@ -459,12 +507,12 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           TcConvPlan* plan = nullptr;
           for (auto& pe : L.plans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }
           if (!plan) {
-            rc = tc_conv_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan);
+            rc = tc_conv_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan, L.x3 ? 1 : 0, o.dtype == FLD_BF16X3 ? 1 : 0);
             if (rc) return rc;
             if (L.plans.size() >= 16 && net->retained == 0) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
             L.plans.push_back({B, pin, plan});
           }
-          rc = tc_conv_run(plan, L.d_bias, pout, o.dtype, st);
+          rc = tc_conv_run(plan, L.d_bias, pout, o.dtype == FLD_BF16X3 ? FLD_BF16 : o.dtype, st);
         } else {
           rc = simt_conv(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, pout, o.dtype, L.g, B, st);
         }
@@ -503,7 +551,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
       }
       case FLD_OP_DENSE:
         rc = simt_dense(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, (float*)pout, dense_scratch, B, (int)a.elems(), o.c, d.act,
-                        st);
+                        st, a.c);
         break;
       case FLD_OP_SOFTMAX:
         if (L.skip) break;  // computed by the preceding transposed conv's epilogue

@@ -24,8 +24,9 @@ int simt_add_crop(const float* a, int AH, int AW, const float* b, int BH, int BW
                   cudaStream_t st);
 int simt_softmax(const float* in, float* out, long long n_px, int C, cudaStream_t st);
 size_t simt_dense_scratch_bytes(int B, int In, int Out);
+// in_dtype FLD_BF16X3: `in` is a SPLIT tensor ([hi | lo] bf16 per pixel of in_channels channels); In counts logical elements
 int simt_dense(const void* in, int in_dtype, const float* w /*[In][Out]*/, const float* bias, float* out, float* scratch /*split-K partials*/,
-               int B, int In, int Out, int act, cudaStream_t st);
+               int B, int In, int Out, int act, cudaStream_t st, int in_channels = 0);
 int simt_maxpool(const float* in, float* out, int B, int IH, int IW, int C, int OH, int OW, int k, int s, cudaStream_t st);
 int simt_cvt_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
 
@@ -46,8 +47,10 @@ int tc_conv_stem(const fld_handle* h, const void* in, int in_dtype, const __nv_b
                  int B, cudaStream_t st);
 // generic: stride 1, Cin % 64 == 0, bf16 NHWC in; weights bf16 [kh*kw][Cout_pad][Cin]; out bf16 or f32 NHWC
 bool tc_conv_supported(const ConvGeom& g);
+// x3: FLD_BF16X3 operands (activations [x_hi | x_lo] 2*Cin channels, weights [w_hi | w_hi | w_lo] 3*Cin); split_out: bf16 output
+// stored as a SPLIT tensor; ksplit > 1 (flat 1x1 convs, fp32 output): slice s writes its partial sums to out + s * npx * Cout
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcConvPlan** out);
+                        TcConvPlan** out, int x3 = 0, int split_out = 0, int ksplit = 1);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype, cudaStream_t st);
 
@@ -55,7 +58,7 @@ int tc_conv_run(const TcConvPlan* p, const float* bias, void* out, int out_dtype
 struct TcHaloPlan;
 bool tc_halo_supported(const ConvGeom& g, int cout_pad);
 int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcHaloPlan** out);
+                        TcHaloPlan** out, int x3 = 0, int split_out = 0);
 void tc_halo_plan_destroy(TcHaloPlan* p);
 int tc_halo_run(const TcHaloPlan* p, const float* bias, void* out, cudaStream_t st);
 

@@ -14,6 +14,16 @@ template <typename T> __device__ __forceinline__ float ld_f(const T* p);
 template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_f<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 template <> __device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+// SPLIT tensors (FLD_BF16X3 mode, see tc_common.cuh): per pixel [hi(C) | lo(C)] bf16.  As an output type of the SIMT conv it is
+// addressed in bf16 elements with pixel pitch 2 * Cout; st_split writes both halves.
+struct SplitBf16 { __nv_bfloat16 v; };
+__device__ __forceinline__ void st_split(__nv_bfloat16* p, int cout, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  p[0] = h;
+  p[cout] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+template <typename T> struct OutTraits { static constexpr bool split = false; typedef T elem; };
+template <> struct OutTraits<SplitBf16> { static constexpr bool split = true; typedef __nv_bfloat16 elem; };
 template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
 template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -34,7 +44,11 @@ constexpr int BM = 64, BN = 64, BK = 16, PT = 8;
 template <typename TIn, typename TOut, bool POOL>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ w /*[K][Cout]*/, const float* __restrict__ bias,
-                 TOut* __restrict__ out, ConvGeom g) {
+                 TOut* __restrict__ out_, ConvGeom g) {
+  typedef typename OutTraits<TOut>::elem TO;
+  constexpr bool SPLIT = OutTraits<TOut>::split;
+  TO* __restrict__ out = reinterpret_cast<TO*>(out_);
+  const int opitch = SPLIT ? 2 * g.Cout : g.Cout;   // elements per output pixel
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   __shared__ float Cs[POOL ? BM : 1][POOL ? BN + 1 : 1];
@@ -116,11 +130,14 @@ conv_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ w /*[K][C
       const int m = cty * 4 + i;
       const int oy = ty_ * PT + (m >> 3), ox = tx_ * PT + (m & 7);
       if (oy >= g.OH || ox >= g.OW) continue;
-      TOut* o = out + (((size_t)b * g.OH + oy) * g.OW + ox) * g.Cout;
+      TO* o = out + (((size_t)b * g.OH + oy) * g.OW + ox) * opitch;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = n0 + ctx * 4 + j;
-        if (n < g.Cout) st_f<TOut>(o + n, acc[i][j]);
+        if (n < g.Cout) {
+          if constexpr (SPLIT) st_split(o + n, g.Cout, acc[i][j]);
+          else st_f<TO>(o + n, acc[i][j]);
+        }
       }
     }
   } else {
@@ -137,7 +154,9 @@ conv_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ w /*[K][C
       if (oy >= PH || ox >= PW || n0 + n >= g.Cout) continue;
       const int m = (py * 2) * 8 + px * 2;
       const float v = fmaxf(fmaxf(Cs[m][n], Cs[m + 1][n]), fmaxf(Cs[m + 8][n], Cs[m + 9][n]));
-      st_f<TOut>(out + (((size_t)b * PH + oy) * PW + ox) * g.Cout + n0 + n, v);
+      TO* o = out + (((size_t)b * PH + oy) * PW + ox) * opitch + n0 + n;
+      if constexpr (SPLIT) st_split(o, g.Cout, v);
+      else st_f<TO>(o, v);
     }
   }
 }
@@ -224,7 +243,7 @@ __global__ void softmax_kernel(const float* __restrict__ in, float* __restrict__
 constexpr int DF = 8, DK = 128, DSLICE = 256;
 template <typename TIn>
 __global__ void __launch_bounds__(128)
-dense_partial_kernel(const TIn* __restrict__ in, const float* __restrict__ w, float* __restrict__ part, int B, int In, int Out) {
+dense_partial_kernel(const TIn* __restrict__ in, const float* __restrict__ w, float* __restrict__ part, int B, int In, int Out, int csplit) {
   __shared__ float xs[DF][DK];
   const int b0 = blockIdx.x * DF;
   const int j = blockIdx.y * 128 + threadIdx.x;
@@ -235,7 +254,17 @@ dense_partial_kernel(const TIn* __restrict__ in, const float* __restrict__ w, fl
   for (int k0 = kbeg; k0 < kend; k0 += DK) {
     for (int e = threadIdx.x; e < DF * DK; e += 128) {
       const int f = e / DK, k = e - f * DK;
-      xs[f][k] = (b0 + f < B && k0 + k < kend) ? ld_f<TIn>(in + (size_t)(b0 + f) * In + k0 + k) : 0.f;
+      float xv = 0.f;
+      if (b0 + f < B && k0 + k < kend) {
+        if (csplit) {   // SPLIT input: logical element kk = (pixel, c) lives at pixel * 2C + c (hi) and + C (lo)
+          const int kk = k0 + k, px = kk / csplit, c = kk - px * csplit;
+          const TIn* q = in + (size_t)(b0 + f) * In * 2 + (size_t)px * 2 * csplit + c;
+          xv = ld_f<TIn>(q) + ld_f<TIn>(q + csplit);
+        } else {
+          xv = ld_f<TIn>(in + (size_t)(b0 + f) * In + k0 + k);
+        }
+      }
+      xs[f][k] = xv;
     }
     __syncthreads();
     if (j < Out) {
@@ -325,6 +354,9 @@ int simt_conv(const void* in, int in_dtype, const float* w, const float* bias, v
     if (in_dtype == FLD_U8) return launch_conv_t<uint8_t, __nv_bfloat16>(in, w, bias, out, g, B, st);
     if (in_dtype == FLD_F32) return launch_conv_t<float, __nv_bfloat16>(in, w, bias, out, g, B, st);
     if (in_dtype == FLD_BF16) return launch_conv_t<__nv_bfloat16, __nv_bfloat16>(in, w, bias, out, g, B, st);
+  } else if (out_dtype == FLD_BF16X3) {   // SPLIT output feeding a FLD_BF16X3 tensor-core conv
+    if (in_dtype == FLD_U8) return launch_conv_t<uint8_t, SplitBf16>(in, w, bias, out, g, B, st);
+    if (in_dtype == FLD_F32) return launch_conv_t<float, SplitBf16>(in, w, bias, out, g, B, st);
   }
   fld_set_error("simt_conv: unsupported dtype combination %d -> %d", in_dtype, out_dtype);
   return FLD_ERR_INVALID;
@@ -373,12 +405,14 @@ int simt_softmax(const float* in, float* out, long long n_px, int C, cudaStream_
 size_t simt_dense_scratch_bytes(int B, int In, int Out) { return (size_t)fld_div_up(In, DSLICE) * B * Out * sizeof(float); }
 
 int simt_dense(const void* in, int in_dtype, const float* w, const float* bias, float* out, float* scratch, int B, int In, int Out,
-               int act, cudaStream_t st) {
+               int act, cudaStream_t st, int in_channels) {
   if (B == 0) return FLD_OK;
   const int KS = fld_div_up(In, DSLICE);
   dim3 grid(fld_div_up(B, DF), fld_div_up(Out, 128), KS);
-  if (in_dtype == FLD_F32) dense_partial_kernel<float><<<grid, 128, 0, st>>>((const float*)in, w, scratch, B, In, Out);
-  else if (in_dtype == FLD_BF16) dense_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, scratch, B, In, Out);
+  if (in_dtype == FLD_F32) dense_partial_kernel<float><<<grid, 128, 0, st>>>((const float*)in, w, scratch, B, In, Out, 0);
+  else if (in_dtype == FLD_BF16) dense_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, scratch, B, In, Out, 0);
+  else if (in_dtype == FLD_BF16X3 && in_channels > 0)   // SPLIT tensor: hi + lo summed on load
+    dense_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, scratch, B, In, Out, in_channels);
   else { fld_set_error("simt_dense: unsupported input dtype"); return FLD_ERR_INVALID; }
   FLD_LAUNCHED();
   dense_reduce_kernel<<<fld_div_up(B * Out, 256), 256, 0, st>>>(scratch, bias, out, B, Out, KS, act);

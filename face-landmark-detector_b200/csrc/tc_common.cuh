@@ -245,4 +245,84 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], const float*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FLD_BF16X3 mode: activations travel as SPLIT tensors — per pixel 2*C bf16 values [hi(C) | lo(C)] with
+// hi = bf16(v), lo = bf16(v - hi) — so that the next tensor-core conv can form x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+// (fp32 accumulation in TMEM; relative error ~2^-17 per product instead of bf16's 2^-9).
+// Epilogue for one 32-column chunk with a split store.  o.ptr points at channel (n0 + chunk*32) of the hi half of this
+// thread's (pooled) output pixel; the lo half lives `cout` elements further.  Pooling runs on the fp32 values (two rounds
+// of half-exchanges with the pool partners lane^1 / lane^TW: 16 + 8 shuffles), the activation after it (monotone).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_store8(__nv_bfloat16* hi_ptr, int cout, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const float r0 = v[2 * i] - __bfloat162float(h0), r1 = v[2 * i + 1] - __bfloat162float(h1);
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = pack_bf16(r0, r1);
+  }
+  *reinterpret_cast<uint4*>(hi_ptr) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(hi_ptr + cout) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool POOL, bool BIAS = true>
+__device__ __forceinline__ void epilogue_chunk_split(uint32_t (&acc)[32], const float* __restrict__ bias, int act, int lane, int TW,
+                                                     const EpiOut& o, int cout) {
+  float v[32];
+  if (BIAS) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(b4 + q);
+      v[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) + b.x;
+      v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b.y;
+      v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b.z;
+      v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.ptr);
+  if (POOL) {
+    const bool bx = lane & 1;
+    float k1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {    // x partner: this lane keeps channels [16*bx, 16*bx + 16)
+      const float send = bx ? v[i] : v[16 + i];
+      const float keep = bx ? v[16 + i] : v[i];
+      k1[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+    }
+    const bool by = (lane & TW) != 0;
+    float k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {     // y partner: keeps [8*by, 8*by + 8) of those
+      const float send = by ? k1[i] : k1[8 + i];
+      const float keep = by ? k1[8 + i] : k1[i];
+      k2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, TW));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k2[i] = act_f(k2[i], act);
+    const int cb = (bx ? 16 : 0) + (by ? 8 : 0);
+    if (o.valid && cb + 8 <= o.c_left) split_store8(p + cb, cout, k2);
+  } else {
+    if (!o.valid) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], act);
+    if (o.c_left >= 32 && o.vec_ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_store8(p + 8 * q, cout, v + 8 * q);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < o.c_left) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+          p[j] = h;
+          p[cout + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+        }
+    }
+  }
+}
+
 }  // namespace tc

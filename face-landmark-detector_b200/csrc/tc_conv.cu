@@ -49,6 +49,10 @@ struct TmaConvParams {
   int tiles_x, tiles_y, tiles_b, total_tiles;
   int stages;
   int act, pool;
+  int a_chunks;        // FLD_BF16X3: k-chunk kc reads activation chunk kc % a_chunks ([x_hi | x_lo] against [w_hi | w_hi | w_lo])
+  int split;           // bf16 output stored as a SPLIT tensor ([hi | lo], pixel pitch 2 * Cout)
+  int ksplit;          // split-K: tile = (k slice, N tile, M tile); slice s accumulates k-chunks [s*kchunks/ksplit, ...) into its own
+                       // fp32 partial output [ksplit][npx][Cout] (flat mode only; a fixed-order reduce kernel sums them)
   unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
   int dbg;             // FLD_TC_DBG bisect switches (results are garbage when set): 1 skip epilogue math/stores,
                        // 2 skip TMEM loads too, 4 skip the A-operand TMA, 8 skip the B-operand TMA, 16 skip the MMAs
@@ -108,6 +112,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
 
   const int kchunks = p.Cin >> 6;
+  const int kcs = kchunks / p.ksplit;      // k-chunks per slice
   const int mtiles = p.tiles_x * p.tiles_y * p.tiles_b;
 
   if (warp == 0) {
@@ -118,8 +123,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int it = blockIdx.x; it < p.n_iter; it += gridDim.x) {
       const int tile = p.sched ? __ldg(p.sched + it) : it;
       if (tile < 0) continue;
-      const int nt = tile / mtiles;             // N tile is the slow index: concurrent CTAs share the weight tile
-      int m = tile - nt * mtiles;
+      const int ks = tile / (mtiles * p.n_ntiles);   // k slice (0 unless split-K)
+      const int tile_mn = tile - ks * (mtiles * p.n_ntiles);
+      const int nt = tile_mn / mtiles;             // N tile is the slow index: concurrent CTAs share the weight tile
+      int m = tile_mn - nt * mtiles;
       const int tb = m / (p.tiles_x * p.tiles_y);
       m -= tb * (p.tiles_x * p.tiles_y);
       const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
@@ -127,10 +134,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int ky_lo, ky_hi, kx_lo, kx_hi;
       ky_range(p, ty, ky_lo, ky_hi);
       kx_range(p, tx, kx_lo, kx_hi);
+      const int kc_lo = ks * kcs, kc_hi = kc_lo + kcs;
       for (int ky = ky_lo; ky <= ky_hi; ++ky) {
         for (int kx = kx_lo; kx <= kx_hi; ++kx) {
           const int wrow = n0 + (ky * p.kw + kx) * p.cout_pad;  // row of the [taps*cout_pad][Cin] weight matrix
-          for (int kc = 0; kc < kchunks; ++kc) {
+          for (int kc = kc_lo; kc < kc_hi; ++kc) {
+            const int ka = kc >= p.a_chunks ? kc - p.a_chunks : kc;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             TRACE(0, ti, 1);
             {
@@ -141,8 +150,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               mbar_arrive_expect_tx(fb, bytes);
               TRACE(0, ti, 6);
               if (!(p.dbg & 4)) {
-                if (p.flat) tma_load_2d(sa, &tmA, fb, kc * 64, tb * 128);     // rows past npx are zero-filled
-                else tma_load_4d(sa, &tmA, fb, kc * 64, x0 + kx, y0 + ky, b0);
+                if (p.flat) tma_load_2d(sa, &tmA, fb, ka * 64, tb * 128);     // rows past npx are zero-filled
+                else tma_load_4d(sa, &tmA, fb, ka * 64, x0 + kx, y0 + ky, b0);
               }
               TRACE(0, ti, 7);
               if (!(p.dbg & 8)) tma_load_2d(sa + a_bytes, &tmB, fb, kc * 64, wrow);
@@ -173,13 +182,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       TRACE(1, ti, 0);
       int kblocks_t;
       {
-        const int m = tile % mtiles;
+        const int m = tile % mtiles;               // tile = (ks * n_ntiles + nt) * mtiles + m
         const int mm = m % (p.tiles_x * p.tiles_y);
         const int ty = mm / p.tiles_x, tx = mm - ty * p.tiles_x;
         int ky_lo, ky_hi, kx_lo, kx_hi;
         ky_range(p, ty, ky_lo, ky_hi);
         kx_range(p, tx, kx_lo, kx_hi);
-        kblocks_t = (ky_hi - ky_lo + 1) * (kx_hi - kx_lo + 1) * kchunks;
+        kblocks_t = (ky_hi - ky_lo + 1) * (kx_hi - kx_lo + 1) * kcs;
       }
       mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
       TRACE(1, ti, 3);
@@ -229,8 +238,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int it = blockIdx.x; it < p.n_iter; it += gridDim.x) {
       const int tile = p.sched ? __ldg(p.sched + it) : it;
       if (tile < 0) continue;
-      const int nt = tile / mtiles;
-      int m = tile - nt * mtiles;
+      const int ks = tile / (mtiles * p.n_ntiles);
+      const int tile_mn = tile - ks * (mtiles * p.n_ntiles);
+      const int nt = tile_mn / mtiles;
+      int m = tile_mn - nt * mtiles;
       const int tb = m / (p.tiles_x * p.tiles_y);
       m -= tb * (p.tiles_x * p.tiles_y);
       const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
@@ -259,7 +270,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (p.dbg & 1) { if ((regs[0] ^ regs[31]) == 0x7fc12345u) eo.valid = false; continue; }
         EpiOut e2 = eo;
         e2.c_left = p.Cout - n0 - ch;
-        if (OUT_F32) e2.ptr = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0 + ch;
+        if (!OUT_F32 && p.split) {
+          e2.ptr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (2 * p.Cout) + n0 + ch;
+          if (p.pool) epilogue_chunk_split<true>(regs, p.bias + n0 + ch, p.act, lane, p.TW, e2, p.Cout);
+          else epilogue_chunk_split<false>(regs, p.bias + n0 + ch, p.act, lane, p.TW, e2, p.Cout);
+          continue;
+        }
+        if (OUT_F32) e2.ptr = reinterpret_cast<float*>(p.out) + ((size_t)ks * p.npx + pix) * p.Cout + n0 + ch;
         else e2.ptr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0 + ch;
         if (p.pool) epilogue_chunk<true, false>(regs, p.bias + n0 + ch, p.act, lane, p.TW, e2);
         else epilogue_chunk<false, OUT_F32>(regs, p.bias + n0 + ch, p.act, lane, p.TW, e2);
@@ -299,14 +316,17 @@ bool tc_conv_supported(const ConvGeom& g) {
 }
 
 int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcConvPlan** out) {
+                        TcConvPlan** out, int x3, int split_out, int ksplit) {
   if (!h->encode_tiled) { fld_set_error("cuTensorMapEncodeTiled entry point not available"); return FLD_ERR_CUDA; }
   EncodeTiledFn enc = (EncodeTiledFn)h->encode_tiled;
   TcConvPlan* pl = new TcConvPlan();
   TmaConvParams& p = pl->p;
   p.bias = nullptr; p.out = nullptr;
+  // x3: the K dimension is [x_hi w_hi | x_lo w_hi | x_hi w_lo] = 3 Cin channels over a 2 Cin-channel activation tensor
+  const int Kc = x3 ? 3 * g.Cin : g.Cin, Ac = x3 ? 2 * g.Cin : g.Cin;
   p.B = B; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout;
-  p.Cin = g.Cin; p.kh = g.kh; p.kw = g.kw; p.pad_t = g.pad_t; p.pad_l = g.pad_l;
+  p.Cin = Kc; p.kh = g.kh; p.kw = g.kw; p.pad_t = g.pad_t; p.pad_l = g.pad_l;
+  p.a_chunks = Ac / 64; p.split = split_out; p.ksplit = 1;
   p.st = g.stride; p.IH = g.IH; p.IW = g.IW;
   p.act = g.act; p.pool = g.pool;
   { const char* e = getenv("FLD_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -331,7 +351,11 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   p.npx = (long long)B * g.OH * g.OW;
   p.tiles_x = fld_div_up(g.OW, TW); p.tiles_y = fld_div_up(g.OH, TH); p.tiles_b = fld_div_up(B, NB);
   if (p.flat) { p.tiles_x = 1; p.tiles_y = 1; p.tiles_b = (int)((p.npx + 127) / 128); }
-  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_ntiles;
+  if (ksplit > 1) {
+    if (!p.flat || (Kc / 64) % ksplit != 0) { delete pl; fld_set_error("tc_conv: split-K needs a flat 1x1 conv and ksplit | K/64"); return FLD_ERR_INVALID; }
+    p.ksplit = ksplit;
+  }
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.n_ntiles * p.ksplit;
   p.sched = nullptr;
   p.n_iter = p.total_tiles;
 
@@ -343,7 +367,7 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   pl->grid = std::min(p.total_tiles, h->sm_count);
   if (row_tiles && !p.flat && p.total_tiles > pl->grid && p.total_tiles <= (1 << 20)) {
     // tile cost = k-blocks that touch the map (same formulas as ky_range / kx_range) + a fixed epilogue / pipeline-fill share
-    const int mt = p.tiles_x * p.tiles_y * p.tiles_b, G = pl->grid, kch = g.Cin / 64;
+    const int mt = p.tiles_x * p.tiles_y * p.tiles_b, G = pl->grid, kch = Kc / 64;
     std::vector<std::pair<long long, int>> cost(p.total_tiles);
     for (int t = 0; t < p.total_tiles; ++t) {
       const int mm = (t % mt) % (p.tiles_x * p.tiles_y), ty = mm / p.tiles_x, tx = mm % p.tiles_x;
@@ -380,8 +404,8 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
 
   // activations: bf16 NHWC [B][IH][IW][Cin]
   if (p.flat) {
-    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)p.npx};
-    cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)Ac, (cuuint64_t)p.npx};
+    cuuint64_t strides[1] = {(cuuint64_t)Ac * 2};
     cuuint32_t box[2] = {64, 128};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(in), dims, strides, box, es,
@@ -389,8 +413,8 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(A, flat) failed: %d", (int)r); return FLD_ERR_CUDA; }
   } else {
-    cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.IW * g.Cin * 2, (cuuint64_t)g.IH * g.IW * g.Cin * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)Ac, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Ac * 2, (cuuint64_t)g.IW * Ac * 2, (cuuint64_t)g.IH * g.IW * Ac * 2};
     // boxDim counts TRAVERSED elements: with element stride s the box loads ceil(boxDim / s) pixels per spatial dimension
     const cuuint32_t s = (cuuint32_t)g.stride;
     cuuint32_t box[4] = {64, (cuuint32_t)TW * s, (cuuint32_t)TH * s, (cuuint32_t)NB};
@@ -402,8 +426,8 @@ int tc_conv_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   }
   // weights: bf16 [taps*cout_pad][Cin]
   {
-    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)g.kh * g.kw * cout_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)Kc, (cuuint64_t)g.kh * g.kw * cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)Kc * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w_packed), dims, strides, box, es,

@@ -28,6 +28,9 @@ struct HaloParams {
   int tiles_x, tiles_y, total_tiles;
   int SA, SB;          // halo ring depth, weight ring depth (SB = 0: stationary weights)
   int act, pool;
+  int a_chunks;        // distinct 64-channel chunks of the activation tensor; k-chunk kc reads activation chunk kc % a_chunks.
+                       // FLD_BF16X3: activations are [x_hi | x_lo] (a_chunks = 2 Cin/64), weights [w_hi | w_hi | w_lo] (3 Cin/64 chunks)
+  int split;           // store the output as a SPLIT tensor ([hi | lo] bf16, pixel pitch 2 * Cout)
   int baseoff;         // bring-up switch FLD_TC_HALO_BASEOFF=1: set descriptor base_offset = kx (WRONG on B200; default 0)
 };
 
@@ -88,9 +91,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m = tile - b * txy;
         const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
         const int slot = g & 1;
+        const int ka = kc >= p.a_chunks ? kc - p.a_chunks : kc;
         mbar_wait(emptyA0 + 8 * slot, ((g >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(fullA0 + 8 * slot, kHaloBytes);
-        tma_load_4d(smemA + slot * kHaloBytes, &tmA, fullA0 + 8 * slot, kc * 64, tx * 8 - 1, ty * 16 - 1, b);
+        tma_load_4d(smemA + slot * kHaloBytes, &tmA, fullA0 + 8 * slot, ka * 64, tx * 8 - 1, ty * 16 - 1, b);
       };
       if (stationary) {
         mbar_arrive_expect_tx(wfull0, 9u * kchunks * b_bytes);
@@ -197,6 +201,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         EpiOut e2 = eo;
         e2.c_left = p.Cout - ch;
+        if (p.split) {
+          e2.ptr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (2 * p.Cout) + ch;
+          if (p.pool) epilogue_chunk_split<true>(regs, p.bias + ch, p.act, lane, 8, e2, p.Cout);
+          else epilogue_chunk_split<false>(regs, p.bias + ch, p.act, lane, 8, e2, p.Cout);
+          continue;
+        }
         e2.ptr = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + ch;
         if (p.pool) epilogue_chunk<true, false>(regs, p.bias + ch, p.act, lane, 8, e2);
         else epilogue_chunk<false, false>(regs, p.bias + ch, p.act, lane, 8, e2);
@@ -234,13 +244,16 @@ bool tc_halo_supported(const ConvGeom& g, int cout_pad) {
 }
 
 int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16* w_packed, int cout_pad, const ConvGeom& g, int B,
-                        TcHaloPlan** out) {
+                        TcHaloPlan** out, int x3, int split_out) {
   if (!h->encode_tiled) { fld_set_error("cuTensorMapEncodeTiled entry point not available"); return FLD_ERR_CUDA; }
   EncodeTiledFn enc = (EncodeTiledFn)h->encode_tiled;
   TcHaloPlan* pl = new TcHaloPlan();
   HaloParams& p = pl->p;
   p.bias = nullptr; p.out = nullptr;
-  p.B = B; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout; p.Cin = g.Cin;
+  // x3: the K dimension is [x_hi w_hi | x_lo w_hi | x_hi w_lo] = 3 Cin channels over a 2 Cin-channel activation tensor
+  const int Kc = x3 ? 3 * g.Cin : g.Cin, Ac = x3 ? 2 * g.Cin : g.Cin;
+  p.B = B; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout; p.Cin = Kc;
+  p.a_chunks = Ac / 64; p.split = split_out;
   p.BN = cout_pad; p.cout_pad = cout_pad;
   p.tiles_x = fld_div_up(g.OW, 8); p.tiles_y = fld_div_up(g.OH, 16);
   p.total_tiles = p.tiles_x * p.tiles_y * B;
@@ -248,7 +261,7 @@ int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   { const char* e = getenv("FLD_TC_HALO_BASEOFF"); p.baseoff = e ? atoi(e) : 0; }
   const size_t b_bytes = (size_t)cout_pad * 128;
   const size_t budget = 226 * 1024;
-  const size_t w_all = 9 * (size_t)(g.Cin / 64) * b_bytes;
+  const size_t w_all = 9 * (size_t)(Kc / 64) * b_bytes;
   p.SA = 2;
   if (w_all + 2 * kHaloBytes + 1024 <= budget) {
     p.SB = 0;  // stationary weights
@@ -260,8 +273,8 @@ int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
   }
   pl->grid = std::min(p.total_tiles, h->sm_count);
   {
-    cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.IW * g.Cin * 2, (cuuint64_t)g.IH * g.IW * g.Cin * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)Ac, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Ac * 2, (cuuint64_t)g.IW * Ac * 2, (cuuint64_t)g.IH * g.IW * Ac * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es,
@@ -270,8 +283,8 @@ int tc_halo_plan_create(const fld_handle* h, const void* in, const __nv_bfloat16
     if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(halo A) failed: %d", (int)r); return FLD_ERR_CUDA; }
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)9 * cout_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)Kc, (cuuint64_t)9 * cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)Kc * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)cout_pad};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w_packed), dims, strides, box, es,

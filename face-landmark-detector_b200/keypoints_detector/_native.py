@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfld_sm100.so")
 
-FLD_U8, FLD_F32, FLD_BF16 = 0, 1, 2
+FLD_U8, FLD_F32, FLD_BF16, FLD_BF16X3 = 0, 1, 2, 3
 OP_CONV, OP_DECONV, OP_ADD, OP_DENSE, OP_SOFTMAX, OP_DWCONV, OP_MAXPOOL = range(7)
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 MAX_TOPN = 128

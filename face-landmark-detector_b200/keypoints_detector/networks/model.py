@@ -142,7 +142,9 @@ class Model:
             self.output_height = self.output_width = 1
             self.n_classes = oc
         self.in_dtype = in_dtype             # "uint8" | "float32"
-        self.compute_dtype = "float32"       # "float32" (parity mode) | "bfloat16" (tensor cores)
+        # "float32"  fp32 CUDA cores (the reference's arithmetic) | "bf16x3" fp32-accurate tensor cores (3-term bf16 split,
+        # same 0.05 px bar) | "bfloat16" plain bf16 tensor cores (0.5 px bar)
+        self.compute_dtype = "float32"
         self.weights = {}
         self._specs = weight_specs(graph)
         self._nets = {}                      # (device index, compute) -> (net handle, ...)
@@ -315,7 +317,9 @@ class Model:
             return N.FLD_F32
         if d in ("bfloat16", "bf16", torch.bfloat16):
             return N.FLD_BF16
-        raise ValueError("compute dtype must be float32 or bfloat16, got %r" % (d,))
+        if d in ("bf16x3", "bfloat16x3"):
+            return N.FLD_BF16X3
+        raise ValueError("compute dtype must be float32, bf16x3 or bfloat16, got %r" % (d,))
 
     def compiled(self, device=None, dtype=None):
         """fld_net for (device, dtype); built and weight-loaded on first use."""
@@ -463,6 +467,9 @@ class Model:
         off = lib.fld_net_tensor_offset(net, tensor, x.shape[0])
         B = x.shape[0]
         n = B * h * w * c
+        if dt == N.FLD_BF16X3:   # SPLIT tensor of the bf16x3 mode: per pixel [hi(c) | lo(c)] bf16, value = hi + lo
+            raw = ws[al + off: al + off + n * 4].view(torch.bfloat16).view(B, h, w, 2, c).float()
+            return raw[:, :, :, 0] + raw[:, :, :, 1]
         tdt = {N.FLD_F32: torch.float32, N.FLD_BF16: torch.bfloat16, N.FLD_U8: torch.uint8}[dt]
         esz = {N.FLD_F32: 4, N.FLD_BF16: 2, N.FLD_U8: 1}[dt]
         raw = ws[al + off: al + off + n * esz]

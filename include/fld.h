@@ -46,10 +46,16 @@ typedef enum {
   FLD_ERR_STATE = -5      /* call order (e.g. forward before finalize) */
 } fld_status;
 
-typedef enum { FLD_U8 = 0, FLD_F32 = 1, FLD_BF16 = 2 } fld_dtype;
+typedef enum { FLD_U8 = 0, FLD_F32 = 1, FLD_BF16 = 2, FLD_BF16X3 = 3 } fld_dtype;
 
-/* compute modes of a network: FLD_F32 = fp32 CUDA-core kernels (parity mode, <=0.05 px bar);
- * FLD_BF16 = tcgen05 tensor-core kernels, bf16 operands / fp32 accumulate (<=0.5 px bar). */
+/* compute modes of a network:
+ *   FLD_F32    fp32 CUDA-core kernels — the reference's arithmetic (TensorFlow fp32, prediction.py:84,208); <=0.05 px bar;
+ *   FLD_BF16   tcgen05 tensor-core kernels, bf16 operands / fp32 accumulate; <=0.5 px bar;
+ *   FLD_BF16X3 fp32-ACCURATE tensor-core mode: every conv operand is split into bf16 hi + lo parts and the product is formed as
+ *              x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation in TMEM (relative error ~2^-17 per product, 250x below
+ *              plain bf16); activations travel between tensor-core convs as SPLIT tensors [hi(C) | lo(C)] bf16 per pixel
+ *              (fld_net_tensor_shape reports them as FLD_BF16X3).  Layers the tensor-core kernels do not cover run the FLD_F32
+ *              kernels.  Meets the <=0.05 px bar; the drop-in package's default. */
 
 typedef struct fld_handle fld_handle;
 typedef struct fld_net fld_net;
@@ -116,7 +122,7 @@ typedef struct {
 } fld_layer_desc;
 
 FLD_API int fld_net_create(fld_handle* h, const fld_layer_desc* layers_h, int n_layers, int in_h, int in_w, int in_c,
-                   int in_dtype /* FLD_U8 | FLD_F32 */, int compute /* FLD_F32 | FLD_BF16 */, fld_net** out);
+                   int in_dtype /* FLD_U8 | FLD_F32 */, int compute /* FLD_F32 | FLD_BF16 | FLD_BF16X3 */, fld_net** out);
 FLD_API void fld_net_destroy(fld_net* net);
 /* Keras layouts, host fp32: Conv2D kernel [kh,kw,Cin,Cout]; Conv2DTranspose [kh,kw,Cout,Cin]; Dense
  * [In,Out]; depthwise [kh,kw,C,1]; bias [Cout] or NULL; bn = gamma|beta|moving_mean|moving_variance

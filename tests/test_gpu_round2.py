@@ -78,7 +78,7 @@ def test_c2_batch256_against_oracle(dev):
     ref = o_cnn.regression_forward(crops, m.weights, torch.float64)
     marks_ref = np.stack([o_dec.regression_decode(ref[i], fbs[i])[0] for i in range(B)])
     xt = T(crops, dev)
-    for dtype, tol_n, tol_px in (("float32", 1.25e-4, 0.05), ("bfloat16", 1.25e-3, 0.5)):
+    for dtype, tol_n, tol_px in (("float32", 1.25e-4, 0.05), ("bf16x3", 1.25e-4, 0.05), ("bfloat16", 1.25e-3, 0.5)):
         out = m.forward_device(xt, dtype).cpu().numpy()
         err = np.abs(out - ref).max()
         assert out.shape == (B, 136) and err < tol_n, (dtype, err)
@@ -103,7 +103,7 @@ def test_c3_224_against_oracle(dev):
     soft_ref = _soft_centroids(pr)
     top_ref, margin = _topn_centroids(pr, 4)
     xt = T(x, dev)
-    for dtype, rate, tol in (("float32", 0.999, 0.05), ("bfloat16", 0.97, 0.5)):
+    for dtype, rate, tol in (("float32", 0.999, 0.05), ("bf16x3", 0.999, 0.05), ("bfloat16", 0.97, 0.5)):
         cm = m.forward_classmap_device(xt, dtype).cpu().numpy()
         assert cm.shape == (2, 232, 232) and (cm == cm_ref).mean() > rate, (dtype, (cm == cm_ref).mean())
         soft = m.forward_landmarks_device(xt, dtype, n_points=0).cpu().numpy().reshape(2, 68, 2)
@@ -111,9 +111,10 @@ def test_c3_224_against_oracle(dev):
         top = m.forward_landmarks_device(xt, dtype, n_points=4).cpu().numpy().reshape(2, 68, 2)
         # the top-4 SET is a discrete choice: where the 4th and 5th largest probabilities are closer than the mode's own
         # relative precision the choice is not defined by the arithmetic, so those channels are compared only when clear
-        clear = margin > (1e-4 if dtype == "float32" else 2e-2)
+        # (random-init weights saturate the softmax: most channels have several pixels at probability ~1, i.e. a top-4 tie)
+        clear = margin > (2e-2 if dtype == "bfloat16" else 1e-4)
         d = np.abs(top - top_ref).max(-1)
-        assert clear.mean() > 0.3, clear.mean()
+        assert clear.mean() > 0.1, clear.mean()
         assert d[clear].max() <= tol, (dtype, d[clear].max(), clear.mean())
 
 
@@ -137,7 +138,7 @@ def test_decoded_landmarks_every_encoder_bf16(dev, name, H, W):
     pr = o_cnn.segmentation_probs_t(logits).numpy().reshape(2, oh, ow, 68)
     soft_ref = _soft_centroids(pr)
     xt = T(x, dev)
-    for dtype, tol in (("float32", 0.05), ("bfloat16", 0.5)):
+    for dtype, tol in (("float32", 0.05), ("bf16x3", 0.05), ("bfloat16", 0.5)):
         soft = m.forward_landmarks_device(xt, dtype, n_points=0).cpu().numpy().reshape(2, 68, 2)
         assert np.abs(soft - soft_ref).max() <= tol, (name, dtype, np.abs(soft - soft_ref).max())
 
@@ -341,3 +342,29 @@ def test_video_predict_with_fake_capture(dev, monkeypatch):
             ref = prediction.detect_marks(frames[fi], m, r)
             assert drawn[k].shape == (68, 2) and np.array_equal(drawn[k].astype(np.uint64), ref.astype(np.uint64))
             k += 1
+
+
+# ------------------------------------------------------------------------------------------------ fp32-accurate tensor-core mode
+@pytest.mark.parametrize("B", [1, 5, 33])
+def test_regression_net_bf16x3(dev, B):
+    """FLD_BF16X3 (3-term bf16 split on the tensor cores, fp32 accumulation): the same bars as the fp32 CUDA-core mode —
+    1.25e-4 on the normalised output (0.05 px on a 400 px box) and 2e-5 relative at every trunk level — and the layers really
+    run as SPLIT tensors through the tcgen05 kernels."""
+    from keypoints_detector import _native as N
+    from keypoints_detector.networks.regression import landmark_regressor
+    from oracle import cnn as o_cnn
+    m = landmark_regressor().init_weights(3)
+    rng = np.random.default_rng(2)
+    x = np.stack([gi.image(200 + i, 128, 128) for i in range(min(B, 8))])[np.arange(B) % min(B, 8)].copy()
+    x ^= rng.integers(0, 32, x.shape, dtype=np.uint8)
+    ref = o_cnn.regression_forward(x, m.weights, torch.float64)
+    xt = T(x, dev)
+    out = m.forward_device(xt, "bf16x3").cpu().numpy()
+    assert np.abs(out - ref).max() < 1.25e-4, np.abs(out - ref).max()
+    levels = o_cnn.trunk_forward(x.astype(np.float64), m.weights, torch.float64, scale=1 / 255.0)
+    for t in range(1, 6):
+        (_, dt) = m.tensor_info(t, dev, "bf16x3")
+        assert dt == N.FLD_BF16X3, (t, dt)                                   # SPLIT tensors between the convs
+        got = m.intermediate(xt, t, "bf16x3").cpu().numpy()
+        scale = np.abs(levels[t - 1]).max()
+        assert np.abs(got - levels[t - 1]).max() < 2e-5 * scale, (t, np.abs(got - levels[t - 1]).max() / scale)
