@@ -113,7 +113,8 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.0005):
+        self.period, self.power = period, []
         self.rows, self.proc, self.index = [], None, index
         self.nv, self.h, self.samples, self.run, self.thread = None, None, [], False, None
         try:
@@ -138,6 +139,10 @@ class ClockSampler:
         except Exception:
             mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
         self.samples.append((mhz, mask))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
 
     def _poll(self):
         while self.run:
@@ -145,7 +150,7 @@ class ClockSampler:
                 self._sample()
             except Exception:
                 break
-            time.sleep(0.0005)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv is not None:
@@ -179,6 +184,8 @@ class ClockSampler:
             for _, m in self.samples:
                 mask |= m
             return {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": self.max_mhz,
+                    "sm_mhz_min": float(min(c for c, _ in self.samples)), "power_w_max": max(self.power) if self.power else None,
+                    "power_w_median": float(np.median(self.power)) if self.power else None,
                     "reasons": sorted(n for bit, n in self.REASONS if mask & bit), "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return None
@@ -280,21 +287,143 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _cuda_time(fn, reps, dev, inner=1):
+    """median / min ms of fn() (enqueue only) over `reps` CUDA-event brackets on the current stream"""
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ts.append(e0.elapsed_time(e1) / inner)
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def sub_c4(dev, peaks):
+    """config C4: 4096 faces from 64 synthetic 1080p frames, 5-point fit + warp to 112x112 (align-only), HBM roofline."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    F, B = 64, 4096
+    g = torch.Generator(device="cpu").manual_seed(7)
+    frames = torch.randint(0, 256, (F, FRAME_H, FRAME_W, 3), dtype=torch.uint8, generator=g).to(dev)   # 398 MB > L2
+    pts, Ms = synthetic.make_similarity_landmarks(B, FRAME_H, FRAME_W, prediction.TEMPLATE_112, seed=4)
+    f2f = torch.from_numpy((np.arange(B) // 64).astype(np.int32)).to(dev)
+    marks = torch.from_numpy(pts).to(dev)
+    out = torch.empty((B, 112, 112, 3), dtype=torch.uint8, device=dev)
+    M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
+    fn = lambda: prediction.align_device(frames, f2f, marks, None, (112, 112), five_point=False, out=out, out_matrix=M)
+    for _ in range(3):
+        fn()
+    med, mn = _cuda_time(fn, 20, dev, inner=4)
+    s2 = np.array([np.linalg.det(m[:, :2]) for m in Ms])                     # scale^2 per face
+    alg = B * 37632 + float((112 * 112 * 3 / s2).sum()) + B * (5 * 2 * 4 + 48)  # crop write + unique source footprint + marks + M
+    hbm = peaks.get("hbm_gbs", 6551.7)
+    return {"workload": "configs[3]: 4096 faces, 64 x 1080p frames -> 112x112x3, fit + warp", "kernel": "align_tile_kernel",
+            "ms_median": med, "ms_min": mn, "faces_per_s": B / med * 1e3, "algorithmic_bytes": alg, "bytes_per_face": alg / B,
+            "achieved_GBs": alg / med / 1e6, "peak_GBs": hbm, "frac_of_hbm": alg / med / 1e6 / hbm, "bound": "hbm",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+
+
+def sub_c3(dev, peaks, batch=1024):
+    """config C3: fcn_8 over the vanilla encoder @224x224, 68 classes, batch 1024, soft-argmax fused into the last transposed
+    conv's epilogue (bf16 tensor cores): images/s, TFLOP/s on the valid-tap FLOP count of SURVEY §8d, share of up8."""
+    from keypoints_detector.networks.fcn import fcn_8
+    m = fcn_8(68, input_height=224, input_width=224).init_weights(0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn((64, 224, 224, 3), generator=g) * 50).to(dev).repeat(batch // 64, 1, 1, 1).contiguous()
+    x += torch.arange(batch, device=dev, dtype=torch.float32).view(-1, 1, 1, 1) * 0.01        # no two images alike
+    fn = lambda: m.forward_landmarks_device(x, "bfloat16", n_points=0)
+    for _ in range(2):
+        fn()
+    med, mn = _cuda_time(fn, 5, dev)
+    m.set_profiling(True, dev, "bfloat16")
+    fn()
+    lt = dict(m.layer_times(dev, "bfloat16"))
+    m.set_profiling(False, dev, "bfloat16")
+    gflop = 11.37                                                              # per image, valid taps (SURVEY §8d)
+    tf = gflop * 1e9 * batch / (med * 1e-3) / 1e12
+    burst, sust = peaks.get("bf16_tflops", 1642.1), peaks.get("bf16_tflops_sustained", 1351.1)
+    top = sorted(lt.items(), key=lambda kv: -kv[1])[:6]
+    rec = {"workload": "configs[2]: fcn_8/vanilla @224x224x3, 68 classes, batch %d, fused soft-argmax decode" % batch, "dtype": "bf16",
+           "ms_per_batch": med, "ms_min": mn, "images_per_s": batch / med * 1e3, "gflop_per_image_valid_taps": gflop,
+           "achieved_TFLOPs": tf, "frac_burst": tf / burst, "frac_sustained": tf / sust,
+           "up8_ms": lt.get("up8"), "up8_share": (lt.get("up8", 0.0) / sum(lt.values())) if lt else None,
+           "layer_ms_top": {k: round(v, 4) for k, v in top}}
+    del x
+    m._release()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def sub_mode(dev, model, dev_set, dtype, steps, batch):
+    """config C2 in another compute mode (fp32 CUDA cores / fp32-accurate bf16x3 tensor cores), device-resident, one lane."""
+    from keypoints_detector import prediction
+    pipe = prediction.LandmarkPipeline(model, dtype=dtype, device=dev)
+    cap = pipe.capture(*dev_set, lane=7)
+    for _ in range(2):
+        cap.replay()
+    med, mn = _cuda_time(cap.replay, steps, dev)
+    cap.close()
+    return {"workload": "configs[1], %s mode, device-resident, 1 lane" % dtype, "dtype": dtype, "ms_per_step": med,
+            "faces_per_s": batch / med * 1e3, "TFLOPs_valid_taps": sum(flops_per_face()[0]) * batch / (med * 1e-3) / 1e12}
+
+
+def sub_strong(model, dtype, n_gpus, total_faces=65536, frames_n=128):
+    """config C5, strong scaling through the product's multi-GPU API: ONE batch of 65 536 faces (128 distinct 1080p frames) in
+    pinned host memory, sharded by frame over the GPUs by MultiGpuPipeline (thread per GPU, no collective), results gathered
+    into one pinned host buffer.  Wall-clock per call (host threads included)."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    g = torch.Generator(device="cpu").manual_seed(77)
+    frames = torch.randint(0, 256, (frames_n, FRAME_H, FRAME_W, 3), dtype=torch.uint8, generator=g).pin_memory()
+    boxes = torch.from_numpy(synthetic.make_boxes(total_faces, FRAME_H, FRAME_W, seed=78, min_side=96, max_side=400)).pin_memory()
+    f2f = (torch.arange(total_faces, dtype=torch.int32) // (total_faces // frames_n)).to(torch.int32).pin_memory()
+    mg = prediction.MultiGpuPipeline(model, devices=list(range(n_gpus)), dtype=dtype)
+    mg.run(frames, boxes, f2f)                                                # warm-up: plans, buffers, pinned gather buffers
+    walls, devms = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = mg.run(frames, boxes, f2f)
+        walls.append(time.perf_counter() - t0)
+        devms.append(max(mg.last_device_ms))
+    import hashlib
+    digest = hashlib.sha256(r["marks"].tobytes() + r["aligned"].tobytes()).hexdigest()
+    mg.close()
+    w = float(np.median(walls))
+    return {"workload": "configs[4]: one batch of %d faces from %d 1080p frames in pinned host memory, sharded by frame over %d GPU(s), "
+                        "host-side gather" % (total_faces, frames_n, n_gpus), "scaling": "strong", "n_gpus": n_gpus,
+            "faces_per_s": total_faces / w, "wall_ms": w * 1e3, "max_device_ms": float(np.median(devms)),
+            "h2d_bytes": int(frames.numel() + boxes.numel() * 4 + f2f.numel() * 4), "d2h_bytes": int(total_faces * (112 * 112 * 3 + 68 * 2 * 4 + 48 + 16)),
+            "result_sha256": digest[:16]}
+
+
 def run_gpu(args, rank, world, local_rank):
     from keypoints_detector import _native, prediction
     from keypoints_detector.networks.regression import landmark_regressor
     import __graft_entry__ as entry
+    import torch.distributed as dist
     if local_rank == 0:
         entry.build()
+    cpu_group = None
     if world > 1:
-        import torch.distributed as dist
         dist.barrier()
+        cpu_group = dist.new_group(backend="gloo")     # CPU-side waits: an NCCL barrier would spin a kernel on every waiting GPU
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     all_cpus = os.sched_getaffinity(0)
     bound_cpus = bind_to_gpu_numa_node(local_rank)
     B = args.batch
     dtype = {"bf16": "bfloat16", "fp32": "float32", "bf16x3": "bf16x3"}[args.dtype]
+    peaks = _peaks()
     model = landmark_regressor().init_weights(seed=0)
     pipe = prediction.LandmarkPipeline(model, dtype=dtype, device=dev)
 
@@ -306,20 +435,19 @@ def run_gpu(args, rank, world, local_rank):
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn, steps, streams):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cur = torch.cuda.current_stream(dev)
         e0.record(cur)
-        for st in lane_streams:
+        for st in streams:
             st.wait_event(e0)
         for k in range(steps):
             fn(k)
-        for st in lane_streams:
+        for st in streams:
             cur.wait_stream(st)
         e1.record(cur)
         barrier()
@@ -343,9 +471,8 @@ def run_gpu(args, rank, world, local_rank):
         try:
             for sidx in range(n_sets):
                 l_before = _native.launch_count()
-                g, _ = pipe.capture(*dev_sets[sidx], lane=sidx % n_lanes)
+                graphs.append(pipe.capture(*dev_sets[sidx], lane=sidx % n_lanes))
                 launches_per_step = (_native.launch_count() - l_before) // 2  # capture() = one warm-up run + the recorded run
-                graphs.append(g)
         except Exception as e:                                # keep measuring: every kernel is then enqueued from Python
             print("bench: CUDA graph capture failed (%s); running eagerly" % e, file=sys.stderr)
             use_graph = False
@@ -365,7 +492,7 @@ def run_gpu(args, rank, world, local_rank):
     if sampler:
         sampler.start()
     l0 = _native.launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, args.steps, lane_streams)
     launches = (_native.launch_count() - l0) if not use_graph else launches_per_step * args.steps
     clocks = sampler.stop() if sampler else None
     total_faces = sum_over_ranks(B, dev)
@@ -376,115 +503,176 @@ def run_gpu(args, rank, world, local_rank):
     model_profiling[0] = True
     per_layer = np.zeros(len(model.graph.layers))
     barrier()
-    for k in range(args.steps):
+    n_prof = min(args.steps, 50)
+    for k in range(n_prof):
         step_resident(k)
         per_layer += np.array([t for _, t in model.layer_times(dev, dtype)])
     model.set_profiling(False, dev, dtype)
     model_profiling[0] = False
-    per_layer /= args.steps
+    per_layer /= n_prof
     conv_flops, fc_flops = flops_per_face()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    if dtype == "bfloat16":
-        # dominant kernel: conv_tma_kernel (conv2..conv5, four launches per step)
-        t_dom = float(per_layer[1:5].sum()) * 1e-3
-        fl = sum(conv_flops[1:5]) * B
-        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    burst, sust = peaks.get("bf16_tflops", 1642.1), peaks.get("bf16_tflops_sustained", 1351.1)
+    # which regime the timed region ran in: seconds at full power end up at the sustained clocks, a short burst does not
+    regime = "sustained" if ms >= 2000.0 else "burst"
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+
+    def tensor_roof(kernel, fl, t_s, extra=None):
+        ach = fl / t_s / 1e12
+        r = {"kernel": kernel, "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
+             "peak": burst if regime == "burst" else sust, "peak_regime": regime,
+             "peak_source": "%s bf16_tflops%s (timed region %.0f ms: %s regime)" % (src, "" if regime == "burst" else "_sustained", ms, regime),
+             "frac": ach / (burst if regime == "burst" else sust), "frac_burst": ach / burst, "frac_sustained": ach / sust,
+             "frac_nominal_2250": ach / 2250.0, "flops_per_launch_set": fl, "ms_per_launch_set": t_s * 1e3}
+        if extra:
+            r.update(extra)
+        return r
+
+    if dtype in ("bfloat16", "bf16x3"):
         traffic, traffic_src = ncu_traffic_bytes()
-        roof = {"kernel": "tcgen05 conv trunk: conv_halo_kernel x3 (conv2..conv4) + conv_tma_kernel (conv5), 4 launches/step",
-                "bound": "tensor", "achieved": fl / t_dom / 1e12,
-                "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (sustained, B200_PROFILING.md)",
-                "unit": "TFLOP/s", "traffic": traffic, "traffic_source": traffic_src, "traffic_note": "DRAM bytes per launch set at batch 256",
-                "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3}
+        roof = tensor_roof("tcgen05 conv trunk: conv_halo_kernel x3 (conv2..conv4) + conv_tma_kernel (conv5), 4 launches/step",
+                           sum(conv_flops[1:5]) * B, float(per_layer[1:5].sum()) * 1e-3,
+                           {"traffic": traffic, "traffic_source": traffic_src, "traffic_note": "DRAM bytes per launch set at batch 256"})
+        roof_cnn = tensor_roof("whole CNN: conv1 (conv_first_kernel) + conv2..conv5 + FC, 6-7 launches/step",
+                               (sum(conv_flops) + fc_flops) * B, float(per_layer.sum()) * 1e-3)
     else:
+        peak = 75.0  # fp32 FMA nominal: 148 SMs x 128 lanes x 2 x ~1.97 GHz
         t_dom = float(per_layer[0:5].sum()) * 1e-3
         fl = sum(conv_flops) * B
-        peak = 75.0  # fp32 FMA nominal: 148 SMs x 128 lanes x 2 x ~1.97 GHz
         roof = {"kernel": "conv_simt_kernel (conv1..conv5, fp32 CUDA cores)", "bound": "fp32-fma", "achieved": fl / t_dom / 1e12, "peak": peak,
                 "peak_source": "nominal fp32 FMA (no measured fp32 peak in MEASURED_PEAKS.json)", "unit": "TFLOP/s", "traffic": None,
-                "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3}
-    roof["frac"] = roof["achieved"] / roof["peak"]
+                "flops_per_launch_set": fl, "ms_per_launch_set": t_dom * 1e3, "frac": fl / t_dom / 1e12 / peak}
+        roof_cnn = None
     roof["layer_ms"] = {L["name"]: round(float(t), 5) for L, t in zip(model.graph.layers, per_layer)}
 
-    # ---- end to end through the public API objects with HOST (pinned) buffers: H2D + compute + D2H every step
+    # ---- end to end through the package's host-buffer API (prediction.HostStream): H2D + compute + D2H every step
     pin_sets = [tuple(t.pin_memory() for t in hs) for hs in host_sets]
     n_slots = max(2, n_lanes)   # in-flight steps: H2D of step k+2 never waits for the compute of step k when there are 3
-    marks_h = [torch.empty((B, 68, 2), dtype=torch.float32).pin_memory() for _ in range(n_slots)]
-    crops_h = [torch.empty((B, 112, 112, 3), dtype=torch.uint8).pin_memory() for _ in range(n_slots)]
-    slots = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(n_slots)]
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    ev_in = [torch.cuda.Event() for _ in range(n_slots)]
-    ev_comp = [torch.cuda.Event() for _ in range(n_slots)]
-    ev_out = [torch.cuda.Event() for _ in range(n_slots)]
-    main = torch.cuda.current_stream(dev)
-
-    e2e_graphs, e2e_results = [], []
-    use_graph_e2e = use_graph
-    if use_graph_e2e:
-        try:
-            for sl in range(n_slots):
-                g, res = pipe.capture(*slots[sl], lane=sl)
-                e2e_graphs.append(g); e2e_results.append(res)
-        except Exception as e:
-            print("bench: CUDA graph capture failed in the e2e leg (%s); running eagerly" % e, file=sys.stderr)
-            use_graph_e2e = False
-            torch.cuda.synchronize(dev)
+    hs = prediction.HostStream(pipe, B, host_sets[0][0].shape[0], (FRAME_H, FRAME_W), n_slots=n_slots, use_graph=use_graph)
 
     def step_e2e(k):
-        sl = k % n_slots
-        comp = lane_streams[sl % n_lanes]                     # compute stream of this slot (slot = lane: own workspace + results)
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_comp[sl])                      # slot's previous compute finished
-            for d, h in zip(slots[sl], pin_sets[k % n_sets]):
-                d.copy_(h, non_blocking=True)
-            ev_in[sl].record(s_in)
-        with torch.cuda.stream(comp):
-            comp.wait_event(ev_in[sl])
-            comp.wait_event(ev_out[sl])                       # the lane's result buffers have been read out
-            if use_graph_e2e:
-                e2e_graphs[sl].replay()
-                r = e2e_results[sl]
-            else:
-                r = pipe.run_device(*slots[sl], lane=sl)
-            ev_comp[sl].record(comp)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_comp[sl])
-            s_out.wait_event(ev_out[sl])                      # pinned slot's previous D2H finished
-            marks_h[sl].copy_(r["marks"], non_blocking=True)
-            crops_h[sl].copy_(r["aligned"], non_blocking=True)
-            ev_out[sl].record(s_out)
+        hs.submit(*pin_sets[k % n_sets])
 
-    def e2e_all(steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(main)
-        for st in lane_streams + [s_in, s_out]:
-            st.wait_event(e0)
-        for k in range(steps):
-            step_e2e(k)
-        for st in lane_streams + [s_in, s_out]:
-            main.wait_stream(st)
-        e1.record(main)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1), dev)
-
-    e2e_all(max(args.warmup, 2))
-    ms_e2e = e2e_all(args.steps)
+    timed(step_e2e, max(args.warmup, 2), hs.streams())
+    ms_e2e = timed(step_e2e, args.steps, hs.streams())
     e2e_val = total_faces * args.steps / (ms_e2e * 1e-3)
-    d2h = marks_h[0].numel() * 4 + crops_h[0].numel()
-    # the host link this box gave us: the same pinned H2D copies alone (the e2e leg cannot be faster than this)
-    def copy_only(k):
-        for d, h in zip(slots[k % n_slots], pin_sets[k % n_sets]):
-            d.copy_(h, non_blocking=True)
-    ms_link = timed(copy_only, max(args.steps, 5)) / max(args.steps, 5)
-    link_gbps = set_bytes / (ms_link * 1e-3) / 1e9
+    last = hs.result(hs.n_submitted - 1)
+    e2e_check = bool(np.isfinite(last["marks"]).all() and last["aligned"].any())
+    d2h = hs.d2h_bytes
+
+    # ---- what the host link of this box allows: the same pinned copies alone, each direction and both at once
+    cur = torch.cuda.current_stream(dev)
+    s_a, s_b = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    n_link = max(args.steps, 10)
+
+    def h2d(k):
+        with torch.cuda.stream(s_a):
+            for d, h in zip(hs.d_in[k % n_slots], pin_sets[k % n_sets]):
+                d.copy_(h, non_blocking=True)
+
+    res0 = hs.caps[0].results if hs.caps else pipe.run_device(*hs.d_in[0], lane=0)
+
+    def d2h_fn(k):
+        with torch.cuda.stream(s_b):
+            hs.h_out[k % n_slots]["marks"].copy_(res0["marks"], non_blocking=True)
+            hs.h_out[k % n_slots]["aligned"].copy_(res0["aligned"], non_blocking=True)
+
+    ms_h2d = timed(h2d, n_link, [s_a]) / n_link
+    ms_d2h = timed(d2h_fn, n_link, [s_b]) / n_link
+    ms_dup = timed(lambda k: (h2d(k), d2h_fn(k)), n_link, [s_a, s_b]) / n_link
+    link = {"h2d_GBps": set_bytes / ms_h2d / 1e6, "d2h_GBps": d2h / ms_d2h / 1e6,
+            "duplex_ms_per_step": ms_dup, "duplex_h2d_GBps": set_bytes / ms_dup / 1e6, "duplex_d2h_GBps": d2h / ms_dup / 1e6,
+            "h2d_GBps_all_ranks": sum_over_ranks(set_bytes / ms_h2d / 1e6, dev), "d2h_GBps_all_ranks": sum_over_ranks(d2h / ms_d2h / 1e6, dev),
+            "bytes_per_face_h2d": set_bytes / B, "bytes_per_face_d2h": d2h / B,
+            "link_bound_faces_per_s": total_faces / (ms_dup * 1e-3),
+            "note": "copy-only passes over the same pinned buffers (max over ranks); link_bound_faces_per_s = faces per step / duplex copy time: "
+                    "the e2e leg cannot exceed it on this box whatever the kernels do"}
+    try:    # write-combined pinned source for the H2D direction (cudaHostAllocWriteCombined = 4)
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        ptr = ctypes.c_void_p()
+        nbytes = host_sets[0][0].numel()
+        if rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(4)) == 0:
+            wc = torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr.value)))
+            wc.copy_(host_sets[0][0].reshape(-1))
+            dst = hs.d_in[0][0].view(-1)
+
+            def h2d_wc(k):
+                with torch.cuda.stream(s_a):
+                    dst.copy_(wc, non_blocking=True)
+            link["h2d_write_combined_GBps"] = nbytes / (timed(h2d_wc, n_link, [s_a]) / n_link) / 1e6
+            torch.cuda.synchronize(dev)
+            rt.cudaFreeHost(ptr)
+    except Exception as e:
+        link["h2d_write_combined_GBps"] = None
+
+    # ---- bit identity across GPUs: every rank runs the SAME seeded batch; the digests of landmarks + aligned crops must agree
+    import hashlib
+    fx = tuple(t.to(dev) for t in make_set(B, 4242))
+    rfix = pipe.run_device(*fx, lane=0)
+    torch.cuda.synchronize(dev)
+    digest = hashlib.sha256(rfix["marks"].cpu().numpy().tobytes() + rfix["aligned"].cpu().numpy().tobytes() + rfix["M"].cpu().numpy().tobytes()).hexdigest()
+    if world > 1:
+        digests = [None] * world
+        dist.all_gather_object(digests, digest, group=cpu_group)
+    else:    # one GPU: a second lane on another stream must reproduce it
+        with torch.cuda.stream(lane_streams[-1]):
+            r2 = pipe.run_device(*fx, lane=n_lanes - 1 if n_lanes > 1 else 5)
+        torch.cuda.synchronize(dev)
+        digests = [digest, hashlib.sha256(r2["marks"].cpu().numpy().tobytes() + r2["aligned"].cpu().numpy().tobytes() + r2["M"].cpu().numpy().tobytes()).hexdigest()]
+    bit_identical = len(set(digests)) == 1
+
+    # ---- sub-records: other configs / modes the driver should see in the same line (rank 0; the other ranks wait on the CPU)
+    subs = {}
+    if rank == 0 and not args.no_sub:
+        wanted = [w for w in args.sub.split(",") if w]
+
+        def guarded(name, fn):
+            if name not in wanted:
+                return
+            t0 = time.perf_counter()
+            try:
+                subs[name] = fn()
+            except Exception as e:   # a failing side measurement must not lose the contract line
+                subs[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.synchronize(dev)
+            subs[name]["bench_seconds"] = round(time.perf_counter() - t0, 2)
+
+        def sustained():
+            n = int(2300.0 / (ms / args.steps)) + 1
+            smp = ClockSampler(local_rank, period=0.01)
+            smp.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            cur.wait_stream(lane_streams[0])
+            e0.record(cur)
+            for st in lane_streams:
+                st.wait_event(e0)
+            for k in range(n):
+                step_resident(k)
+            for st in lane_streams:
+                cur.wait_stream(st)
+            e1.record(cur)
+            torch.cuda.synchronize(dev)
+            t = e0.elapsed_time(e1)
+            ck = smp.stop()
+            v = B * n / (t * 1e-3)
+            cnn_fl = (sum(conv_flops) + fc_flops) * B * n / (t * 1e-3) / 1e12
+            return {"workload": "configs[1] loop for %.1f s (%d steps), this GPU" % (t / 1e3, n), "faces_per_s": v, "ms_per_step": t / n,
+                    "vs_short_run": v / (value / world), "whole_step_TFLOPs": cnn_fl, "frac_sustained_peak": cnn_fl / sust, "clocks": ck}
+
+        guarded("sustained", sustained)
+        guarded("c4", lambda: sub_c4(dev, peaks))
+        guarded("fp32", lambda: sub_mode(dev, model, dev_sets[0], "float32", 5, B))
+        if dtype != "bf16x3":
+            guarded("bf16x3", lambda: sub_mode(dev, model, dev_sets[0], "bf16x3", 20, B))
+        guarded("c3", lambda: sub_c3(dev, peaks, 1024))
+        guarded("strong", lambda: sub_strong(model, dtype, world))
+    if world > 1:
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             os.sched_setaffinity(0, all_cpus)             # the CPU leg gets every host core again
             fps, cms, cores = time_cpu(64, 3, 1)
             cpu = {"value": fps, "unit": "faces/s", "cores": cores, "kind": "port",
@@ -500,10 +688,11 @@ def run_gpu(args, rank, world, local_rank):
                            "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2; activations workspace rewritten every step"
                                  % (n_sets, n_sets * set_bytes / 1e6)},
                 "e2e": {"value": e2e_val, "unit": "faces/s", "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": ms_e2e / args.steps, "h2d_only_ms_per_step": ms_link, "h2d_link_GBps": link_gbps, "cpus_bound": bound_cpus,
-                        "note": "H2D of the step's frames alone takes h2d_only_ms_per_step on this box; the leg is host-link-bound when that "
-                                "is close to ms_per_step"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+                        "ms_per_step": ms_e2e / args.steps, "api": "keypoints_detector.prediction.HostStream.submit / result (pinned host "
+                        "buffers in and out, %d slots)" % n_slots, "results_checked": e2e_check, "cpus_bound": bound_cpus, "link": link,
+                        "frac_of_link_bound": e2e_val / link["link_bound_faces_per_s"]},
+                "gpu_launches": int(launches), "roofline": roof, "roofline_cnn": roof_cnn, "cross_gpu_bit_identical": bit_identical,
+                "cross_gpu_digests": sorted(set(d[:12] for d in digests)), "sub": subs, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     return 0
 
@@ -520,6 +709,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (other configs / modes)")
+    ap.add_argument("--sub", default="sustained,c4,fp32,bf16x3,c3,strong", help="comma-separated sub-records to measure on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

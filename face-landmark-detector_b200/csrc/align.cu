@@ -11,14 +11,14 @@
 // Two warp kernels:
 //   * align_tile_kernel (round 2; C == 3, 16-byte-aligned frame rows, output a multiple of 16 x 16, <= 256 x 256):
 //     round 1's per-pixel global gathers were L1-tag / issue bound (ncu: ~21 sectors per warp load, 107 instructions per
-//     output pixel, DRAM at 16 %).  Here a 64-thread CTA walks the 16 x 16-pixel output tiles of its face; the source
+//     output pixel, DRAM at 16 %).  Here the two warps of a CTA walk the 16 x 16-pixel output tiles of a face (alternate tiles each); the source
 //     bounding box of a tile (a square for a similarity transform) arrives by ONE TMA load into a shared-memory ring
 //     (out-of-frame bytes are zero-filled by the tensor map = BORDER_CONSTANT 0, so the blend has no bounds checks and
 //     32-bit addresses), with the next tiles' boxes in flight while the current one is blended.  The tensor-map box is
 //     fixed per map, so eight maps (box sides 16..80 source pixels) are passed and the face picks the smallest that fits.
 //     The blend is exact integer arithmetic: out = (sum_ij a_i b_j p_ij + 512) >> 10 with a = (32 - fx, fx),
 //     b = (32 - fy, fy) (OpenCV's 15-bit table is exactly 32 a_i b_j for 5-bit fractions; its +-1 fix-ups at fx = fy = 0
-//     cannot change the rounded byte), computed as two IDP.4A per channel over the gathered (p00, p01, p10, p11) bytes.
+//     cannot change the rounded byte), computed as two IDP.2A per channel (16-bit weights a_i b_j against the gathered (p00, p01, p10, p11) bytes).
 //     Tiles whose box does not fit the class (never for similarity transforms; possible for caller matrices with
 //     shear) and faces scaled down by more than ~3.7x take the per-pixel global path below.
 //   * align_warp_kernel (round 1): any C in {1, 3, 4}, any shape; one CTA per (face, row block), per-pixel global loads.
@@ -240,16 +240,51 @@ struct TileArgs {
   int F, H, W, N, five_point, out_h, out_w, ysplit;
 };
 
+// Blend of four consecutive output pixels from the staged source box.  bxv / byv: the row's X0 / Y0; av / bv: adelta / bdelta of
+// the four columns; base: shared-memory address of the box; corr = -oy * BW - ox.  Returns the 12 output bytes in three words.
+__device__ __forceinline__ void blend4_smem(int bxv, int byv, const int4& a4, const int4& b4, uint32_t base, int corr, int BW, uint32_t (&w)[3]) {
+  const int av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+  uint32_t q[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int X = (bxv + av[j]) >> 5, Y = (byv + bv[j]) >> 5;
+    const int sx = X >> 5, sy = Y >> 5;
+    const uint32_t fx = X & 31, fy = Y & 31;
+    const uint32_t o = base + (uint32_t)(sy * BW + sx * 3 + corr);
+    const uint32_t oa = o & ~3u, k8 = (o & 3u) << 3;
+    const uint32_t l0 = lds32(oa), l1 = lds32(oa + 4), l2 = lds32(oa + 8);
+    const uint32_t m0 = lds32(oa + BW), m1 = lds32(oa + BW + 4), m2 = lds32(oa + BW + 8);
+    const uint32_t w0 = __funnelshift_r(l0, l1, k8), w1 = __funnelshift_r(l1, l2, k8);   // row sy  : c0 c1 c2 c0' | c1' c2'
+    const uint32_t v0 = __funnelshift_r(m0, m1, k8), v1 = __funnelshift_r(m1, m2, k8);   // row sy+1
+    const uint32_t t0 = prmt(w0, w1, 0x5241u), t1 = prmt(v0, v1, 0x5241u);                 // c1 c1' c2 c2'
+    const uint32_t P0 = prmt(w0, v0, 0x7430u), P1 = prmt(t0, t1, 0x5410u), P2 = prmt(t0, t1, 0x7632u);   // p00 p01 p10 p11 per channel
+    // weights w_ij = a_i b_j (<= 1024) as 16-bit pairs: out = (sum_ij w_ij p_ij + 512) >> 10, two IDP.2A per channel
+    const uint32_t A16 = fx * 65535u + 32u;          // (32 - fx) | fx << 16
+    const uint32_t W01 = (32u - fy) * A16, W23 = fy * A16;
+    const uint32_t S0 = __dp2a_hi(W23, P0, __dp2a_lo(W01, P0, 512u));
+    const uint32_t S1 = __dp2a_hi(W23, P1, __dp2a_lo(W01, P1, 512u));
+    const uint32_t S2 = __dp2a_hi(W23, P2, __dp2a_lo(W01, P2, 512u));
+    q[j] = prmt(prmt(S0 >> 10, S1 >> 10, 0x0040u), S2 >> 10, 0x0410u);
+  }
+  w[0] = prmt(q[0], q[1], 0x4210u);
+  w[1] = prmt(q[1], q[2], 0x5421u);
+  w[2] = prmt(q[2], q[3], 0x6542u);
+}
+
+// Warp-autonomous pipelines: the CTA (2 warps) shares the face's fit, coordinate tables and tile origins; after that each warp
+// walks its own tiles (alternate tiles of the CTA's tile rows) with its own half of the shared-memory ring and its own mbarriers:
+// lane 0 issues the TMA load of the tile after next into the buffer the warp has just finished reading (__syncwarp), so there is
+// no CTA-wide barrier in the loop.  A lane blends 2 x 4 pixels of a tile (rows r and r + 8, four consecutive columns).
 __global__ void __launch_bounds__(kTileThreads)
 align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ Fit fit;
   __shared__ __align__(16) int s_ad[kMaxOut], s_bd[kMaxOut], s_X0[kMaxOut], s_Y0[kMaxOut];
   __shared__ int s_ox[(kMaxOut / kTile) * (kMaxOut / kTile)], s_oy[(kMaxOut / kTile) * (kMaxOut / kTile)];   // per tile of this CTA: box origin (byte column, row); ox = INT_MIN -> global path
-  __shared__ __align__(8) uint64_t full_bar[kMaxBuf];
+  __shared__ __align__(8) uint64_t full_bar[2][kMaxBuf];
   __shared__ int s_cls;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int face = blockIdx.x;
   const int tiles_x = p.out_w / kTile, tiles_y = p.out_h / kTile;
   const int ty_per = (tiles_y + p.ysplit - 1) / p.ysplit;
@@ -259,7 +294,7 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
 
   cta_fit(fit, face, p.F, p.face2frame, p.marks, p.N, p.tmpl, p.five_point, p.M_in, p.M_out, blockIdx.y == 0, tid);
   if (tid == 0) {
-    for (int i = 0; i < kMaxBuf; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+    for (int i = 0; i < 2 * kMaxBuf; ++i) mbar_init(smem_u32(&full_bar[0][0]) + 8 * i, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -305,72 +340,71 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   }
   __syncthreads();
 
+  // ---- per-warp pipeline.  Buffers: each warp owns half of the ring when a box fits there at least once; a box larger than
+  // half the ring (the largest class) leaves the whole ring to warp 0 alone.
   const int frame_idx = p.face2frame[face];
   const uint8_t* frame = p.frames + (size_t)frame_idx * p.H * p.W * 3;
   const size_t row = (size_t)p.W * 3;
   const uint32_t box_bytes = (uint32_t)(BW * BH);
   const uint32_t buf_pitch = (box_bytes + 16u + 127u) & ~127u;       // + 16: the last pixel's third word may lie past the box
-  const int nbuf = cls >= 0 ? max(1, min(kMaxBuf, (int)(kRingBytes / buf_pitch))) : 1;
+  const uint32_t half_ring = (uint32_t)(kRingBytes / 2) & ~127u;
+  const bool solo = cls >= 0 && buf_pitch > half_ring;               // one warp, whole ring
+  if (solo && warp != 0) return;
+  const int nbuf = cls < 0 ? 1 : solo ? max(1, min(kMaxBuf, (int)(kRingBytes / buf_pitch))) : max(1, min(kMaxBuf, (int)(half_ring / buf_pitch)));
+  const uint32_t my_ring = solo ? ring : ring + warp * half_ring;
+  const uint32_t my_bar = smem_u32(&full_bar[warp][0]);
+  const int t_first = solo ? 0 : warp, t_step = solo ? 1 : 2;
+  const int n_my = t_first < T ? (T - t_first + t_step - 1) / t_step : 0;
   const CUtensorMap* tm = &maps.m[cls >= 0 ? cls : 0];
 
-  auto issue = [&](int t) {   // one thread
+  auto issue = [&](int i) {   // lane 0: load the box of this warp's i-th tile into buffer i % nbuf
+    const int t = t_first + i * t_step;
     const int ox = s_ox[t];
     if (ox == INT_MIN) return;
-    const int buf = t % nbuf;
-    const uint32_t bar = smem_u32(&full_bar[buf]);
-    mbar_arrive_expect_tx(bar, box_bytes);
-    tma_load_3d(ring + buf * buf_pitch, tm, bar, ox >> 2, s_oy[t], frame_idx);   // 32-bit elements: column = byte / 4
+    const uint32_t b = (uint32_t)(i % nbuf);
+    mbar_arrive_expect_tx(my_bar + 8u * b, box_bytes);
+    tma_load_3d(my_ring + b * buf_pitch, tm, my_bar + 8u * b, ox >> 2, s_oy[t], frame_idx);   // 32-bit elements: column = byte / 4
   };
-  if (tid == 0) for (int t = 0; t < min(nbuf, T); ++t) issue(t);
+  if (lane == 0) for (int i = 0; i < min(nbuf, n_my); ++i) issue(i);
 
-  const int yl = tid >> 2, xg = (tid & 3) << 2;
-  uint32_t phase_bits = 0u;   // bit b = parity the next wait on buffer b expects (slow tiles do not use their slot)
-  for (int t = 0; t < T; ++t) {
-    const int ty = ty0 + t / tiles_x, tx = t - (t / tiles_x) * tiles_x;
+  const int yl = lane >> 2, xg = (lane & 3) << 2;
+  uint32_t phase_bits = 0u;                 // bit b = parity the next wait on buffer b expects (global-path tiles skip their slot)
+  int tx = t_first % tiles_x, ty = ty0 + t_first / tiles_x, buf = 0;
+  for (int i = 0; i < n_my; ++i) {
+    const int t = t_first + i * t_step;
     const int y = ty * kTile + yl, x = tx * kTile + xg;
-    const int bxv = s_X0[y], byv = s_Y0[y];
     const int4 a4 = *reinterpret_cast<const int4*>(&s_ad[x]);
     const int4 b4 = *reinterpret_cast<const int4*>(&s_bd[x]);
-    const int av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
     const int ox = s_ox[t], oy = s_oy[t];
-    uint32_t q[4];
+    uint32_t wA[3], wB[3];
     if (ox != INT_MIN) {
-      const int buf = t % nbuf;
-      mbar_wait(smem_u32(&full_bar[0]) + 8u * buf, (phase_bits >> buf) & 1u);
+      mbar_wait(my_bar + 8u * buf, (phase_bits >> buf) & 1u);
       phase_bits ^= 1u << buf;
-      const uint32_t base = ring + buf * buf_pitch;
+      const uint32_t base = my_ring + buf * buf_pitch;
       const int corr = -oy * BW - ox;
+      blend4_smem(s_X0[y], s_Y0[y], a4, b4, base, corr, BW, wA);
+      blend4_smem(s_X0[y + 8], s_Y0[y + 8], a4, b4, base, corr, BW, wB);
+    } else {
+      const int av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      uint32_t qa[4], qb[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int X = (bxv + av[j]) >> 5, Y = (byv + bv[j]) >> 5;
-        const int sx = X >> 5, sy = Y >> 5;
-        const uint32_t fx = X & 31, fy = Y & 31;
-        const uint32_t o = base + (uint32_t)(sy * BW + sx * 3 + corr);
-        const uint32_t oa = o & ~3u, k8 = (o & 3u) << 3;
-        const uint32_t l0 = lds32(oa), l1 = lds32(oa + 4), l2 = lds32(oa + 8);
-        const uint32_t m0 = lds32(oa + BW), m1 = lds32(oa + BW + 4), m2 = lds32(oa + BW + 8);
-        const uint32_t w0 = __funnelshift_r(l0, l1, k8), w1 = __funnelshift_r(l1, l2, k8);   // row sy  : c0 c1 c2 c0' | c1' c2'
-        const uint32_t v0 = __funnelshift_r(m0, m1, k8), v1 = __funnelshift_r(m1, m2, k8);   // row sy+1
-        const uint32_t t0 = prmt(w0, w1, 0x5241u), t1 = prmt(v0, v1, 0x5241u);                 // c1 c1' c2 c2'
-        const uint32_t P0 = prmt(w0, v0, 0x7430u), P1 = prmt(t0, t1, 0x5410u), P2 = prmt(t0, t1, 0x7632u);   // p00 p01 p10 p11 per channel
-        const uint32_t A0 = fx * 255u + 32u;          // bytes (32 - fx, fx, 0, 0)
-        const uint32_t A1 = A0 << 16;                 // bytes (0, 0, 32 - fx, fx)
-        const uint32_t b1 = fy << 6, b0 = 2048u - b1; // (32 - fy, fy) << 6: the result byte lands in bits [16, 24)
-        const uint32_t S0 = b0 * __dp4a(P0, A0, 0u) + b1 * __dp4a(P0, A1, 0u) + 32768u;
-        const uint32_t S1 = b0 * __dp4a(P1, A0, 0u) + b1 * __dp4a(P1, A1, 0u) + 32768u;
-        const uint32_t S2 = b0 * __dp4a(P2, A0, 0u) + b1 * __dp4a(P2, A1, 0u) + 32768u;
-        q[j] = prmt(prmt(S0, S1, 0x0062u), S2, 0x0610u);
+        qa[j] = blend_px_global3(frame, p.H, p.W, row, (s_X0[y] + av[j]) >> 5, (s_Y0[y] + bv[j]) >> 5);
+        qb[j] = blend_px_global3(frame, p.H, p.W, row, (s_X0[y + 8] + av[j]) >> 5, (s_Y0[y + 8] + bv[j]) >> 5);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) q[j] = blend_px_global3(frame, p.H, p.W, row, (bxv + av[j]) >> 5, (byv + bv[j]) >> 5);
+      wA[0] = prmt(qa[0], qa[1], 0x4210u); wA[1] = prmt(qa[1], qa[2], 0x5421u); wA[2] = prmt(qa[2], qa[3], 0x6542u);
+      wB[0] = prmt(qb[0], qb[1], 0x4210u); wB[1] = prmt(qb[1], qb[2], 0x5421u); wB[2] = prmt(qb[2], qb[3], 0x6542u);
     }
-    uint32_t* dst = reinterpret_cast<uint32_t*>(crop + ((size_t)y * p.out_w + x) * 3);
-    dst[0] = prmt(q[0], q[1], 0x4210u);
-    dst[1] = prmt(q[1], q[2], 0x5421u);
-    dst[2] = prmt(q[2], q[3], 0x6542u);
-    __syncthreads();   // every thread has finished reading this tile's buffer
-    if (tid == 0 && t + nbuf < T) issue(t + nbuf);
+    const uint32_t off = (uint32_t)(y * p.out_w + x) * 3u;
+    uint32_t* dA = reinterpret_cast<uint32_t*>(crop + off);
+    uint32_t* dB = reinterpret_cast<uint32_t*>(crop + off + (uint32_t)(8 * p.out_w * 3));
+    dA[0] = wA[0]; dA[1] = wA[1]; dA[2] = wA[2];
+    dB[0] = wB[0]; dB[1] = wB[1]; dB[2] = wB[2];
+    __syncwarp();          // every lane has finished reading this tile's buffer
+    if (lane == 0 && i + nbuf < n_my) issue(i + nbuf);
+    if (++buf == nbuf) buf = 0;
+    tx += t_step;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
   }
 }
 

@@ -39,6 +39,7 @@ struct LayerRt {
   float* d_w = nullptr;
   float* d_bias = nullptr;
   __nv_bfloat16* d_wbf = nullptr;
+  float* d_zero = nullptr;      // all-zero bias for split-K partial sums (tensor-core dense)
   std::vector<PlanEntry> plans;
   std::vector<HaloPlanEntry> hplans;
   std::vector<DeconvPlanEntry> dplans;
@@ -147,6 +148,15 @@ int infer_shapes(fld_net* net) {
       }
       const bool want_f32 = f32_needed[i + 1] != 0;
       if (L.d.op == FLD_OP_DWCONV || L.d.op == FLD_OP_MAXPOOL || L.d.op == FLD_OP_ADD) { o.dtype = want_f32 ? FLD_F32 : FLD_BF16; continue; }
+      if (L.d.op == FLD_OP_DENSE && a.dtype == FLD_BF16 && a.elems() % 64 == 0 && L.d.act == FLD_ACT_NONE && !getenv("FLD_TC_DENSE_OFF")) {
+        // Flatten + Dense as a flat 1x1 conv over B "pixels" with Cin = H*W*C on the tensor cores, split-K (see net_forward)
+        L.path = PATH_TC_TMA;
+        L.cout_pad = (int)align_up(L.d.cout, 16);
+        L.g = ConvGeom{};
+        L.g.IH = L.g.IW = L.g.OH = L.g.OW = 1; L.g.Cin = (int)a.elems(); L.g.Cout = L.d.cout;
+        L.g.kh = L.g.kw = 1; L.g.stride = 1; L.g.act = FLD_ACT_NONE; L.g.pool = 0;
+        if (L.cout_pad > 256 || !tc_conv_supported(L.g)) L.path = PATH_SIMT;
+      }
       if (L.d.op != FLD_OP_CONV) { o.dtype = FLD_F32; continue; }
       const bool in_ok_first = (a.dtype == FLD_U8 || a.dtype == FLD_F32) && (tc_conv_first_supported(L.g) || tc_conv_stem_supported(L.g));
       const bool in_ok_tma = (a.dtype == FLD_BF16) && tc_conv_supported(L.g);
@@ -194,6 +204,10 @@ int infer_shapes(fld_net* net) {
         L.path = PATH_TC_TMA;
         L.x3 = true;
         L.cout_pad = (int)align_up(L.g.Cout, L.g.Cout > 256 ? 128 : 16);
+      } else if (L.d.op == FLD_OP_CONV && out_split[i] && net->tensors[L.d.in0].dtype == FLD_U8 && tc_conv_first_supported(L.g) &&
+                 !getenv("FLD_X3_FIRST_OFF")) {
+        L.path = PATH_TC_FIRST;   // uint8 is exact in bf16: only the weights are split (tc_conv_first.cu, K = 80)
+        L.x3 = true;
       }
     }
   }
@@ -204,6 +218,8 @@ void free_layer(LayerRt& L) {
   if (L.d_w) cudaFree(L.d_w);
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_wbf) cudaFree(L.d_wbf);
+  if (L.d_zero) cudaFree(L.d_zero);
+  L.d_zero = nullptr;
   for (auto& pe : L.plans) tc_conv_plan_destroy(pe.plan);
   for (auto& pe : L.hplans) tc_halo_plan_destroy(pe.plan);
   L.hplans.clear();
@@ -350,7 +366,19 @@ extern "C" int fld_net_finalize(fld_net* net) {
       FLD_CUDA(cudaMalloc(&L.d_bias, nb * sizeof(float)));
       FLD_CUDA(cudaMemcpy(L.d_bias, b.data(), nb * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) {
+    if (L.d.op == FLD_OP_DENSE && L.path == PATH_TC_TMA) {
+      // [cout_pad][In] K-major bf16  <-  w[In][Out]; the fp32 copy stays for batches too small for a 128-row tile
+      const size_t In = a.elems();
+      std::vector<uint16_t> pk((size_t)L.cout_pad * In, 0);
+      for (size_t k = 0; k < In; ++k)
+        for (int o = 0; o < Cout; ++o) pk[(size_t)o * In + k] = f2bf(L.w_host[k * Cout + o]);
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      FLD_CUDA(cudaMalloc(&L.d_zero, (size_t)(L.cout_pad + 64) * sizeof(float)));
+      FLD_CUDA(cudaMemset(L.d_zero, 0, (size_t)(L.cout_pad + 64) * sizeof(float)));
+      FLD_CUDA(cudaMalloc(&L.d_w, L.w_host.size() * sizeof(float)));
+      FLD_CUDA(cudaMemcpy(L.d_w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA) {
       std::vector<uint16_t> pk;
       tc_deconv_pack_weights(L.w_host.data(), L.d.stride, a.c, Cout, f2bf, pk);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
@@ -366,8 +394,9 @@ extern "C" int fld_net_finalize(fld_net* net) {
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
       // core-matrix packed [6 kgroups][Cout/8][8][8], k' = kh*12 + kw*4 + c (see tc_conv_first.cu)
-      std::vector<uint16_t> pk((size_t)Cout * 48, 0);
-      tc_conv_first_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data());
+      const int kg = L.x3 ? 10 : 6;
+      std::vector<uint16_t> pk((size_t)Cout * 8 * kg, 0);
+      tc_conv_first_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data(), kg);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.x3) {
@@ -402,6 +431,17 @@ extern "C" int fld_net_finalize(fld_net* net) {
   return FLD_OK;
 }
 
+// split-K factor of the tensor-core dense layer: the largest divisor of the k-chunk count that keeps the grid within one wave
+// and leaves at least two k-blocks per CTA
+static int dense_ksplit(const fld_net* net, int B, int kchunks) {
+  const int mtiles = (B + 127) / 128;
+  int best = 1;
+  for (int s = 1; s <= kchunks; ++s)
+    if (kchunks % s == 0 && s * mtiles <= net->h->sm_count && kchunks / s >= 2) best = s;
+  return best;
+}
+constexpr int kDenseTcMinBatch = 64;
+
 static size_t dense_scratch_bytes(const fld_net* net, int B) {
   size_t m = 0;
   for (size_t i = 0; i < net->layers.size(); ++i)
@@ -409,6 +449,8 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     const LayerRt& L = net->layers[i];
     const TensorInfo& a = net->tensors[L.d.in0];
     if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
+    if (L.d.op == FLD_OP_DENSE && L.path == PATH_TC_TMA)
+      m = std::max(m, (size_t)dense_ksplit(net, B, (int)a.elems() / 64) * B * L.d.cout * sizeof(float));
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
       m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
   }
@@ -492,7 +534,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
           rc = tc_conv_stem(net->h, pin, a.dtype, L.d_wbf, (__nv_bfloat16*)pout, L.g, B, st);
         } else if (L.path == PATH_TC_FIRST) {
-          rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st);
+          rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st, L.x3 ? 1 : 0);
         } else if (L.path == PATH_TC_TMA && (o.dtype == FLD_BF16 || o.dtype == FLD_BF16X3) && tc_halo_supported(L.g, L.cout_pad)) {
           TcHaloPlan* plan = nullptr;
           for (auto& pe : L.hplans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }
@@ -550,6 +592,21 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         break;
       }
       case FLD_OP_DENSE:
+        if (L.path == PATH_TC_TMA && B >= kDenseTcMinBatch) {
+          const int ks = dense_ksplit(net, B, (int)a.elems() / 64);
+          TcConvPlan* plan = nullptr;
+          for (auto& pe : L.plans) if (pe.B == B && pe.in == pin) { plan = pe.plan; break; }
+          if (!plan) {
+            rc = tc_conv_plan_create(net->h, pin, L.d_wbf, L.cout_pad, L.g, B, &plan, 0, 0, ks);
+            if (rc) return rc;
+            if (L.plans.size() >= 16 && net->retained == 0) { tc_conv_plan_destroy(L.plans.front().plan); L.plans.erase(L.plans.begin()); }
+            L.plans.push_back({B, pin, plan});
+          }
+          rc = tc_conv_run(plan, L.d_zero, dense_scratch, FLD_F32, st);    // partial sums [ks][B][Out]
+          if (rc) return rc;
+          rc = simt_dense_reduce(dense_scratch, L.b_host.empty() ? nullptr : L.d_bias, (float*)pout, B, o.c, ks, d.act, st);
+          break;
+        }
         rc = simt_dense(pin, a.dtype, L.d_w, L.b_host.empty() ? nullptr : L.d_bias, (float*)pout, dense_scratch, B, (int)a.elems(), o.c, d.act,
                         st, a.c);
         break;

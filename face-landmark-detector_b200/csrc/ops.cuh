@@ -27,17 +27,20 @@ size_t simt_dense_scratch_bytes(int B, int In, int Out);
 // in_dtype FLD_BF16X3: `in` is a SPLIT tensor ([hi | lo] bf16 per pixel of in_channels channels); In counts logical elements
 int simt_dense(const void* in, int in_dtype, const float* w /*[In][Out]*/, const float* bias, float* out, float* scratch /*split-K partials*/,
                int B, int In, int Out, int act, cudaStream_t st, int in_channels = 0);
+// fixed-order sum of split-K partials [KS][B][Out] + bias + activation (deterministic: no atomics)
+int simt_dense_reduce(const float* part, const float* bias, float* out, int B, int Out, int KS, int act, cudaStream_t st);
 int simt_maxpool(const float* in, float* out, int B, int IH, int IW, int C, int OH, int OW, int k, int s, cudaStream_t st);
 int simt_cvt_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
 
 // ---- tcgen05 tensor-core kernels (tc_conv.cu)
 struct TcConvPlan;  // opaque: tensor maps + launch geometry for one (layer, batch, buffers) combination
 // first layer: 3x3, Cin = 3, pad 1, stride 1, fused bias + ReLU (+pool2); input u8 or f32 NHWC, output bf16 NHWC
+// x3: FLD_BF16X3 variant (uint8 input only): weights split hi / lo (K = 80), SPLIT output
 int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_bfloat16* w_packed /*[Cout][32]*/,
-                  const float* bias, __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st);
+                  const float* bias, __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st, int x3 = 0);
 bool tc_conv_first_supported(const ConvGeom& g);
 void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_host /*[Cout] or null*/, int Cout,
-                        uint16_t (*f2bf)(float), uint16_t* out /*[Cout*48]*/);
+                        uint16_t (*f2bf)(float), uint16_t* out /*[Cout*8*kg]*/, int kg = 6);
 // strided stems (tc_conv_stem.cu): k x k (3 or 7), stride 2, Cin = 3, any zero padding, bias folded, no pool; bf16 NHWC out
 bool tc_conv_stem_supported(const ConvGeom& g);
 int tc_conv_stem_kgroups(int ks);

@@ -420,6 +420,13 @@ int simt_dense(const void* in, int in_dtype, const float* w, const float* bias, 
   return FLD_OK;
 }
 
+int simt_dense_reduce(const float* part, const float* bias, float* out, int B, int Out, int KS, int act, cudaStream_t st) {
+  if (B == 0) return FLD_OK;
+  dense_reduce_kernel<<<fld_div_up(B * Out, 256), 256, 0, st>>>(part, bias, out, B, Out, KS, act);
+  FLD_LAUNCHED();
+  return FLD_OK;
+}
+
 int simt_maxpool(const float* in, float* out, int B, int IH, int IW, int C, int OH, int OW, int k, int s, cudaStream_t st) {
   if (B == 0) return FLD_OK;
   const long long total = (long long)B * OH * OW * C;

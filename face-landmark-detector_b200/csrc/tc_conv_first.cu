@@ -30,6 +30,7 @@ struct FirstParams {
   int act, pool;
   int tiles_x, tiles_y, n_tiles;
   unsigned long long mul_x, mul_y;  // ceil(2^40 / tiles_x), ceil(2^40 / tiles_y): exact division for n < 2^21
+  int split;               // FLD_BF16X3: store the output as a SPLIT tensor ([hi | lo] bf16, pixel pitch 2 * Cout)
   int dbg;                 // FLD_C1_DBG timing experiments (results are garbage): 1 no pooling shuffles, 2 no epilogue math,
                            // 4 no TMEM loads, 8 no im2col, 16 no MMA, 32 no pixel fetch, 64 no park, 128 no async-proxy fence, 256 no commit / mbarrier wait
 };
@@ -57,9 +58,13 @@ __device__ __forceinline__ void load_pixel(const TIn* __restrict__ img, int H, i
 // per-thread address arithmetic, bounds checks and three byte loads per pixel (measured at 22 % of the kernel).  The box starts at
 // a 16-byte-aligned byte offset (measured: a uint8 box that starts at an unaligned byte never completes its mbarrier, a float32
 // box at a 4-byte-aligned start does); threads add the remainder.  conv1: 0.109 -> 0.105 ms per 256 faces.
-template <typename TIn, bool DBG, int NT, bool TIN>
+// KG = K groups of 8 elements: 6 (K = 48: 36 tap slots + 2 bias slots) in bf16 mode; 10 (K = 80) in FLD_BF16X3 mode with a uint8
+// input, which is exact in bf16, so only the weights need the hi / lo split: k 0..35 taps x w_hi, 36..38 = 1.0 x the bias split three
+// ways, 40..75 the same taps x w_lo — five K = 16 MMAs instead of three, fp32 accumulation.
+template <typename TIn, bool DBG, int NT, bool TIN, int KG = 6>
 __global__ void __launch_bounds__(128 * NT, 8 / NT)
 conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p) {
+  constexpr int ABYTES = KG * 2048;                        // A tile of one stacked tile: KG k-groups x 16 row groups x 128 B
   constexpr int THc = 16 * NT, PH_ = THc + 2, NPIX = PW_ * PH_, NTHR = 128 * NT;
   constexpr int EPA = 16 / (int)sizeof(TIn);               // elements per 16 bytes
   constexpr int RAWW = 30 + EPA;                            // box width in elements: 30 needed + alignment slack, multiple of EPA? (46 / 34)
@@ -69,9 +74,9 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // A NT x [6 kgroups][16 rowgroups][8 rows][16 B] = NT x 12 KB | B [6 kgroups][Cout/8][8][16 B] = Cout*96 B | patch [PH_][10] x 8 B
   uint8_t* sA = smem_raw;
-  uint8_t* sB = smem_raw + 12288 * NT;
-  uint2* patch = reinterpret_cast<uint2*>(sB + p.Cout * 96);
-  const TIn* raw = reinterpret_cast<const TIn*>(smem_raw + (((size_t)12288 * NT + (size_t)p.Cout * 96 + (size_t)NPIX * 8 + 127) & ~(size_t)127));
+  uint8_t* sB = smem_raw + ABYTES * NT;
+  uint2* patch = reinterpret_cast<uint2*>(sB + p.Cout * 16 * KG);
+  const TIn* raw = reinterpret_cast<const TIn*>(smem_raw + (((size_t)ABYTES * NT + (size_t)p.Cout * 16 * KG + (size_t)NPIX * 8 + 127) & ~(size_t)127));
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t in_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -84,8 +89,8 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
   {  // weights (already in core-matrix order) and the all-zero sixth K group of A
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = tid; i < p.Cout * 6; i += NTHR) dst[i] = src[i];
-    *reinterpret_cast<uint4*>(sA + thalf * 12288 + (5 * 16 + (t128 >> 3)) * 128 + (t128 & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < p.Cout * KG; i += NTHR) dst[i] = src[i];
+    if (KG == 6) *reinterpret_cast<uint4*>(sA + thalf * ABYTES + (5 * 16 + (t128 >> 3)) * 128 + (t128 & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid == 0) {
     mbar_init(smem_u32(&mma_bar), 1);
@@ -178,12 +183,19 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) q[kh][kw] = patch[(ly + kh) * PW_ + lx + kw];
-      uint8_t* row = sA + thalf * 12288 + (t128 >> 3) * 128 + (t128 & 7) * 16;  // + kgroup * 16 * 128
+      uint8_t* row = sA + thalf * ABYTES + (t128 >> 3) * 128 + (t128 & 7) * 16;  // + kgroup * 16 * 128
       *reinterpret_cast<uint4*>(row + 0 * 2048) = make_uint4(q[0][0].x, q[0][0].y, q[0][1].x, q[0][1].y);
       *reinterpret_cast<uint4*>(row + 1 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
       *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
       *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
-      *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0x3f803f80u, 0u);  // k 36,37 = 1.0 (bias)
+      *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0x3f803f80u, KG == 10 ? 0x00003f80u : 0u);  // k 36,37(,38) = 1.0 (bias)
+      if (KG == 10) {   // the same taps again, against the lo halves of the weights
+        *reinterpret_cast<uint4*>(row + 5 * 2048) = make_uint4(q[0][0].x, q[0][0].y, q[0][1].x, q[0][1].y);
+        *reinterpret_cast<uint4*>(row + 6 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
+        *reinterpret_cast<uint4*>(row + 7 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
+        *reinterpret_cast<uint4*>(row + 8 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
+        *reinterpret_cast<uint4*>(row + 9 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0u, 0u);
+      }
     }
     if (!(DBG && (p.dbg & 128))) fence_async_smem();
     __syncthreads();
@@ -195,11 +207,10 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
         if (!(DBG && (p.dbg & 16))) {
 #pragma unroll
           for (int hf = 0; hf < NT; ++hf) {
-            const uint64_t ad = adesc0 + (uint64_t)(hf * (12288 >> 4));
+            const uint64_t ad = adesc0 + (uint64_t)(hf * (ABYTES >> 4));
             const uint32_t d = tmem_base + hf * ncols1;
-            umma_bf16(d, ad, bdesc0, idesc, 0u);
-            umma_bf16(d, ad + astep, bdesc0 + bstep, idesc, 1u);
-            umma_bf16(d, ad + 2 * astep, bdesc0 + 2 * bstep, idesc, 1u);
+#pragma unroll
+            for (int m = 0; m < KG / 2; ++m) umma_bf16(d, ad + m * astep, bdesc0 + m * bstep, idesc, m ? 1u : 0u);
           }
         }
         umma_commit(smem_u32(&mma_bar));
@@ -215,10 +226,10 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
     if (p.pool) {
       const int py = (y0 + ly) >> 1, px = (x0 + lx) >> 1;
       eo.valid = (py < PH) && (px < PW);
-      eo.ptr = p.out + (((size_t)b * PH + py) * PW + px) * p.Cout;
+      eo.ptr = p.out + (((size_t)b * PH + py) * PW + px) * (KG == 10 ? 2 * p.Cout : p.Cout);
     } else {
       eo.valid = (y0 + ly < p.H) && (x0 + lx < p.W);
-      eo.ptr = p.out + (((size_t)b * p.H + (y0 + ly)) * p.W + (x0 + lx)) * p.Cout;
+      eo.ptr = p.out + (((size_t)b * p.H + (y0 + ly)) * p.W + (x0 + lx)) * (KG == 10 ? 2 * p.Cout : p.Cout);
     }
     for (int ch = 0; ch < p.Cout; ch += 32) {
       uint32_t acc[32];
@@ -245,6 +256,11 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
       EpiOut e2 = eo;
       e2.ptr = reinterpret_cast<__nv_bfloat16*>(eo.ptr) + ch;
       e2.c_left = p.Cout - ch;
+      if (KG == 10) {   // SPLIT output (eo.ptr was computed with the 2 * Cout pixel pitch)
+        if (p.pool) epilogue_chunk_split<true, false>(acc, p.bias + ch, p.act, lane, TWc, e2, p.Cout);
+        else epilogue_chunk_split<false, false>(acc, p.bias + ch, p.act, lane, TWc, e2, p.Cout);
+        continue;
+      }
       if (p.pool) epilogue_chunk<true, false, false>(acc, p.bias + ch, p.act, lane, TWc, e2);
       else epilogue_chunk<false, false, false>(acc, p.bias + ch, p.act, lane, TWc, e2);
     }
@@ -263,44 +279,58 @@ bool tc_conv_first_supported(const ConvGeom& g) {
 }
 
 // host-side weight packing for conv_first_kernel: w_host fp32 [27][Cout] (k = (kh*3+kw)*3 + c) -> bf16 bits
-// [6][Cout/8][8][8] with k' = kh*12 + kw*4 + c; k' = 36 / 37 carry the bias split into bf16 hi / lo
-void tc_conv_first_pack(const float* w_host, const float* bias_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out) {
-  for (int kg = 0; kg < 6; ++kg)
+// [KG][Cout/8][8][8] with k' = kh*12 + kw*4 + c.  kg = 6: k' = 36 / 37 carry the bias split into bf16 hi / lo.
+// kg = 10 (FLD_BF16X3): k' < 36 holds bf16(w), k' = 40 + (kh*12 + kw*4 + c) the remainder bf16(w - bf16(w)), and k' = 36..38 the
+// bias split three ways (exact to 2^-25).
+static float bf_to_float(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+void tc_conv_first_pack(const float* w_host, const float* bias_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out, int kg_n) {
+  for (int kg = 0; kg < kg_n; ++kg)
     for (int ng = 0; ng < Cout / 8; ++ng)
       for (int r = 0; r < 8; ++r)
         for (int e = 0; e < 8; ++e) {
           const int kp = kg * 8 + e, o = ng * 8 + r;
-          const int kh = kp / 12, kw = (kp % 12) / 4, c = kp % 4;
+          const bool lo_blk = kg_n == 10 && kp >= 40;
+          const int kq = lo_blk ? kp - 40 : kp;
+          const int kh = kq / 12, kw = (kq % 12) / 4, c = kq % 4;
           float v = 0.f;
-          if (kp < 36 && c < 3) v = w_host[(size_t)((kh * 3 + kw) * 3 + c) * Cout + o];
-          if (bias_host && (kp == 36 || kp == 37)) {  // bias = hi + lo (both bf16), multiplied by A[k] = 1.0
-            uint16_t hb = f2bf(bias_host[o]);
-            uint32_t hu = (uint32_t)hb << 16;
-            float hi;
-            memcpy(&hi, &hu, 4);
-            v = (kp == 36) ? hi : bias_host[o] - hi;
+          if (kq < 36 && c < 3) {
+            const float w = w_host[(size_t)((kh * 3 + kw) * 3 + c) * Cout + o];
+            v = lo_blk ? w - bf_to_float(f2bf(w)) : w;
+          }
+          if (bias_host && !lo_blk && kp >= 36 && kp <= (kg_n == 10 ? 38 : 37)) {  // bias = hi + mid (+ lo), multiplied by A[k] = 1.0
+            const float b0 = bf_to_float(f2bf(bias_host[o]));
+            const float b1 = bf_to_float(f2bf(bias_host[o] - b0));
+            v = kp == 36 ? b0 : kp == 37 ? (kg_n == 10 ? b1 : bias_host[o] - b0) : bias_host[o] - b0 - b1;
           }
           out[(((size_t)kg * (Cout / 8) + ng) * 8 + r) * 8 + e] = f2bf(v);
         }
 }
 
 int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_bfloat16* w_packed, const float* bias,
-                  __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st) {
+                  __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st, int x3) {
   if (B == 0) return FLD_OK;
+  if (x3 && in_dtype != FLD_U8) { fld_set_error("tc_conv_first: the FLD_BF16X3 variant takes a uint8 input"); return FLD_ERR_INVALID; }
+  const int KG = x3 ? 10 : 6;
   FirstParams p;
+  p.split = x3;
   p.in = in; p.w = w_packed; p.bias = bias; p.out = out;
   p.B = B; p.H = g.IH; p.W = g.IW; p.Cout = g.Cout; p.act = g.act; p.pool = g.pool;
   const int ncols1 = g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : g.Cout <= 128 ? 128 : 256;
   // stacked tiles per CTA iteration: measured equal within noise at batch 256 (0.112 ms with 2 vs 0.109 ms with 1), so the
   // kernel's time is per-pixel work, not the per-iteration barrier chain; 2 stays available for experiments (FLD_C1_NT=2)
   int NT = 1;
-  { const char* e = getenv("FLD_C1_NT"); if (e && atoi(e) == 2 && g.OH >= 32 && ncols1 <= 128) NT = 2; }
+  { const char* e = getenv("FLD_C1_NT"); if (!x3 && e && atoi(e) == 2 && g.OH >= 32 && ncols1 <= 128) NT = 2; }
   const int TH = 16 * NT;
   p.tiles_x = fld_div_up(g.OW, TWc); p.tiles_y = fld_div_up(g.OH, TH);
   p.n_tiles = B * p.tiles_x * p.tiles_y;
   p.mul_x = ((1ull << 40) + p.tiles_x - 1) / p.tiles_x;
   p.mul_y = ((1ull << 40) + p.tiles_y - 1) / p.tiles_y;
-  { const char* e = getenv("FLD_C1_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("FLD_C1_DBG"); p.dbg = (e && !x3) ? atoi(e) : 0; }
   if (p.n_tiles >= (1 << 21)) { fld_set_error("tc_conv_first: too many tiles (%d)", p.n_tiles); return FLD_ERR_INVALID; }
   // TMA-fed raw patch: needs 16-byte-multiple row pitch and base (tensor-map rules), one tile per iteration, production build
   const size_t esz = in_dtype == FLD_U8 ? 1 : 4;
@@ -309,7 +339,7 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
   const int epa = (int)(16 / esz);
   const int raww = ((30 + epa) * (int)esz + 15) / 16 * 16 / (int)esz;      // box width in elements (same formula as the kernel)
   const size_t rawb = (size_t)(TH + 2) * raww * esz;
-  const size_t smem_base_bytes = (size_t)12288 * NT + (size_t)g.Cout * 96 + (size_t)PW_ * (TH + 2) * 8;
+  const size_t smem_base_bytes = (size_t)KG * 2048 * NT + (size_t)g.Cout * 16 * KG + (size_t)PW_ * (TH + 2) * 8;
   const size_t smem = tin ? ((smem_base_bytes + 127) & ~(size_t)127) + 2 * ((rawb + 127) & ~(size_t)127) + 128 : smem_base_bytes + 64;
   const int cta_per_sm = std::max(1, std::min(512 / (ncols1 * NT), 8 / NT));
   const int grid = std::min(p.n_tiles, h->sm_count * cta_per_sm);
@@ -333,7 +363,9 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
     return FLD_OK;
   };
   int rc;
-  if (in_dtype == FLD_U8) {
+  if (x3) {
+    rc = tin ? launch(conv_first_kernel<uint8_t, false, 1, true, 10>) : launch(conv_first_kernel<uint8_t, false, 1, false, 10>);
+  } else if (in_dtype == FLD_U8) {
     if (tin) rc = launch(conv_first_kernel<uint8_t, false, 1, true>);
     else if (NT == 2) rc = p.dbg ? launch(conv_first_kernel<uint8_t, true, 2, false>) : launch(conv_first_kernel<uint8_t, false, 2, false>);
     else rc = p.dbg ? launch(conv_first_kernel<uint8_t, true, 1, false>) : launch(conv_first_kernel<uint8_t, false, 1, false>);

@@ -3,8 +3,10 @@ on a B200 (sm_100a CUDA kernels behind libfld_sm100.so).
 
 Unchanged entry points (reference prediction.py): detect_marks :16-96, video_predict :99-113,
 model_from_checkpoint_path :116-133, keypts_predict :158-196, _prediction :199-222.
-Additions: detect_marks_batch, align_faces, LandmarkPipeline (device-resident batched path used by
-bench.py and example.py), shard_faces (multi-GPU batch sharding).
+Additions: detect_marks_batch, align_faces, LandmarkPipeline (batched path: run_device for device-resident tensors, run_host
+for host arrays), HostStream (overlapped copy / compute / copy pipeline over pinned host buffers — what bench.py's e2e leg
+calls), MultiGpuPipeline (one batch sharded by frame over the GPUs of a box with a host-side gather), shard_faces /
+shard_by_frames.
 
 Where the reference crashes as written behaviour is defined and documented inline.
 """
@@ -171,8 +173,10 @@ class LandmarkPipeline:
         self.device = _device(device)
         self.input_size = model.input_height
         self._bufs = {}
+        self._host_state = {}                 # run_host's cached staging / result buffers
         self.max_batch = 4096
-        model.compiled(self.device, dtype)
+        with torch.cuda.device(self.device):
+            model.compiled(self.device, dtype)
 
     def _buffers(self, lane, B, C, dev):
         """Per-lane result buffers, allocated once per batch size: no allocator traffic (and no allocator-induced stream
@@ -242,10 +246,279 @@ class LandmarkPipeline:
             return {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
 
 
+    def run_host(self, frames, boxes, face2frame=None, out=None):
+        """Host buffers in, host buffers out, one call (the reference's boundary: host arrays, prediction.py:16-113): frames
+        uint8 [F,H,W,3] BGR, boxes [B,4], face2frame [B] as NumPy arrays or CPU tensors.  Pinned inputs are copied as they are;
+        pageable ones pass through a cached pinned staging buffer first.  Returns NumPy views of cached PINNED result buffers
+        {"marks" float32 [B,68,2], "aligned" uint8 [B,oh,ow,3], "M" float64 [B,2,3], "faceboxes" int32 [B,4]} that the next
+        run_host call on this pipeline overwrites (pass `out`, a dict of pinned CPU tensors, to own them).  For a steady stream
+        of equally shaped batches use HostStream, which overlaps the copies with the compute."""
+        dev = self.device
+        fr = _as_cpu_tensor(frames, torch.uint8)
+        if fr.dim() == 3:
+            fr = fr[None]
+        bx = _as_cpu_tensor(boxes, torch.int32).reshape(-1, 4)
+        B = bx.shape[0]
+        ff = torch.zeros(B, dtype=torch.int32) if face2frame is None else _as_cpu_tensor(face2frame, torch.int32)
+        st = self._host_state
+        with torch.cuda.device(dev):
+            d_in = []
+            for name, t in (("frames", fr), ("boxes", bx), ("f2f", ff)):
+                if not t.is_pinned():
+                    stage = st.get(("pin", name))
+                    if stage is None or stage.numel() < t.numel():
+                        stage = st[("pin", name)] = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+                    stage[:t.numel()].view(t.shape).copy_(t)
+                    t = stage[:t.numel()].view(t.shape)
+                d = st.get(("dev", name))
+                if d is None or d.numel() < t.numel():
+                    d = st[("dev", name)] = torch.empty(max(t.numel(), 1), dtype=t.dtype, device=dev)
+                dv = d[:t.numel()].view(t.shape)
+                dv.copy_(t, non_blocking=True)
+                d_in.append(dv)
+            r = self.run_device(d_in[0], d_in[1], d_in[2], lane=0)
+            res = {}
+            for k in ("marks", "aligned", "M", "faceboxes"):
+                if out is not None and k in out:
+                    h = out[k]
+                else:
+                    h = st.get(("out", k))
+                    if h is None or h.numel() < r[k].numel() or h.dtype != r[k].dtype:
+                        h = st[("out", k)] = torch.empty(max(r[k].numel(), 1), dtype=r[k].dtype).pin_memory()
+                    h = h[:r[k].numel()].view(r[k].shape)
+                h.copy_(r[k], non_blocking=True)
+                res[k] = h
+            torch.cuda.current_stream(dev).synchronize()
+        return {k: v.numpy() for k, v in res.items()}
+
+
+def _as_cpu_tensor(a, dtype):
+    if isinstance(a, torch.Tensor):
+        assert not a.is_cuda, "host entry points take host arrays"
+        return a.contiguous() if a.dtype == dtype else a.to(dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype={torch.uint8: np.uint8, torch.int32: np.int32, torch.float32: np.float32}[dtype]))
+
+
+class HostStream:
+    """Streaming host-buffer entry point for equally shaped batches (video: F frames, up to B faces per step): the H2D copy of
+    batch k+1, the compute of batch k and the D2H copy of batch k-1 run concurrently on three CUDA streams over `n_slots` slots
+    of device buffers, pinned result buffers and (optionally) one captured CUDA graph per slot.
+
+        hs = HostStream(pipe, batch=256, n_frames=4, frame_hw=(1080, 1920))
+        t = hs.submit(frames, boxes, face2frame)        # returns at once; pinned inputs are copied as they are
+        r = hs.result(t)                                # {"marks", "aligned", "M"}: NumPy views of the slot's pinned buffers,
+                                                        # valid until n_slots further submits
+
+    `hs.inputs(slot)` exposes a slot's pinned staging arrays so that a producer (decoder, detector) can write into them
+    directly; submit() without arrays then sends that staging area."""
+
+    def __init__(self, pipeline, batch, n_frames, frame_hw, n_slots=3, use_graph=True, channels=3):
+        self.pipe, self.B, self.F, self.n_slots = pipeline, int(batch), int(n_frames), int(n_slots)
+        dev = self.dev = pipeline.device
+        H, W = frame_hw
+        oh, ow = pipeline.out_size
+        with torch.cuda.device(dev):
+            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.s_comp = [torch.cuda.Stream(dev) for _ in range(self.n_slots)]
+            self.ev_in = [torch.cuda.Event() for _ in range(self.n_slots)]
+            self.ev_comp = [torch.cuda.Event() for _ in range(self.n_slots)]
+            self.ev_out = [torch.cuda.Event() for _ in range(self.n_slots)]
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            p = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self.d_in = [(e((self.F, H, W, channels), torch.uint8), e((self.B, 4), torch.int32), e((self.B,), torch.int32))
+                         for _ in range(self.n_slots)]
+            self.h_in = [(p((self.F, H, W, channels), torch.uint8), p((self.B, 4), torch.int32), p((self.B,), torch.int32))
+                         for _ in range(self.n_slots)]
+            self.h_out = [{"marks": p((self.B, 68, 2), torch.float32), "aligned": p((self.B, oh, ow, channels), torch.uint8),
+                           "M": p((self.B, 2, 3), torch.float64)} for _ in range(self.n_slots)]
+            for hi in self.h_in:                      # a never-filled slot must still hold valid boxes / frame indices
+                hi[1][:] = torch.tensor([0, 0, 32, 32], dtype=torch.int32)
+                hi[2].zero_()
+            for d, hsrc in zip(self.d_in, self.h_in):
+                d[0].zero_(); d[1].copy_(hsrc[1]); d[2].copy_(hsrc[2])
+            torch.cuda.synchronize(dev)
+            self.caps = None
+            if use_graph:
+                self.caps = [pipeline.capture(*self.d_in[s], lane=s) for s in range(self.n_slots)]
+            self._res = [None] * self.n_slots
+        self.n_submitted = 0
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.d_in[0])
+        self.d2h_bytes = sum(t.numel() * t.element_size() for k, t in self.h_out[0].items() if k != "M")
+
+    def inputs(self, slot):
+        """Pinned staging arrays of a slot (NumPy views): frames [F,H,W,C], boxes [B,4], face2frame [B]."""
+        return tuple(t.numpy() for t in self.h_in[slot % self.n_slots])
+
+    def next_slot(self):
+        return self.n_submitted % self.n_slots
+
+    def submit(self, frames=None, boxes=None, face2frame=None, want_matrix=False):
+        """Enqueue one batch; returns its ticket.  Arrays that are pinned CPU tensors are sent as they are, other arrays are
+        first copied into the slot's pinned staging area (a host memcpy), None sends the staging area as it stands.  Fewer than
+        B boxes: the remaining rows keep their previous (valid) content and their results are to be ignored."""
+        k = self.n_submitted
+        sl = k % self.n_slots
+        src = []
+        for given, stage in zip((frames, boxes, face2frame), self.h_in[sl]):
+            if given is None:
+                src.append(stage)
+                continue
+            t = _as_cpu_tensor(given, stage.dtype)
+            if t.is_pinned() and t.shape == stage.shape:
+                src.append(t)
+            else:
+                if stage.dim() == 2:
+                    t = t.reshape(-1, 4)
+                self.ev_in[sl].synchronize()          # the slot's previous H2D has read the staging area
+                stage[:t.shape[0]].copy_(t)
+                src.append(stage)
+        dev = self.dev
+        with torch.cuda.device(dev):
+            with torch.cuda.stream(self.s_in):
+                self.s_in.wait_event(self.ev_comp[sl])                # the slot's previous compute has consumed its inputs
+                for d, h in zip(self.d_in[sl], src):
+                    d.copy_(h, non_blocking=True)
+                self.ev_in[sl].record(self.s_in)
+            comp = self.s_comp[sl]
+            with torch.cuda.stream(comp):
+                comp.wait_event(self.ev_in[sl])
+                comp.wait_event(self.ev_out[sl])                      # the slot's results have been read out
+                if self.caps is not None:
+                    r = self.caps[sl].replay()
+                else:
+                    r = self.pipe.run_device(*self.d_in[sl], lane=sl)
+                self.ev_comp[sl].record(comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_comp[sl])
+                self.h_out[sl]["marks"].copy_(r["marks"], non_blocking=True)
+                self.h_out[sl]["aligned"].copy_(r["aligned"], non_blocking=True)
+                if want_matrix:
+                    self.h_out[sl]["M"].copy_(r["M"], non_blocking=True)
+                self.ev_out[sl].record(self.s_out)
+        self._src_keep = src                                          # keep caller tensors alive until the copy was enqueued
+        self.n_submitted += 1
+        return k
+
+    def result(self, ticket):
+        """Wait for a ticket's D2H copy and return NumPy views of its slot's pinned result buffers."""
+        if ticket < self.n_submitted - self.n_slots:
+            raise N.FldError("ticket %d: its slot has been reused (%d slots, %d submitted)" % (ticket, self.n_slots, self.n_submitted))
+        sl = ticket % self.n_slots
+        self.ev_out[sl].synchronize()
+        return {k: v.numpy() for k, v in self.h_out[sl].items()}
+
+    def streams(self):
+        return [self.s_in, self.s_out] + self.s_comp
+
+    def drain(self):
+        for ev in self.ev_out:
+            ev.synchronize()
+
+
 def shard_faces(n_faces, n_shards):
     """Contiguous split of a face batch over GPUs: [(start, stop)] per shard."""
     per = -(-n_faces // max(n_shards, 1))
     return [(min(i * per, n_faces), min((i + 1) * per, n_faces)) for i in range(n_shards)]
+
+
+def shard_by_frames(face2frame, n_frames, n_shards):
+    """Split for the alignment path ("for C4, split by frame so each frame is uploaded to exactly one GPU"):
+    face2frame must be non-decreasing.  Returns [(frame_start, frame_stop, face_start, face_stop)] per shard — contiguous frame
+    ranges chosen so that every shard gets about n_faces / n_shards faces and all faces of a frame stay together."""
+    f2f = np.asarray(face2frame)
+    n = len(f2f)
+    assert n == 0 or (np.diff(f2f) >= 0).all(), "face2frame must be sorted (faces grouped by frame)"
+    first = np.searchsorted(f2f, np.arange(n_frames + 1), side="left")      # first face of every frame (and n at the end)
+    out, f0 = [], 0
+    for s in range(n_shards):
+        target = (s + 1) * n / n_shards
+        f1 = n_frames if s == n_shards - 1 else int(np.clip(np.searchsorted(first, target, side="left"), f0, n_frames))
+        if s < n_shards - 1 and f1 > f0 and abs(first[f1 - 1] - target) < abs(first[min(f1, n_frames)] - target):
+            f1 -= 1                                                            # the nearer frame boundary
+        f1 = max(f1, f0)
+        out.append((f0, f1, int(first[f0]), int(first[f1])))
+        f0 = f1
+    return out
+
+
+class MultiGpuPipeline:
+    """One face batch over several GPUs of one box: the faces are split by frame (shard_by_frames), every GPU gets
+    its frames and boxes from the caller's host arrays, runs crop/resize -> CNN -> decode -> fit + warp on its own stream, and
+    copies its results into ITS SLICE of one pinned host buffer — the host-side gather; no collective, no peer traffic.  One
+    worker thread per GPU drives its device (ctypes calls and CUDA copies release the GIL); weights are replicated at
+    construction.  `devices` may name a GPU more than once (two workers then share it)."""
+
+    def __init__(self, model, devices=None, dtype="bfloat16", out_size=(112, 112), template=None):
+        import concurrent.futures
+        if not torch.cuda.is_available():
+            N.handle()
+        self.devices = list(range(torch.cuda.device_count())) if devices is None else [torch.device("cuda", d).index if not isinstance(d, int) else d
+                                                                                       for d in devices]
+        self.out_size = tuple(out_size)
+        # a pipeline (result buffers, lane) per worker; the model object is shared (compiled once per device)
+        self.pipes = [LandmarkPipeline(model, dtype=dtype, out_size=out_size, template=template, device=d) for d in self.devices]
+        self.lanes = [self.devices[:i].count(d) for i, d in enumerate(self.devices)]    # workers on one GPU use different lanes
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=len(self.devices))
+        self._out, self._dev_in = {}, [dict() for _ in self.devices]
+        self.streams = [torch.cuda.Stream(torch.device("cuda", d)) for d in self.devices]
+        import threading
+        self._dev_locks = {d: threading.Lock() for d in set(self.devices)}      # a GPU's handle / net are not thread-safe
+
+    def _host_out(self, name, shape, dtype):
+        t = self._out.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = self._out[name] = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+        return t[:n].view(shape)
+
+    def _worker(self, w, fr, bx, ff, shard, outs):
+        f0, f1, i0, i1 = shard
+        if i1 <= i0:
+            return 0.0
+        dev = torch.device("cuda", self.devices[w])
+        pipe, st, cache = self.pipes[w], self.streams[w], self._dev_in[w]
+        with torch.cuda.device(dev), torch.cuda.stream(st):
+            def to_dev(name, src):
+                d = cache.get(name)
+                if d is None or d.numel() < src.numel():
+                    d = cache[name] = torch.empty(src.numel(), dtype=src.dtype, device=dev)
+                dv = d[:src.numel()].view(src.shape)
+                dv.copy_(src, non_blocking=True)
+                return dv
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            d_fr, d_bx = to_dev("frames", fr[f0:f1]), to_dev("boxes", bx[i0:i1])
+            d_ff = to_dev("f2f", ff[i0:i1]) - f0
+            with self._dev_locks[self.devices[w]]:                               # enqueue only: the GPU work itself runs asynchronously
+                r = pipe.run_device(d_fr, d_bx, d_ff.contiguous(), lane=self.lanes[w])
+            for k, h in outs.items():
+                h[i0:i1].copy_(r[k], non_blocking=True)
+            e1.record(st)
+            st.synchronize()
+            return e0.elapsed_time(e1)
+
+    def run(self, frames, boxes, face2frame):
+        """frames uint8 [F,H,W,3], boxes [B,4], face2frame [B] (non-decreasing) as host arrays (pinned CPU tensors are read in
+        place by the GPUs' copy engines; NumPy / pageable arrays are staged by the driver).  Returns NumPy views of the pinned
+        gather buffers {"marks", "aligned", "M", "faceboxes"} (overwritten by the next run) and sets `last_device_ms` to every
+        worker's device time (copies included)."""
+        fr = _as_cpu_tensor(frames, torch.uint8)
+        if fr.dim() == 3:
+            fr = fr[None]
+        bx = _as_cpu_tensor(boxes, torch.int32).reshape(-1, 4)
+        ff = _as_cpu_tensor(face2frame, torch.int32)
+        B, C = bx.shape[0], fr.shape[3]
+        oh, ow = self.out_size
+        outs = {"marks": self._host_out("marks", (B, 68, 2), torch.float32), "aligned": self._host_out("aligned", (B, oh, ow, C), torch.uint8),
+                "M": self._host_out("M", (B, 2, 3), torch.float64), "faceboxes": self._host_out("faceboxes", (B, 4), torch.int32)}
+        shards = shard_by_frames(ff.numpy(), fr.shape[0], len(self.devices))
+        self.last_shards = shards
+        futs = [self.pool.submit(self._worker, w, fr, bx, ff, shards[w], outs) for w in range(len(self.devices))]
+        self.last_device_ms = [f.result() for f in futs]
+        return {k: v.numpy() for k, v in outs.items()}
+
+    def close(self):
+        self.pool.shutdown(wait=True)
 
 
 # ----------------------------------------------------------------------------------------------- reference API
