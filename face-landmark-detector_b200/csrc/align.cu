@@ -261,10 +261,11 @@ __device__ __forceinline__ void blend4_smem(int bxv, int byv, const int4& a4, co
     // weights w_ij = a_i b_j (<= 1024) as 16-bit pairs: out = (sum_ij w_ij p_ij + 512) >> 10, two IDP.2A per channel
     const uint32_t A16 = fx * 65535u + 32u;          // (32 - fx) | fx << 16
     const uint32_t W01 = (32u - fy) * A16, W23 = fy * A16;
-    const uint32_t S0 = __dp2a_hi(W23, P0, __dp2a_lo(W01, P0, 512u));
-    const uint32_t S1 = __dp2a_hi(W23, P1, __dp2a_lo(W01, P1, 512u));
-    const uint32_t S2 = __dp2a_hi(W23, P2, __dp2a_lo(W01, P2, 512u));
-    q[j] = prmt(prmt(S0 >> 10, S1 >> 10, 0x0040u), S2 >> 10, 0x0410u);
+    // (S + 512) >> 10 is byte 2 of (S + 512) * 64: the multiply runs on the FMA pipe, which is idle next to the ALU pipe here
+    const uint32_t S0 = __dp2a_hi(W23, P0, __dp2a_lo(W01, P0, 512u)) * 64u;
+    const uint32_t S1 = __dp2a_hi(W23, P1, __dp2a_lo(W01, P1, 512u)) * 64u;
+    const uint32_t S2 = __dp2a_hi(W23, P2, __dp2a_lo(W01, P2, 512u)) * 64u;
+    q[j] = prmt(prmt(S0, S1, 0x0062u), S2, 0x0610u);
   }
   w[0] = prmt(q[0], q[1], 0x4210u);
   w[1] = prmt(q[1], q[2], 0x5421u);
@@ -589,7 +590,9 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
     a.F = F; a.H = H; a.W = W; a.N = N; a.five_point = five_point; a.out_h = out_h; a.out_w = out_w;
     // split a face's tile rows over several CTAs while the grid would otherwise be only a few waves deep
     const int tiles_y = out_h / kTile;
-    a.ysplit = ((long long)B < 8ll * 8 * h->sm_count) ? tiles_y : 1;
+    // measured on C4 (4096 faces): 2 CTAs per face 0.199 ms, 1: 0.211, 4: 0.218, 7: 0.277 (the per-CTA fit + tables then dominate):
+    // aim at ~8 k CTAs, i.e. a few waves of the ~1000 resident ones
+    a.ysplit = (int)std::max(1ll, std::min((long long)tiles_y, (8192ll + B - 1) / B));
     { const char* e = getenv("FLD_ALIGN_YSPLIT"); if (e && atoi(e) > 0) a.ysplit = std::min(tiles_y, atoi(e)); }
     const size_t smem = kRingBytes + 128 + 32;
     FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -431,16 +431,16 @@ extern "C" int fld_net_finalize(fld_net* net) {
   return FLD_OK;
 }
 
-// split-K factor of the tensor-core dense layer: the largest divisor of the k-chunk count that keeps the grid within one wave
-// and leaves at least two k-blocks per CTA
-static int dense_ksplit(const fld_net* net, int B, int kchunks) {
-  const int mtiles = (B + 127) / 128;
+// split-K factor of the tensor-core dense layer: the largest divisor of the k-chunk count <= 32 that leaves at least two k-blocks
+// per slice.  It must NOT depend on the batch: a face's result has to be bit-identical whatever batch (chunk, shard) it runs in,
+// and the slice boundaries fix the summation order.  For the same reason every batch size takes this path.
+static int dense_ksplit(const fld_net*, int, int kchunks) {
   int best = 1;
-  for (int s = 1; s <= kchunks; ++s)
-    if (kchunks % s == 0 && s * mtiles <= net->h->sm_count && kchunks / s >= 2) best = s;
+  for (int s = 1; s <= 32 && s <= kchunks; ++s)
+    if (kchunks % s == 0 && kchunks / s >= 2) best = s;
   return best;
 }
-constexpr int kDenseTcMinBatch = 64;
+constexpr int kDenseTcMinBatch = 1;
 
 static size_t dense_scratch_bytes(const fld_net* net, int B) {
   size_t m = 0;

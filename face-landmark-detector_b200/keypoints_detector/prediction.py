@@ -457,7 +457,8 @@ class MultiGpuPipeline:
         self.out_size = tuple(out_size)
         # a pipeline (result buffers, lane) per worker; the model object is shared (compiled once per device)
         self.pipes = [LandmarkPipeline(model, dtype=dtype, out_size=out_size, template=template, device=d) for d in self.devices]
-        self.lanes = [self.devices[:i].count(d) for i, d in enumerate(self.devices)]    # workers on one GPU use different lanes
+        # workers sharing a GPU use different lanes; lanes 16.. keep clear of the ones HostStream / captured graphs pin
+        self.lanes = [16 + self.devices[:i].count(d) for i, d in enumerate(self.devices)]
         self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=len(self.devices))
         self._out, self._dev_in = {}, [dict() for _ in self.devices]
         self.streams = [torch.cuda.Stream(torch.device("cuda", d)) for d in self.devices]

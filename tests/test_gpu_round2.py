@@ -372,3 +372,99 @@ def test_regression_net_bf16x3(dev, B):
         got = m.intermediate(xt, t, "bf16x3").cpu().numpy()
         scale = np.abs(levels[t - 1]).max()
         assert np.abs(got - levels[t - 1]).max() < 5e-5 * scale, (t, np.abs(got - levels[t - 1]).max() / scale)
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer product API
+def test_run_host_and_host_stream_match_run_device(dev):
+    """The host-array entry points (reference boundary: host arrays in and out, prediction.py:16-113) give exactly what the
+    device-resident path gives: run_host (one shot, pageable or pinned inputs) and HostStream (overlapped copy / compute / copy
+    over three slots, one captured CUDA graph per slot, pinned or NumPy inputs, short batches, ticket expiry)."""
+    from keypoints_detector import _native as N, prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = landmark_regressor().init_weights(seed=4)
+    pipe = prediction.LandmarkPipeline(m, dtype="bfloat16")
+    B, F, H, W = 24, 2, 480, 640
+    sets = []
+    for k in range(5):
+        frames = synthetic.make_frames(F, H, W, seed=70 + k)
+        boxes = synthetic.make_boxes(B, H, W, seed=80 + k, max_side=300)
+        f2f = (np.arange(B) % F).astype(np.int32)
+        r = pipe.run_device(T(frames, dev), T(boxes, dev), T(f2f, dev), lane=6)
+        sets.append((frames, boxes, f2f, {k_: r[k_].cpu().numpy().copy() for k_ in ("marks", "aligned", "M")}))
+    for frames, boxes, f2f, ref in sets[:2]:
+        got = pipe.run_host(frames, boxes, f2f)
+        for k_ in ref:
+            assert np.array_equal(got[k_], ref[k_]), k_
+    got = pipe.run_host(torch.from_numpy(sets[2][0]).pin_memory(), sets[2][1], sets[2][2])          # pinned frames are sent as they are
+    assert np.array_equal(got["aligned"], sets[2][3]["aligned"])
+    hs = prediction.HostStream(pipe, batch=B, n_frames=F, frame_hw=(H, W), n_slots=3)
+    tickets = []
+    for k in range(11):
+        frames, boxes, f2f, _ = sets[k % 5]
+        if k % 2:
+            tickets.append(hs.submit(torch.from_numpy(frames).pin_memory(), torch.from_numpy(boxes).pin_memory(), torch.from_numpy(f2f).pin_memory(),
+                                     want_matrix=True))
+        else:
+            tickets.append(hs.submit(frames, boxes, f2f, want_matrix=True))
+        if k >= 2:                                                              # read a result two submits later: its slot is still intact
+            r = hs.result(tickets[k - 2])
+            ref = sets[(k - 2) % 5][3]
+            for k_ in ref:
+                assert np.array_equal(r[k_], ref[k_]), (k, k_)
+    with pytest.raises(N.FldError):
+        hs.result(tickets[3])                                                   # that slot has been reused
+    # short batch through the staging area: rows beyond the given boxes keep older (valid) content, the first rows are right
+    fr, bx, ff = hs.inputs(hs.next_slot())
+    fr[:] = sets[4][0]
+    t = hs.submit(None, sets[4][1][:7], sets[4][2][:7])
+    r = hs.result(t)
+    assert np.array_equal(r["marks"][:7], sets[4][3]["marks"][:7]) and np.array_equal(r["aligned"][:7], sets[4][3]["aligned"][:7])
+    hs.drain()
+
+
+def test_multi_gpu_pipeline_gathers_shards(dev):
+    """MultiGpuPipeline: one batch, faces split by frame over the workers (all GPUs of the box; on a 1-GPU box three workers share
+    the GPU on different lanes and streams), results gathered into one pinned host buffer — bit-identical to a single run."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = landmark_regressor().init_weights(seed=9)
+    F, H, W = 5, 360, 480
+    counts = [40, 0, 64, 7, 33]                                               # faces per frame: uneven on purpose
+    f2f = np.repeat(np.arange(F), counts).astype(np.int32)
+    Bn = len(f2f)
+    frames = synthetic.make_frames(F, H, W, seed=91)
+    boxes = synthetic.make_boxes(Bn, H, W, seed=92, min_side=80, max_side=220)
+    ref = prediction.LandmarkPipeline(m, dtype="bfloat16").run_device(T(frames, dev), T(boxes, dev), T(f2f, dev))
+    ref = {k: ref[k].cpu().numpy() for k in ("marks", "aligned", "M", "faceboxes")}
+    n = torch.cuda.device_count()
+    devices = list(range(n)) if n > 1 else [0, 0, 0]
+    mg = prediction.MultiGpuPipeline(m, devices=devices, dtype="bfloat16")
+    for rep in range(2):
+        got = mg.run(frames, boxes, f2f) if rep == 0 else mg.run(torch.from_numpy(frames).pin_memory(), boxes, f2f)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k]), (rep, k)
+    sh = mg.last_shards
+    assert sh[0][0] == 0 and sh[-1][1] == F and sh[-1][3] == Bn and all(a[1] == b[0] and a[3] == b[2] for a, b in zip(sh[:-1], sh[1:]))
+    assert len(mg.last_device_ms) == len(devices)
+    mg.close()
+
+
+def test_dense_on_tensor_cores_matches_fp32_dense(dev):
+    """bf16 mode: Flatten + Dense runs as a split-K tcgen05 GEMM (partials reduced in a fixed order) at every batch size.  Against
+    a dense in fp64 on the same bf16 activations and bf16-rounded weights it agrees to accumulation-order noise, it is
+    deterministic run to run, and a face's result does not depend on the batch it runs in (bit-identical in a batch of 8)."""
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = landmark_regressor().init_weights(seed=12)
+    rng = np.random.default_rng(12)
+    for Bn in (20, 200, 256):
+        x = T(rng.integers(0, 256, (Bn, 128, 128, 3), dtype=np.uint8), dev)
+        out = m.forward_device(x, "bfloat16")
+        f5 = m.intermediate(x, 5, "bfloat16").reshape(Bn, -1)                       # bf16 activations feeding the dense layer
+        wk = torch.from_numpy(m.weights["fc/kernel"]).to(dev)
+        ref = f5.double() @ wk.bfloat16().double() + torch.from_numpy(m.weights["fc/bias"]).to(dev).double()
+        assert (out.double() - ref).abs().max().item() < 2e-5, (Bn, (out.double() - ref).abs().max().item())
+        assert torch.equal(out, m.forward_device(x, "bfloat16"))
+        assert torch.equal(m.forward_device(x[:8].contiguous(), "bfloat16"), out[:8])
+        assert torch.equal(m.forward_device(x[Bn - 3:].contiguous(), "bfloat16"), out[Bn - 3:])
