@@ -23,9 +23,11 @@ def main():
     marks_f, _ = prediction.detect_marks_batch(frame[None], [face], [0], model)
     crop, M = prediction.align_faces(frame, marks_f, return_matrix=True)    # (1, 112, 112, 3) uint8
     print("aligned crop", crop.shape, crop.dtype, "M =", np.round(M[0], 4).tolist())
-    model.compute_dtype = "bfloat16"                                         # tensor-core path
-    marks_bf = prediction.detect_marks_batch(frame[None], [face], [0], model)[0]
-    print("max |fp32 - bf16| landmark delta: %.4f px" % np.abs(marks_bf - marks_f).max())
+    # compute modes: "bf16x3" (default: fp32-accurate tensor cores), "float32" (CUDA cores, the reference's arithmetic),
+    # "bfloat16" (plain bf16 tensor cores, fastest)
+    for mode in ("float32", "bfloat16"):
+        m = prediction.detect_marks_batch(frame[None], [face], [0], model, dtype=mode)[0]
+        print("max |%s - bf16x3| landmark delta: %.5f px" % (mode, np.abs(m - marks_f).max()))
 
 
 if __name__ == "__main__":

@@ -2,9 +2,11 @@
 
 Layer names are the reference's: conv1 / bn_conv1, res{stage}{block}_branch{2a,2b,2c,1} / bn{stage}{block}_branch...
 Every conv carries a bias (Keras default) and is followed by a BatchNormalization, folded here; the residual
-`add -> relu` (:68-69, :117-118) is one ADD layer with a ReLU epilogue.  Stride-2 1x1 convs (first conv of the main
-branch and the shortcut, :98,110) and the 7x7 stride-2 stem run on the strided CUDA-core conv; every stride-1 conv
-with Cin % 64 == 0 runs on the tensor cores in bf16 mode.
+`add -> relu` (:68-69, :117-118) is one ADD layer with a ReLU epilogue.  In bf16 mode every conv runs on the tensor cores:
+the 7x7 stride-2 stem through shared-memory im2col (csrc/tc_conv_stem.cu), the stride-2 1x1 convs (first conv of the main
+branch and the shortcut, :98,110) through TMA element strides that pick every second pixel (csrc/tc_conv.cu), the stride-1
+convs (Cin % 64 == 0) through the halo / per-tap TMA kernels.  The 3x3/2 max-pool and the residual adds are 16-byte
+vectorised CUDA-core kernels (csrc/simt_extra.cu).
 
 Levels: the reference returns f1 = conv1 output BEFORE bn_conv1 (:147) and f2 = one_side_pad(stage 2) (:153); no FCN
 head of the reference consumes them (fcn_8 uses f3, f4, f5; fcn_32 uses f5), so f1 / f2 here are the tensors after

@@ -165,9 +165,9 @@ class LandmarkPipeline:
     """frames + detector boxes -> 68 landmarks -> aligned crops, entirely on one GPU:
     crop/resize (a1) -> regression CNN (a2) -> decode (a3) -> Umeyama + warp (a10)."""
 
-    def __init__(self, model, dtype="float32", out_size=(112, 112), template=None, device=None):
+    def __init__(self, model, dtype=None, out_size=(112, 112), template=None, device=None):
         self.model = model
-        self.dtype = dtype
+        self.dtype = dtype or model.compute_dtype        # default: the model's mode ("bf16x3": fp32-accurate tensor cores)
         self.out_size = tuple(out_size)
         self.template = TEMPLATE_112 if template is None else np.asarray(template, dtype=np.float64)
         self.device = _device(device)
