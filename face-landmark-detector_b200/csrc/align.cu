@@ -238,6 +238,7 @@ struct TileArgs {
   double* M_out;
   uint8_t* crops;
   int F, H, W, N, five_point, out_h, out_w, ysplit;
+  int ring_bytes;   // dynamic shared memory of the box ring (multiple of 256)
 };
 
 // Blend of four consecutive output pixels from the staged source box.  bxv / byv: the row's X0 / Y0; av / bv: adelta / bdelta of
@@ -319,6 +320,7 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
       const int side = (int)ceil(e);
       for (int k = 0; k < kNumCls; ++k) if (side <= cls_side(k)) { cls = k; break; }
     }
+    if (cls >= 0 && (cls_bw(cls) * cls_side(cls) + 16 + 127) / 128 * 128 > p.ring_bytes) cls = -1;   // box larger than the ring: global path
     s_cls = cls;
   }
   __syncthreads();
@@ -348,10 +350,10 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   const size_t row = (size_t)p.W * 3;
   const uint32_t box_bytes = (uint32_t)(BW * BH);
   const uint32_t buf_pitch = (box_bytes + 16u + 127u) & ~127u;       // + 16: the last pixel's third word may lie past the box
-  const uint32_t half_ring = (uint32_t)(kRingBytes / 2) & ~127u;
+  const uint32_t half_ring = (uint32_t)(p.ring_bytes / 2) & ~127u;
   const bool solo = cls >= 0 && buf_pitch > half_ring;               // one warp, whole ring
   if (solo && warp != 0) return;
-  const int nbuf = cls < 0 ? 1 : solo ? max(1, min(kMaxBuf, (int)(kRingBytes / buf_pitch))) : max(1, min(kMaxBuf, (int)(half_ring / buf_pitch)));
+  const int nbuf = cls < 0 ? 1 : solo ? max(1, min(kMaxBuf, (int)(p.ring_bytes / buf_pitch))) : max(1, min(kMaxBuf, (int)(half_ring / buf_pitch)));
   const uint32_t my_ring = solo ? ring : ring + warp * half_ring;
   const uint32_t my_bar = smem_u32(&full_bar[warp][0]);
   const int t_first = solo ? 0 : warp, t_step = solo ? 1 : 2;
@@ -594,7 +596,9 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
     // aim at ~8 k CTAs, i.e. a few waves of the ~1000 resident ones
     a.ysplit = (int)std::max(1ll, std::min((long long)tiles_y, (8192ll + B - 1) / B));
     { const char* e = getenv("FLD_ALIGN_YSPLIT"); if (e && atoi(e) > 0) a.ysplit = std::min(tiles_y, atoi(e)); }
-    const size_t smem = kRingBytes + 128 + 32;
+    a.ring_bytes = kRingBytes;
+    { const char* e = getenv("FLD_ALIGN_RING_KB"); if (e && atoi(e) >= 4 && atoi(e) <= 200) a.ring_bytes = atoi(e) * 1024; }
+    const size_t smem = (size_t)a.ring_bytes + 128 + 32;
     FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     align_tile_kernel<<<dim3(B, a.ysplit), kTileThreads, smem, st>>>(maps, a);

@@ -24,6 +24,7 @@ enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
 struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; };
+struct Px8PlanEntry { int B; const void* scratch; TcPx8Plan* plan; };
 
 struct LayerRt {
   fld_layer_desc d;
@@ -31,6 +32,7 @@ struct LayerRt {
   int path = PATH_SIMT;
   int cout_pad = 0;
   bool x3 = false;              // FLD_BF16X3 tensor-core conv: SPLIT input, weights packed [w_hi | w_hi | w_lo]
+  bool px8 = false;             // first layer through tc_conv_px8.cu (TMA-built A operand) instead of tc_conv_first.cu
   bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
   bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
   bool needs_weights = false, has_weights = false;
@@ -43,6 +45,7 @@ struct LayerRt {
   std::vector<PlanEntry> plans;
   std::vector<HaloPlanEntry> hplans;
   std::vector<DeconvPlanEntry> dplans;
+  std::vector<Px8PlanEntry> pplans;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -225,6 +228,8 @@ void free_layer(LayerRt& L) {
   L.hplans.clear();
   for (auto& pe : L.dplans) tc_deconv_plan_destroy(pe.plan);
   L.dplans.clear();
+  for (auto& pe : L.pplans) tc_conv_px8_plan_destroy(pe.plan);
+  L.pplans.clear();
   L.d_w = nullptr; L.d_bias = nullptr; L.d_wbf = nullptr; L.plans.clear();
 }
 
@@ -392,6 +397,13 @@ extern "C" int fld_net_finalize(fld_net* net) {
       tc_conv_stem_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), L.d.kh, Cout, f2bf, pk.data());
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (L.path == PATH_TC_FIRST && tc_conv_px8_supported(L.g) && (a.dtype == FLD_U8 || !L.x3)) {
+      // tc_conv_px8.cu: K group = tap, 8 channel slots per tap; the bias stays in d_bias (epilogue add)
+      L.px8 = true;
+      std::vector<uint16_t> pk((size_t)Cout * 8 * (L.x3 ? 20 : 10), 0);
+      tc_conv_px8_pack(L.w_host.data(), Cout, f2bf, pk.data(), L.x3 ? 1 : 0);
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
       // core-matrix packed [6 kgroups][Cout/8][8][8], k' = kh*12 + kw*4 + c (see tc_conv_first.cu)
       const int kg = L.x3 ? 10 : 6;
@@ -451,6 +463,7 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
     if (L.d.op == FLD_OP_DENSE && L.path == PATH_TC_TMA)
       m = std::max(m, (size_t)dense_ksplit(net, B, (int)a.elems() / 64) * B * L.d.cout * sizeof(float));
+    if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && tc_conv_px8_supported(L.g)) m = std::max(m, tc_conv_px8_scratch_bytes(L.g, B));
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
       m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
   }
@@ -533,6 +546,16 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
       case FLD_OP_CONV:
         if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
           rc = tc_conv_stem(net->h, pin, a.dtype, L.d_wbf, (__nv_bfloat16*)pout, L.g, B, st);
+        } else if (L.path == PATH_TC_FIRST && L.px8) {
+          TcPx8Plan* plan = nullptr;
+          for (auto& pe : L.pplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
+          if (!plan) {
+            rc = tc_conv_px8_plan_create(net->h, dense_scratch, a.dtype, L.g, B, L.x3 ? 1 : 0, o.dtype == FLD_BF16X3 ? 1 : 0, &plan);
+            if (rc) return rc;
+            if (L.pplans.size() >= 16 && net->retained == 0) { tc_conv_px8_plan_destroy(L.pplans.front().plan); L.pplans.erase(L.pplans.begin()); }
+            L.pplans.push_back({B, (const void*)dense_scratch, plan});
+          }
+          rc = tc_conv_px8_run(plan, pin, L.d_wbf, L.d_bias, pout, st);
         } else if (L.path == PATH_TC_FIRST) {
           rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st, L.x3 ? 1 : 0);
         } else if (L.path == PATH_TC_TMA && (o.dtype == FLD_BF16 || o.dtype == FLD_BF16X3) && tc_halo_supported(L.g, L.cout_pad)) {
