@@ -5,9 +5,12 @@
 // Round 1's kernel (tc_conv_first.cu) built the im2col rows with per-thread shared-memory gathers: ~470 instructions per thread
 // per 128-pixel tile, i.e. issue-bound at 0.105 ms per 256 faces against a TMEM-read floor of 0.059 ms.  Here the image is first
 // widened to 8 bf16 channels per pixel (RGB + 5 zeros = 16 bytes, one pass, stays in L2) so that ONE K group of the UMMA
-// no-swizzle K-major layout (8 elements = 16 bytes per row) is exactly one tap of one pixel: the A tile of a tap is a plain TMA
-// box [8 ch][8 px][16 px] whose rows land 16 bytes apart — the core-matrix layout the tensor core reads — and the convolution's
-// zero padding is the tensor map's out-of-bounds fill.  Nine boxes per tile, no thread touches an operand.
+// no-swizzle K-major layout (8 elements = 16 bytes per row) is exactly one tap of one pixel.  ONE TMA box per tile brings the
+// (16 + 2) x (8 + 2)-pixel halo patch (18 rows of 160 bytes; out-of-bounds fill = the convolution's zero padding); the nine
+// taps are nine UMMA descriptors INTO that patch: start shifted by (ky * 10 + kx) pixels, stride between 8-row core matrices
+// = one patch row (160 B), and — K = 16 per MMA = two taps — a leading-dimension offset equal to the distance between the two
+// taps' starts (16 B, or 128 B across a patch row).  No thread touches an operand.  (A first version with nine [8 ch][8 px][16 px]
+// boxes per tile was TMA-request bound — 1152 sixteen-byte rows per tile — and slower than round 1's kernel: 0.20 ms.)
 //
 // Roles (320 threads, one persistent CTA per SM): warp 0 TMA producer (ring of A stages), warp 1 MMA issuer (K = 16 per MMA =
 // two taps; the tenth K group is a zero block), warps 2-9 epilogue (TMEM -> bias + ReLU + 2x2 pool -> bf16 / SPLIT store), two
@@ -20,9 +23,12 @@
 namespace {
 using namespace tc;
 
-constexpr int kGroupBytes = 128 * 16;            // one K group of the A tile: 128 rows x 16 B
 constexpr int kAGroups = 10;                     // 9 taps + 1 zero group (K = 80)
-constexpr int kStageBytes = kAGroups * kGroupBytes;
+constexpr int kPatchW = 10, kPatchH = 18;        // halo patch of an 8 x 16 tile, 16 B per pixel
+constexpr int kRowBytes = kPatchW * 16;          // 160
+constexpr int kPatchBytes = kPatchH * kRowBytes; // 2880
+constexpr int kStageBytes = 3072;                // patch rounded up to the 128-byte TMA destination alignment
+constexpr int kZeroBytes = 16 * kRowBytes;       // zero K group: 16 core matrices at the same 160-byte stride
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
@@ -46,20 +52,19 @@ conv_px8_kernel(const __grid_constant__ CUtensorMap tmA, const Px8Params p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int KGB = p.x3 ? 2 * kAGroups : kAGroups;
-  const uint32_t smemA = smem_base;                                       // stages x [10 groups][128 rows][16 B]
-  const uint32_t smemB = smem_base + p.stages * kStageBytes;               // [KGB][Cout/8][8][16 B]
+  const uint32_t smemA = smem_base;                                       // stages x halo patch [18][10 px][16 B]
+  const uint32_t smemZ = smem_base + p.stages * kStageBytes;               // zero K group
+  const uint32_t smemB = smemZ + kZeroBytes;                               // [KGB][Cout/8][8][16 B]
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
 
-  {  // weights (already in core-matrix order) and the all-zero tenth K group of every A stage
+  {  // weights (already in core-matrix order) and the all-zero tenth K group
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint8_t* gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    uint4* dstB = reinterpret_cast<uint4*>(gen + p.stages * kStageBytes);
+    uint4* z = reinterpret_cast<uint4*>(gen + p.stages * kStageBytes);
+    for (int i = tid; i < kZeroBytes / 16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* dstB = reinterpret_cast<uint4*>(gen + p.stages * kStageBytes + kZeroBytes);
     for (int i = tid; i < p.Cout * KGB; i += kThreads) dstB[i] = src[i];
-    for (int s = 0; s < p.stages; ++s) {
-      uint4* z = reinterpret_cast<uint4*>(gen + s * kStageBytes + (kAGroups - 1) * kGroupBytes);
-      for (int i = tid; i < kGroupBytes / 16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -85,11 +90,8 @@ conv_px8_kernel(const __grid_constant__ CUtensorMap tmA, const Px8Params p) {
         const int ty = m / p.tiles_x, tx = m - ty * p.tiles_x;
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t fb = full0 + 8 * stage;
-        mbar_arrive_expect_tx(fb, 9u * kGroupBytes);
-        const uint32_t sa = smemA + stage * kStageBytes;
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-          tma_load_4d(sa + t * kGroupBytes, &tmA, fb, 0, tx * 8 + (t % 3) - 1, ty * 16 + (t / 3) - 1, b);
+        mbar_arrive_expect_tx(fb, (uint32_t)kPatchBytes);
+        tma_load_3d(smemA + stage * kStageBytes, &tmA, fb, (tx * 8 - 1) * 8, ty * 16 - 1, b);   // inner coordinate in bf16 elements
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -99,9 +101,10 @@ conv_px8_kernel(const __grid_constant__ CUtensorMap tmA, const Px8Params p) {
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.Cout);
       const uint32_t b_lbo = (uint32_t)(p.Cout / 8) * 128;                 // distance between K groups of B
-      const uint64_t adesc0 = umma_desc(smemA, kGroupBytes, 128, 0);       // K-major, no swizzle: LBO = next K group, SBO = next 8 rows
-      const uint64_t bdesc0 = umma_desc(smemB, b_lbo, 128, 0);
-      const uint64_t astep = (uint64_t)((2 * kGroupBytes) >> 4), bstep = (uint64_t)((2 * b_lbo) >> 4);
+      const uint64_t bdesc0 = umma_desc(smemB, b_lbo, 128, 0);             // K-major, no swizzle: LBO = next K group, SBO = next 8 rows
+      const uint64_t bstep = (uint64_t)((2 * b_lbo) >> 4);
+      // tap t starts (t / 3) patch rows + (t % 3) pixels into the patch
+      auto tap_off = [](int t) { return (uint32_t)(((t / 3) * kPatchW + (t % 3)) * 16); };
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
@@ -109,12 +112,20 @@ conv_px8_kernel(const __grid_constant__ CUtensorMap tmA, const Px8Params p) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * 256;
-        const uint64_t ad = adesc0 + (uint64_t)((stage * kStageBytes) >> 4);
+        const uint32_t patch = smemA + stage * kStageBytes;
+        uint64_t ad[kAGroups / 2];
 #pragma unroll
-        for (int m = 0; m < kAGroups / 2; ++m) umma_bf16(d, ad + m * astep, bdesc0 + m * bstep, idesc, m ? 1u : 0u);
+        for (int m = 0; m < kAGroups / 2; ++m) {
+          const uint32_t s0 = patch + tap_off(2 * m);
+          // K = 16 = taps 2m and 2m + 1: the second K group starts LBO bytes after the first; the tenth group is the zero block
+          const uint32_t lbo = (2 * m + 1 < 9) ? tap_off(2 * m + 1) - tap_off(2 * m) : smemZ - s0;
+          ad[m] = umma_desc(s0, lbo, kRowBytes, 0);                        // SBO: next 8 tile pixels = next patch row
+        }
+#pragma unroll
+        for (int m = 0; m < kAGroups / 2; ++m) umma_bf16(d, ad[m], bdesc0 + m * bstep, idesc, m ? 1u : 0u);
         if (p.x3) {   // the same activations against the lo halves of the weights
 #pragma unroll
-          for (int m = 0; m < kAGroups / 2; ++m) umma_bf16(d, ad + m * astep, bdesc0 + (kAGroups / 2 + m) * bstep, idesc, 1u);
+          for (int m = 0; m < kAGroups / 2; ++m) umma_bf16(d, ad[m], bdesc0 + (kAGroups / 2 + m) * bstep, idesc, 1u);
         }
         umma_commit(empty0 + 8 * stage);
         umma_commit(tfull0 + 8 * acc);
@@ -252,15 +263,16 @@ int tc_conv_px8_plan_create(const fld_handle* h, void* scratch, int in_dtype, co
   p.tiles_x = fld_div_up(g.OW, 8); p.tiles_y = fld_div_up(g.OH, 16);
   p.total_tiles = B * p.tiles_x * p.tiles_y;
   const size_t bbytes = (size_t)g.Cout * 16 * (x3 ? 2 * kAGroups : kAGroups);
-  p.stages = (int)std::max<size_t>(2, std::min<size_t>(kMaxStages, (200 * 1024 - bbytes) / kStageBytes));
-  pl->smem = (size_t)p.stages * kStageBytes + bbytes + 1024;
+  p.stages = kMaxStages;
+  pl->smem = (size_t)p.stages * kStageBytes + kZeroBytes + bbytes + 1024;
   pl->grid = std::min(p.total_tiles, h->sm_count);
   pl->scratch = scratch; pl->in_dtype = in_dtype;
-  cuuint64_t dims[4] = {8, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)B};
-  cuuint64_t strides[3] = {16, (cuuint64_t)g.IW * 16, (cuuint64_t)g.IH * g.IW * 16};
-  cuuint32_t box[4] = {8, 8, 16, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, scratch, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  // the widened image as rows of W * 8 bf16 elements: a box row is 10 pixels = 160 contiguous bytes
+  cuuint64_t dims[3] = {(cuuint64_t)g.IW * 8, (cuuint64_t)g.IH, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)g.IW * 16, (cuuint64_t)g.IH * g.IW * 16};
+  cuuint32_t box[3] = {(cuuint32_t)kPatchW * 8, (cuuint32_t)kPatchH, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, scratch, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(px8 A) failed: %d", (int)r); return FLD_ERR_CUDA; }
   *out = pl;
