@@ -401,7 +401,7 @@ extern "C" int fld_net_finalize(fld_net* net) {
       // tc_conv_px8.cu: K group = tap, 8 channel slots per tap; the bias stays in d_bias (epilogue add)
       L.px8 = true;
       std::vector<uint16_t> pk((size_t)Cout * 8 * (L.x3 ? 20 : 10), 0);
-      tc_conv_px8_pack(L.w_host.data(), Cout, f2bf, pk.data(), L.x3 ? 1 : 0);
+      tc_conv_px8_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data(), L.x3 ? 1 : 0);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {

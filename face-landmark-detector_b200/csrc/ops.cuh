@@ -46,7 +46,7 @@ void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_ho
 struct TcPx8Plan;
 bool tc_conv_px8_supported(const ConvGeom& g);
 size_t tc_conv_px8_scratch_bytes(const ConvGeom& g, int B);
-void tc_conv_px8_pack(const float* w_host /*[27][Cout]*/, int Cout, uint16_t (*f2bf)(float), uint16_t* out /*[Cout*8*(x3 ? 20 : 10)]*/, int x3);
+void tc_conv_px8_pack(const float* w_host /*[27][Cout]*/, const float* bias_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out /*[Cout*8*(x3 ? 20 : 10)]*/, int x3);
 int tc_conv_px8_plan_create(const fld_handle* h, void* scratch, int in_dtype, const ConvGeom& g, int B, int x3, int split_out, TcPx8Plan** out);
 void tc_conv_px8_plan_destroy(TcPx8Plan* p);
 int tc_conv_px8_run(const TcPx8Plan* p, const void* in, const __nv_bfloat16* w_packed, const float* bias, void* out, cudaStream_t st);

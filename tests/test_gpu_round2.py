@@ -468,3 +468,27 @@ def test_dense_on_tensor_cores_matches_fp32_dense(dev):
         assert torch.equal(out, m.forward_device(x, "bfloat16"))
         assert torch.equal(m.forward_device(x[:8].contiguous(), "bfloat16"), out[:8])
         assert torch.equal(m.forward_device(x[Bn - 3:].contiguous(), "bfloat16"), out[Bn - 3:])
+
+
+def test_px8_first_layer_opt_in(dev, monkeypatch):
+    """csrc/tc_conv_px8.cu (first layer with a TMA-built operand: one halo patch per tile, taps as shifted UMMA descriptors, bias
+    through a K group) is opt-in because it measured slower than the default kernel; it must stay correct: same bars as the
+    default first layer in bf16 and bf16x3 mode, pooled and un-pooled (VGG block1_conv1), against the fp64 oracle."""
+    from keypoints_detector.networks.regression import landmark_regressor
+    from oracle import cnn as o_cnn
+    monkeypatch.setenv("FLD_C1_PX8", "1")
+    m = landmark_regressor().init_weights(7)
+    rng = np.random.default_rng(7)
+    x = rng.integers(0, 256, (9, 128, 128, 3), dtype=np.uint8)
+    ref = o_cnn.regression_forward(x, m.weights, torch.float64)
+    lv = o_cnn.trunk_forward(x.astype(np.float64), m.weights, torch.float64, scale=1 / 255.0)[0]
+    xt = T(x, dev)
+    for dtype, tol_out, tol_l1 in (("bfloat16", 1.25e-3, 3e-2), ("bf16x3", 1.25e-4, 5e-5)):
+        out = m.forward_device(xt, dtype).cpu().numpy()
+        assert np.abs(out - ref).max() < tol_out, (dtype, np.abs(out - ref).max())
+        got = m.intermediate(xt, 1, dtype).cpu().numpy()
+        assert np.abs(got - lv).max() < tol_l1 * np.abs(lv).max(), (dtype, np.abs(got - lv).max() / np.abs(lv).max())
+    monkeypatch.delenv("FLD_C1_PX8")
+    m2 = landmark_regressor().init_weights(7)
+    a, b = m2.forward_device(xt, "bfloat16"), m.forward_device(xt, "bfloat16")
+    assert (a - b).abs().max().item() < 1e-3            # default kernel vs opt-in kernel: same bf16 operands, different bias rounding
