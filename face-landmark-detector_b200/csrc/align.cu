@@ -132,11 +132,14 @@ __device__ __forceinline__ void cta_fit(Fit& fit, int face, int F, const int32_t
 
 __device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
 
-// cv2's fixed-point coordinate tables (App. B.2 step 2)
-__device__ __forceinline__ int tab_ad(const Fit& fit, int x) { return (int)__double2ll_rn(dm(dm(fit.iM[0], (double)x), 1024.0)); }
-__device__ __forceinline__ int tab_bd(const Fit& fit, int x) { return (int)__double2ll_rn(dm(dm(fit.iM[3], (double)x), 1024.0)); }
-__device__ __forceinline__ int tab_X0(const Fit& fit, int y) { return (int)__double2ll_rn(dm(da(dm(fit.iM[1], (double)y), fit.iM[2]), 1024.0)) + 16; }
-__device__ __forceinline__ int tab_Y0(const Fit& fit, int y) { return (int)__double2ll_rn(dm(da(dm(fit.iM[4], (double)y), fit.iM[5]), 1024.0)) + 16; }
+// cv2's fixed-point coordinate tables (App. B.2 step 2): saturate_cast<int>(rint(v)).  In range (|v| < 2^31, i.e. source coordinates
+// below 2 M pixels) the native F2I.S32.F64 conversion is exact; beyond it cv2 itself returns INT_MIN garbage — reproduced here so
+// that the 64-bit conversion (a ~20-instruction emulation per table entry) is not needed.
+__device__ __forceinline__ int cv_round(double v) { return (v >= -2147483648.0 && v < 2147483648.0) ? __double2int_rn(v) : INT_MIN; }
+__device__ __forceinline__ int tab_ad(const Fit& fit, int x) { return cv_round(dm(dm(fit.iM[0], (double)x), 1024.0)); }
+__device__ __forceinline__ int tab_bd(const Fit& fit, int x) { return cv_round(dm(dm(fit.iM[3], (double)x), 1024.0)); }
+__device__ __forceinline__ int tab_X0(const Fit& fit, int y) { return cv_round(dm(da(dm(fit.iM[1], (double)y), fit.iM[2]), 1024.0)) + 16; }
+__device__ __forceinline__ int tab_Y0(const Fit& fit, int y) { return cv_round(dm(da(dm(fit.iM[4], (double)y), fit.iM[5]), 1024.0)) + 16; }
 
 // six consecutive bytes starting at an arbitrary address, from two aligned 8-byte loads
 __device__ __forceinline__ uint64_t load6(const uint8_t* p) {
@@ -360,15 +363,14 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   const int n_my = t_first < T ? (T - t_first + t_step - 1) / t_step : 0;
   const CUtensorMap* tm = &maps.m[cls >= 0 ? cls : 0];
 
-  auto issue = [&](int i) {   // lane 0: load the box of this warp's i-th tile into buffer i % nbuf
+  auto issue = [&](int i, int b) {   // lane 0: load the box of this warp's i-th tile into buffer b (= i % nbuf)
     const int t = t_first + i * t_step;
     const int ox = s_ox[t];
     if (ox == INT_MIN) return;
-    const uint32_t b = (uint32_t)(i % nbuf);
     mbar_arrive_expect_tx(my_bar + 8u * b, box_bytes);
     tma_load_3d(my_ring + b * buf_pitch, tm, my_bar + 8u * b, ox >> 2, s_oy[t], frame_idx);   // 32-bit elements: column = byte / 4
   };
-  if (lane == 0) for (int i = 0; i < min(nbuf, n_my); ++i) issue(i);
+  if (lane == 0) for (int i = 0; i < min(nbuf, n_my); ++i) issue(i, i);
 
   const int yl = lane >> 2, xg = (lane & 3) << 2;
   uint32_t phase_bits = 0u;                 // bit b = parity the next wait on buffer b expects (global-path tiles skip their slot)
@@ -404,7 +406,7 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
     dA[0] = wA[0]; dA[1] = wA[1]; dA[2] = wA[2];
     dB[0] = wB[0]; dB[1] = wB[1]; dB[2] = wB[2];
     __syncwarp();          // every lane has finished reading this tile's buffer
-    if (lane == 0 && i + nbuf < n_my) issue(i + nbuf);
+    if (lane == 0 && i + nbuf < n_my) issue(i + nbuf, buf);
     if (++buf == nbuf) buf = 0;
     tx += t_step;
     if (tx >= tiles_x) { tx -= tiles_x; ++ty; }

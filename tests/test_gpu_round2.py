@@ -491,4 +491,4 @@ def test_px8_first_layer_opt_in(dev, monkeypatch):
     monkeypatch.delenv("FLD_C1_PX8")
     m2 = landmark_regressor().init_weights(7)
     a, b = m2.forward_device(xt, "bfloat16"), m.forward_device(xt, "bfloat16")
-    assert (a - b).abs().max().item() < 1e-3            # default kernel vs opt-in kernel: same bf16 operands, different bias rounding
+    assert (a - b).abs().max().item() < 2.5e-3          # default vs opt-in kernel: same bf16 operands, different bias rounding; both within 1.25e-3 of the oracle
