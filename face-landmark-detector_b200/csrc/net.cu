@@ -25,6 +25,7 @@ struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
 struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; };
 struct Px8PlanEntry { int B; const void* scratch; TcPx8Plan* plan; };
+struct S2dPlanEntry { int B; const void* scratch; TcS2dPlan* plan; };
 
 struct LayerRt {
   fld_layer_desc d;
@@ -33,6 +34,7 @@ struct LayerRt {
   int cout_pad = 0;
   bool x3 = false;              // FLD_BF16X3 tensor-core conv: SPLIT input, weights packed [w_hi | w_hi | w_lo]
   bool px8 = false;             // first layer through tc_conv_px8.cu (TMA-built A operand) instead of tc_conv_first.cu
+  bool s2d = false;             // first layer through tc_conv_s2d.cu (pool window in the TMEM columns)
   bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
   bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
   bool needs_weights = false, has_weights = false;
@@ -46,6 +48,7 @@ struct LayerRt {
   std::vector<HaloPlanEntry> hplans;
   std::vector<DeconvPlanEntry> dplans;
   std::vector<Px8PlanEntry> pplans;
+  std::vector<S2dPlanEntry> splans;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -230,6 +233,8 @@ void free_layer(LayerRt& L) {
   L.dplans.clear();
   for (auto& pe : L.pplans) tc_conv_px8_plan_destroy(pe.plan);
   L.pplans.clear();
+  for (auto& pe : L.splans) tc_conv_s2d_plan_destroy(pe.plan);
+  L.splans.clear();
   L.d_w = nullptr; L.d_bias = nullptr; L.d_wbf = nullptr; L.plans.clear();
 }
 
@@ -361,6 +366,7 @@ extern "C" int fld_net_finalize(fld_net* net) {
     if (!L.needs_weights) continue;
     if (!L.has_weights) { fld_set_error("fld_net_finalize: layer %zu has no weights", i); return FLD_ERR_STATE; }
     free_layer(L);
+    L.px8 = L.s2d = false;
     const int Cout = L.d.cout;
     const TensorInfo& a = net->tensors[L.d.in0];
     // bias (padded so the epilogue can always read 32 floats per chunk)
@@ -395,6 +401,13 @@ extern "C" int fld_net_finalize(fld_net* net) {
       // strided stem (tc_conv_stem.cu): [KG][Cout/8][8][8], k' = 4*tap + c
       std::vector<uint16_t> pk((size_t)Cout * 8 * tc_conv_stem_kgroups(L.d.kh), 0);
       tc_conv_stem_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), L.d.kh, Cout, f2bf, pk.data());
+      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else if (L.path == PATH_TC_FIRST && tc_conv_s2d_supported(L.g) && (a.dtype == FLD_U8 || !L.x3)) {
+      // tc_conv_s2d.cu: 40 K groups ordered per (pool position, tap pair); x3: a second block with the weight remainders
+      L.s2d = true;
+      std::vector<uint16_t> pk((size_t)Cout * 8 * (L.x3 ? 80 : 40), 0);
+      tc_conv_s2d_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data(), L.x3 ? 1 : 0);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST && tc_conv_px8_supported(L.g) && (a.dtype == FLD_U8 || !L.x3)) {
@@ -463,7 +476,7 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
     if (L.d.op == FLD_OP_DENSE && L.path == PATH_TC_TMA)
       m = std::max(m, (size_t)dense_ksplit(net, B, (int)a.elems() / 64) * B * L.d.cout * sizeof(float));
-    if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && tc_conv_px8_supported(L.g)) m = std::max(m, tc_conv_px8_scratch_bytes(L.g, B));
+    if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && (L.px8 || L.s2d)) m = std::max(m, tc_conv_px8_scratch_bytes(L.g, B));
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
       m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
   }
@@ -546,6 +559,16 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
       case FLD_OP_CONV:
         if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
           rc = tc_conv_stem(net->h, pin, a.dtype, L.d_wbf, (__nv_bfloat16*)pout, L.g, B, st);
+        } else if (L.path == PATH_TC_FIRST && L.s2d) {
+          TcS2dPlan* plan = nullptr;
+          for (auto& pe : L.splans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
+          if (!plan) {
+            rc = tc_conv_s2d_plan_create(net->h, dense_scratch, a.dtype, L.g, B, L.x3 ? 1 : 0, o.dtype == FLD_BF16X3 ? 1 : 0, &plan);
+            if (rc) return rc;
+            if (L.splans.size() >= 16 && net->retained == 0) { tc_conv_s2d_plan_destroy(L.splans.front().plan); L.splans.erase(L.splans.begin()); }
+            L.splans.push_back({B, (const void*)dense_scratch, plan});
+          }
+          rc = tc_conv_s2d_run(plan, pin, L.d_wbf, pout, st);
         } else if (L.path == PATH_TC_FIRST && L.px8) {
           TcPx8Plan* plan = nullptr;
           for (auto& pe : L.pplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
