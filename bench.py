@@ -553,7 +553,14 @@ def run_gpu(args, rank, world, local_rank):
         hs.submit(*pin_sets[k % n_sets])
 
     timed(step_e2e, max(args.warmup, 2), hs.streams())
-    ms_e2e = timed(step_e2e, args.steps, hs.streams())
+    host_t = [0.0]
+
+    def step_e2e_timed(k):
+        t0 = time.perf_counter()
+        step_e2e(k)
+        host_t[0] += time.perf_counter() - t0
+
+    ms_e2e = timed(step_e2e_timed, args.steps, hs.streams())
     e2e_val = total_faces * args.steps / (ms_e2e * 1e-3)
     last = hs.result(hs.n_submitted - 1)
     e2e_check = bool(np.isfinite(last["marks"]).all() and last["aligned"].any())
@@ -688,7 +695,7 @@ def run_gpu(args, rank, world, local_rank):
                            "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2; activations workspace rewritten every step"
                                  % (n_sets, n_sets * set_bytes / 1e6)},
                 "e2e": {"value": e2e_val, "unit": "faces/s", "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": ms_e2e / args.steps, "api": "keypoints_detector.prediction.HostStream.submit / result (pinned host "
+                        "ms_per_step": ms_e2e / args.steps, "host_enqueue_ms_per_step": host_t[0] * 1e3 / args.steps, "api": "keypoints_detector.prediction.HostStream.submit / result (pinned host "
                         "buffers in and out, %d slots)" % n_slots, "results_checked": e2e_check, "cpus_bound": bound_cpus, "link": link,
                         "frac_of_link_bound": e2e_val / link["link_bound_faces_per_s"]},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_cnn": roof_cnn, "cross_gpu_bit_identical": bit_identical,

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libfld_sm100.so")
-SOURCES = ["api.cu", "align.cu", "preprocess.cu", "decode.cu", "simt_ops.cu", "simt_deconv.cu", "simt_extra.cu", "tc_conv.cu", "tc_deconv.cu", "tc_conv_first.cu", "tc_conv_px8.cu", "tc_conv_s2d.cu", "tc_conv_stem.cu", "tc_conv_halo.cu", "net.cu"]
+SOURCES = ["api.cu", "align.cu", "preprocess.cu", "decode.cu", "simt_ops.cu", "simt_deconv.cu", "simt_extra.cu", "tc_conv.cu", "tc_deconv.cu", "tc_conv_first.cu", "tc_conv_s2d.cu", "tc_conv_stem.cu", "tc_conv_halo.cu", "net.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static"]

@@ -24,7 +24,6 @@ enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
 struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; };
-struct Px8PlanEntry { int B; const void* scratch; TcPx8Plan* plan; };
 struct S2dPlanEntry { int B; const void* scratch; TcS2dPlan* plan; };
 
 struct LayerRt {
@@ -33,7 +32,6 @@ struct LayerRt {
   int path = PATH_SIMT;
   int cout_pad = 0;
   bool x3 = false;              // FLD_BF16X3 tensor-core conv: SPLIT input, weights packed [w_hi | w_hi | w_lo]
-  bool px8 = false;             // first layer through tc_conv_px8.cu (TMA-built A operand) instead of tc_conv_first.cu
   bool s2d = false;             // first layer through tc_conv_s2d.cu (pool window in the TMEM columns)
   bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
   bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
@@ -47,7 +45,6 @@ struct LayerRt {
   std::vector<PlanEntry> plans;
   std::vector<HaloPlanEntry> hplans;
   std::vector<DeconvPlanEntry> dplans;
-  std::vector<Px8PlanEntry> pplans;
   std::vector<S2dPlanEntry> splans;
 };
 
@@ -231,8 +228,6 @@ void free_layer(LayerRt& L) {
   L.hplans.clear();
   for (auto& pe : L.dplans) tc_deconv_plan_destroy(pe.plan);
   L.dplans.clear();
-  for (auto& pe : L.pplans) tc_conv_px8_plan_destroy(pe.plan);
-  L.pplans.clear();
   for (auto& pe : L.splans) tc_conv_s2d_plan_destroy(pe.plan);
   L.splans.clear();
   L.d_w = nullptr; L.d_bias = nullptr; L.d_wbf = nullptr; L.plans.clear();
@@ -366,7 +361,7 @@ extern "C" int fld_net_finalize(fld_net* net) {
     if (!L.needs_weights) continue;
     if (!L.has_weights) { fld_set_error("fld_net_finalize: layer %zu has no weights", i); return FLD_ERR_STATE; }
     free_layer(L);
-    L.px8 = L.s2d = false;
+    L.s2d = false;
     const int Cout = L.d.cout;
     const TensorInfo& a = net->tensors[L.d.in0];
     // bias (padded so the epilogue can always read 32 floats per chunk)
@@ -408,13 +403,6 @@ extern "C" int fld_net_finalize(fld_net* net) {
       L.s2d = true;
       std::vector<uint16_t> pk((size_t)Cout * 8 * (L.x3 ? 80 : 40), 0);
       tc_conv_s2d_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data(), L.x3 ? 1 : 0);
-      FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
-      FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
-    } else if (L.path == PATH_TC_FIRST && tc_conv_px8_supported(L.g) && (a.dtype == FLD_U8 || !L.x3)) {
-      // tc_conv_px8.cu: K group = tap, 8 channel slots per tap; the bias stays in d_bias (epilogue add)
-      L.px8 = true;
-      std::vector<uint16_t> pk((size_t)Cout * 8 * (L.x3 ? 20 : 10), 0);
-      tc_conv_px8_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data(), L.x3 ? 1 : 0);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
@@ -476,7 +464,7 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     if (L.d.op == FLD_OP_DENSE) m = std::max(m, simt_dense_scratch_bytes(B, (int)a.elems(), L.d.cout));
     if (L.d.op == FLD_OP_DENSE && L.path == PATH_TC_TMA)
       m = std::max(m, (size_t)dense_ksplit(net, B, (int)a.elems() / 64) * B * L.d.cout * sizeof(float));
-    if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && (L.px8 || L.s2d)) m = std::max(m, tc_conv_px8_scratch_bytes(L.g, B));
+    if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && L.s2d) m = std::max(m, tc_conv_s2d_scratch_bytes(L.g, B));
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
       m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
   }
@@ -514,8 +502,15 @@ extern "C" size_t fld_net_landmarks_workspace_bytes(const fld_net* net, int B, i
 
 extern "C" int fld_decode_classmap(fld_handle* h, const float* scores, int B, int hw, int L, int64_t* class_map, fld_stream stream);
 
+// byte offset of the scratch region (dense partials / transposed-conv im2col / first-layer staging) inside the workspace
+static size_t scratch_offset(const fld_net* net, int B) {
+  size_t off = 0;
+  for (size_t t = 1; t < net->tensors.size(); ++t) off += tensor_ws_bytes(net, (int)t, B);
+  return off;
+}
+
 static int net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, int64_t* cmap_out, fld_stream stream,
-                       double* xy_out = nullptr, double xy_thresh = 0.0, int xy_n = 0) {
+                       double* xy_out = nullptr, double xy_thresh = 0.0, int xy_n = 0, bool staged = false) {
   FLD_REQUIRE(net, "fld_net_forward: null net");
   int rc = fld_enter(net->h);
   if (rc) return rc;
@@ -568,17 +563,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
             if (L.splans.size() >= 16 && net->retained == 0) { tc_conv_s2d_plan_destroy(L.splans.front().plan); L.splans.erase(L.splans.begin()); }
             L.splans.push_back({B, (const void*)dense_scratch, plan});
           }
-          rc = tc_conv_s2d_run(plan, pin, L.d_wbf, pout, st);
-        } else if (L.path == PATH_TC_FIRST && L.px8) {
-          TcPx8Plan* plan = nullptr;
-          for (auto& pe : L.pplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
-          if (!plan) {
-            rc = tc_conv_px8_plan_create(net->h, dense_scratch, a.dtype, L.g, B, L.x3 ? 1 : 0, o.dtype == FLD_BF16X3 ? 1 : 0, &plan);
-            if (rc) return rc;
-            if (L.pplans.size() >= 16 && net->retained == 0) { tc_conv_px8_plan_destroy(L.pplans.front().plan); L.pplans.erase(L.pplans.begin()); }
-            L.pplans.push_back({B, (const void*)dense_scratch, plan});
-          }
-          rc = tc_conv_px8_run(plan, pin, L.d_wbf, L.d_bias, pout, st);
+          rc = tc_conv_s2d_run(plan, pin, L.d_wbf, pout, st, (staged && i == 0) ? 1 : 0);
         } else if (L.path == PATH_TC_FIRST) {
           rc = tc_conv_first(net->h, pin, a.dtype, L.d_wbf, L.d_bias, (__nv_bfloat16*)pout, L.g, B, st, L.x3 ? 1 : 0);
         } else if (L.path == PATH_TC_TMA && (o.dtype == FLD_BF16 || o.dtype == FLD_BF16X3) && tc_halo_supported(L.g, L.cout_pad)) {
@@ -717,6 +702,24 @@ extern "C" int fld_net_forward_landmarks(fld_net* net, const void* in, int B, vo
 
 extern "C" int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {
   return net_forward(net, in, B, workspace, ws_bytes, out, nullptr, stream);
+}
+
+extern "C" int fld_net_input_staging(const fld_net* net, int B, void* workspace, void** staging) {
+  FLD_REQUIRE(net && staging, "fld_net_input_staging: null pointer");
+  *staging = nullptr;
+  if (!net->finalized || B <= 0 || !workspace || net->layers.empty()) return FLD_OK;
+  const LayerRt& L = net->layers[0];
+  if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && L.s2d && L.d.in0 == 0 && net->tensors[0].dtype == FLD_U8)
+    *staging = (char*)workspace + scratch_offset(net, B);
+  return FLD_OK;
+}
+
+extern "C" int fld_net_forward_staged(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream) {
+  void* stg = nullptr;
+  int rc = fld_net_input_staging(net, B, workspace, &stg);
+  if (rc) return rc;
+  FLD_REQUIRE(B == 0 || stg, "fld_net_forward_staged: this net's first layer takes no staged input (fld_net_input_staging returned NULL)");
+  return net_forward(net, in, B, workspace, ws_bytes, out, nullptr, stream, nullptr, 0.0, 0, true);
 }
 
 extern "C" int fld_net_forward_classmap(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, int64_t* class_map,

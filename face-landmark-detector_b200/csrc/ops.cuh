@@ -41,15 +41,6 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
 bool tc_conv_first_supported(const ConvGeom& g);
 void tc_conv_first_pack(const float* w_host /*[27][Cout]*/, const float* bias_host /*[Cout] or null*/, int Cout,
                         uint16_t (*f2bf)(float), uint16_t* out /*[Cout*8*kg]*/, int kg = 6);
-// first layer with a TMA-built A operand (tc_conv_px8.cu): the input is widened to 8 bf16 channels per pixel in `scratch`, nine TMA
-// boxes per tile are the nine taps; bias in the epilogue; bf16 or SPLIT output; x3 = FLD_BF16X3 weights (uint8 input only)
-struct TcPx8Plan;
-bool tc_conv_px8_supported(const ConvGeom& g);
-size_t tc_conv_px8_scratch_bytes(const ConvGeom& g, int B);
-void tc_conv_px8_pack(const float* w_host /*[27][Cout]*/, const float* bias_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out /*[Cout*8*(x3 ? 20 : 10)]*/, int x3);
-int tc_conv_px8_plan_create(const fld_handle* h, void* scratch, int in_dtype, const ConvGeom& g, int B, int x3, int split_out, TcPx8Plan** out);
-void tc_conv_px8_plan_destroy(TcPx8Plan* p);
-int tc_conv_px8_run(const TcPx8Plan* p, const void* in, const __nv_bfloat16* w_packed, const float* bias, void* out, cudaStream_t st);
 // first layer with the 2x2 pool window in the TMEM columns (tc_conv_s2d.cu): space-to-depth planes of the widened image in
 // `scratch`, four TMA boxes per tile, bias through a K group; pool = 2 only; bf16 output, or SPLIT output with x3 (uint8 input)
 struct TcS2dPlan;
@@ -58,7 +49,8 @@ size_t tc_conv_s2d_scratch_bytes(const ConvGeom& g, int B);
 void tc_conv_s2d_pack(const float* w_host /*[27][Cout]*/, const float* bias_host, int Cout, uint16_t (*f2bf)(float), uint16_t* out /*[Cout*8*(x3 ? 80 : 40)]*/, int x3);
 int tc_conv_s2d_plan_create(const fld_handle* h, void* scratch, int in_dtype, const ConvGeom& g, int B, int x3, int split_out, TcS2dPlan** out);
 void tc_conv_s2d_plan_destroy(TcS2dPlan* p);
-int tc_conv_s2d_run(const TcS2dPlan* p, const void* in, const __nv_bfloat16* w_packed, void* out, cudaStream_t st);
+// staged != 0: the planes in `scratch` were already written by the producer of `in` (fld_preprocess_faces_staged): no widening pass
+int tc_conv_s2d_run(const TcS2dPlan* p, const void* in, const __nv_bfloat16* w_packed, void* out, cudaStream_t st, int staged = 0);
 // strided stems (tc_conv_stem.cu): k x k (3 or 7), stride 2, Cin = 3, any zero padding, bias folded, no pool; bf16 NHWC out
 bool tc_conv_stem_supported(const ConvGeom& g);
 int tc_conv_stem_kgroups(int ks);

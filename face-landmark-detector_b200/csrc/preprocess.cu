@@ -49,7 +49,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 resize_kernel(const uint8_t* __restrict__ src, int F, int H, int W, const int32_t* __restrict__ boxes,
               const int32_t* __restrict__ face2frame, int dw, int dh, int swap_rb, int norm, uint8_t* __restrict__ out_u8,
-              float* __restrict__ out_f32, int32_t* __restrict__ faceboxes) {
+              float* __restrict__ out_f32, int32_t* __restrict__ faceboxes, uint4* __restrict__ staged, int n_items) {
   extern __shared__ int sm[];
   int* xofs = sm;            // [dw]
   int* xa0 = sm + dw;        // [dw]
@@ -129,8 +129,17 @@ resize_kernel(const uint8_t* __restrict__ src, int F, int H, int W, const int32_
     const size_t o = ((size_t)item * dh + y) * dw + x;
     if (MODE == 0) {
       uint8_t* q = out_u8 + o * 3;
-      if (swap_rb) { q[0] = (uint8_t)v[2]; q[1] = (uint8_t)v[1]; q[2] = (uint8_t)v[0]; }
-      else { q[0] = (uint8_t)v[0]; q[1] = (uint8_t)v[1]; q[2] = (uint8_t)v[2]; }
+      const int c0 = swap_rb ? v[2] : v[0], c2 = swap_rb ? v[0] : v[2];
+      q[0] = (uint8_t)c0; q[1] = (uint8_t)v[1]; q[2] = (uint8_t)c2;
+      if (staged) {
+        // the first conv layer's operand staging (csrc/tc_conv_s2d.cu): the same pixel widened to 8 bf16 channels in the
+        // space-to-depth plane (y & 1, x & 1) — written here so that the network's widening pass is skipped
+        const int H2 = dh >> 1, W2 = dw >> 1;
+        const size_t plane = (size_t)n_items * H2 * W2;
+        __nv_bfloat162 lo = __floats2bfloat162_rn((float)c0, (float)v[1]), hi = __floats2bfloat162_rn((float)c2, 0.f);
+        staged[(size_t)((y & 1) * 2 + (x & 1)) * plane + ((size_t)item * H2 + (y >> 1)) * W2 + (x >> 1)] =
+            make_uint4(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi), 0u, 0u);
+      }
     } else {
       float* q = out_f32 + o * 3;
       if (norm == 0) {  // sub_mean then reverse channels (generator.py:53-61)
@@ -150,21 +159,34 @@ resize_kernel(const uint8_t* __restrict__ src, int F, int H, int W, const int32_
 
 }  // namespace
 
-extern "C" int fld_preprocess_faces(fld_handle* h, const uint8_t* frames, int F, int H, int W, const int32_t* boxes,
-                                    const int32_t* face2frame, int B, int S, int swap_rb, uint8_t* out, int32_t* faceboxes,
-                                    fld_stream stream) {
+static int preprocess_faces(fld_handle* h, const uint8_t* frames, int F, int H, int W, const int32_t* boxes, const int32_t* face2frame,
+                            int B, int S, int swap_rb, uint8_t* out, int32_t* faceboxes, void* staging, fld_stream stream) {
   int rc = fld_enter(h);
   if (rc) return rc;
   if (B == 0) return FLD_OK;
   FLD_REQUIRE(frames && boxes && out, "fld_preprocess_faces: null pointer");
   FLD_REQUIRE(F > 0 && H > 0 && W > 0 && S > 0 && S <= 4096 && B >= 0, "fld_preprocess_faces: bad shape");
-  if (B == 0) return FLD_OK;
+  FLD_REQUIRE(!staging || (S % 4 == 0 && (reinterpret_cast<uintptr_t>(staging) & 15) == 0),
+              "fld_preprocess_faces_staged: the staging layout needs S % 4 == 0 and a 16-byte aligned buffer");
   const size_t smem = (size_t)(3 * S + 4 * kRowsPerCta) * sizeof(int);
   dim3 grid(B, fld_div_up(S, kRowsPerCta));
   resize_kernel<0><<<grid, kThreads, smem, (cudaStream_t)stream>>>(frames, F, H, W, boxes, face2frame, S, S, swap_rb, 0, out,
-                                                                   nullptr, faceboxes);
+                                                                   nullptr, faceboxes, (uint4*)staging, B);
   FLD_LAUNCHED();
   return FLD_OK;
+}
+
+extern "C" int fld_preprocess_faces(fld_handle* h, const uint8_t* frames, int F, int H, int W, const int32_t* boxes,
+                                    const int32_t* face2frame, int B, int S, int swap_rb, uint8_t* out, int32_t* faceboxes,
+                                    fld_stream stream) {
+  return preprocess_faces(h, frames, F, H, W, boxes, face2frame, B, S, swap_rb, out, faceboxes, nullptr, stream);
+}
+
+extern "C" int fld_preprocess_faces_staged(fld_handle* h, const uint8_t* frames, int F, int H, int W, const int32_t* boxes,
+                                           const int32_t* face2frame, int B, int S, int swap_rb, uint8_t* out, int32_t* faceboxes,
+                                           void* staging, fld_stream stream) {
+  if (!staging) { fld_set_error("fld_preprocess_faces_staged: null staging (fld_net_input_staging)"); return FLD_ERR_INVALID; }
+  return preprocess_faces(h, frames, F, H, W, boxes, face2frame, B, S, swap_rb, out, faceboxes, staging, stream);
 }
 
 extern "C" int fld_image_array(fld_handle* h, const uint8_t* images, int B, int H, int W, int ow, int oh, int norm, float* out,
@@ -179,7 +201,7 @@ extern "C" int fld_image_array(fld_handle* h, const uint8_t* images, int B, int 
   const size_t smem = (size_t)(3 * ow + 4 * kRowsPerCta) * sizeof(int);
   dim3 grid(B, fld_div_up(oh, kRowsPerCta));
   resize_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(images, B, H, W, nullptr, nullptr, ow, oh, 0, norm, nullptr,
-                                                                   out, nullptr);
+                                                                   out, nullptr, nullptr, B);
   FLD_LAUNCHED();
   return FLD_OK;
 }

@@ -2,10 +2,12 @@
 // WINDOW IN THE TMEM COLUMNS (round 2).  Replaces stage 1 of vanilla_encoder (reference networks/fcn.py:25-31); the input is what
 // prediction.py:82-84 / data/generator.py:53-61 hand the model.
 //
-// The first layer has K = 27: its MMAs are nothing, its cost is the epilogue.  In round 1's kernel (tc_conv_first.cu) and in the
-// TMA-fed variant (tc_conv_px8.cu) a TMEM lane is a conv pixel, so the 2x2 max-pool crosses lanes: 24 SEL + 12 SHFL + 16 HMNMX2
-// per 32-column chunk on top of the per-thread operand building — ~1900 warp instructions per 128-pixel tile, issue-bound at
-// 0.105 ms per 256 faces against a TMEM-read floor of 0.059 ms.  Here a TMEM lane is a POOLED pixel and the four conv pixels of
+// The first layer has K = 27: its MMAs are nothing, its cost is the epilogue.  In round 1's kernel (tc_conv_first.cu) a TMEM lane
+// is a conv pixel, so the 2x2 max-pool crosses lanes: 24 SEL + 12 SHFL + 16 HMNMX2 per 32-column chunk on top of the per-thread
+// operand building — ~1900 warp instructions per 128-pixel tile, issue-bound at 0.105 ms per 256 faces against a TMEM-read floor of
+// 0.059 ms.  (An intermediate round-2 kernel that only replaced the operand building by TMA — same lane = conv pixel epilogue —
+// was measured at 0.118 ms + 0.022 ms for the widening pass: the shuffle epilogue alone is ~2000 warp instructions per tile and
+// the epilogue warps starved on `tfull`; it was dropped.)  Here a TMEM lane is a POOLED pixel and the four conv pixels of
 // its window are four column blocks of the same lane:
 //   D[pooled px][pos * Cout + o],  pos = (dy, dx) in {0,1}^2,
 // so the pool is three in-register FMNMX per output value, no shuffles, no selects, and a thread stores 64 contiguous bytes.
@@ -23,6 +25,8 @@
 // M = 128, N = Cout, K = 16 per tile, two accumulators of 4 * Cout columns), warps 2-9 epilogue in two groups of four warps (one
 // per TMEM lane quadrant) that take tiles alternately.  FLD_BF16X3 (uint8 input, exact in bf16): weights split hi / lo, the
 // same activation groups multiplied a second time against the lo block; SPLIT output.
+// MEASURED (B200, 256 faces @128x128, ncu): conv_s2d_kernel 58 us = the TMEM-read floor; the widening pass costs 21 us unless the
+// producer of the crops writes the planes itself (fld_preprocess_faces_staged: then the layer is 0.058 ms, round 1: 0.105 ms).
 #include <stdlib.h>
 #include <string.h>
 #include "tc_common.cuh"
@@ -354,16 +358,18 @@ int tc_conv_s2d_plan_create(const fld_handle* h, void* scratch, int in_dtype, co
 
 void tc_conv_s2d_plan_destroy(TcS2dPlan* p) { delete p; }
 
-int tc_conv_s2d_run(const TcS2dPlan* pl, const void* in, const __nv_bfloat16* w_packed, void* out, cudaStream_t st) {
+int tc_conv_s2d_run(const TcS2dPlan* pl, const void* in, const __nv_bfloat16* w_packed, void* out, cudaStream_t st, int staged) {
   if (pl->p.total_tiles == 0) return FLD_OK;
   const long long n = (long long)pl->p.B * pl->H * (pl->W / 4);
   const long long blocks = (n + 255) / 256;
   if (blocks >= (1ll << 31)) { fld_set_error("tc_conv_s2d: too many pixels"); return FLD_ERR_INVALID; }
   const int al = (reinterpret_cast<uintptr_t>(in) & 3) == 0;
-  if (pl->in_dtype == FLD_U8) s2d_widen_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>((const uint8_t*)in, (uint4*)pl->scratch, pl->p.B, pl->H, pl->W, al);
+  if (staged) {
+    // the producer of `in` (fld_preprocess_faces_staged) has already written the space-to-depth planes
+  } else if (pl->in_dtype == FLD_U8) s2d_widen_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>((const uint8_t*)in, (uint4*)pl->scratch, pl->p.B, pl->H, pl->W, al);
   else if (pl->in_dtype == FLD_F32) s2d_widen_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)in, (uint4*)pl->scratch, pl->p.B, pl->H, pl->W, al);
   else { fld_set_error("tc_conv_s2d: input must be u8 or f32"); return FLD_ERR_INVALID; }
-  FLD_LAUNCHED();
+  if (!staged) FLD_LAUNCHED();
   S2dParams p = pl->p;
   p.w = w_packed; p.out = out;
   if (p.x3) {

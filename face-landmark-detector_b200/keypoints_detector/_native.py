@@ -44,6 +44,7 @@ SIGNATURES = {
     "fld_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "fld_destroy": (None, [_vp]),
     "fld_preprocess_faces": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "fld_preprocess_faces_staged": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fld_image_array": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "fld_net_create": (_i, [_vp, ctypes.POINTER(LayerDesc), _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "fld_net_destroy": (None, [_vp]),
@@ -53,6 +54,8 @@ SIGNATURES = {
     "fld_net_workspace_bytes": (_sz, [_vp, _i]),
     "fld_net_tensor_offset": (ctypes.c_int64, [_vp, _i, _i]),
     "fld_net_forward": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "fld_net_input_staging": (_i, [_vp, _i, _vp, ctypes.POINTER(_vp)]),
+    "fld_net_forward_staged": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "fld_net_forward_classmap": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "fld_net_landmarks_workspace_bytes": (_sz, [_vp, _i, _i]),
     "fld_net_retain": (_i, [_vp]),

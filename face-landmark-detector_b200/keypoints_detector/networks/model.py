@@ -384,7 +384,23 @@ class Model:
             N.check(dt)
         return tuple(hwc), dt
 
-    def forward_device(self, x, dtype=None, out=None, return_workspace=False, lane=0):
+    def input_staging(self, B, device, dtype=None, lane=0):
+        """Address of the first conv layer's operand staging buffer inside the lane's workspace for batch B, or None when the net
+        keeps none (fld_net_input_staging).  A producer that fills it (preprocess_faces_device(..., staging=...)) lets
+        forward_device(..., staged=True) skip the network's own widening pass over the crops."""
+        lib = N.load_library()
+        dev = torch.device(device).index
+        if self.in_dtype != "uint8" or B <= 0:
+            return None
+        with torch.cuda.device(dev):
+            net = self.compiled(dev, dtype)
+            comp = self._compute_code(dtype)
+            ws, al = self._workspace(dev, comp, lane, lib.fld_net_workspace_bytes(net, B), torch.device("cuda", dev))
+            stg = N._vp()
+            N.check(lib.fld_net_input_staging(net, B, N._vp(ws.data_ptr() + al), ctypes.byref(stg)))
+        return stg if stg.value else None
+
+    def forward_device(self, x, dtype=None, out=None, return_workspace=False, lane=0, staged=False):
         """x: CUDA tensor [B,H,W,C] (uint8 or float32 per model.in_dtype) -> float32 CUDA tensor of the final layer.
 
         `lane` selects one of several independent activation workspaces, so that forwards of independent batches
@@ -407,7 +423,8 @@ class Model:
             oh, ow, oc = self.graph.shapes[-1]
             if out is None:
                 out = torch.empty((B, oh * ow, oc) if self.kind == "segmentation" else (B, oc), dtype=torch.float32, device=x.device)
-            N.check(lib.fld_net_forward(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(out), N.stream_ptr(dev)))
+            fwd = lib.fld_net_forward_staged if staged else lib.fld_net_forward
+            N.check(fwd(net, N.ptr(x), B, N._vp(base + al), ws.numel() - al, N.ptr(out), N.stream_ptr(dev)))
         if return_workspace:
             return out, ws, al
         return out

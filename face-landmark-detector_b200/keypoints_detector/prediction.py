@@ -36,9 +36,10 @@ def _device(device=None):
 
 
 # ----------------------------------------------------------------------------------------------- device ops
-def preprocess_faces_device(frames, boxes, face2frame, size=128, swap_rb=True, out=None, out_boxes=None):
+def preprocess_faces_device(frames, boxes, face2frame, size=128, swap_rb=True, out=None, out_boxes=None, staging=None):
     """frames uint8 CUDA [F,H,W,3] BGR; boxes int32 CUDA [B,4]; face2frame int32 CUDA [B].
-    -> (crops uint8 [B,size,size,3] RGB, faceboxes int32 [B,4]); reference prediction.py:76-83."""
+    -> (crops uint8 [B,size,size,3] RGB, faceboxes int32 [B,4]); reference prediction.py:76-83.
+    `staging` (Model.input_staging): also write the crops into the network's first-layer operand staging buffer."""
     lib = N.load_library()
     F, H, W, C = frames.shape
     assert C == 3 and frames.dtype == torch.uint8
@@ -46,8 +47,12 @@ def preprocess_faces_device(frames, boxes, face2frame, size=128, swap_rb=True, o
     out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=frames.device) if out is None else out
     fb = torch.empty((B, 4), dtype=torch.int32, device=frames.device) if out_boxes is None else out_boxes
     with torch.cuda.device(frames.device):
-        N.check(lib.fld_preprocess_faces(N.handle(frames.device), N.ptr(frames), F, H, W, N.ptr(boxes), N.ptr(face2frame), B, size,
-                                         int(swap_rb), N.ptr(out), N.ptr(fb), N.stream_ptr(frames.device)))
+        if staging is not None:
+            N.check(lib.fld_preprocess_faces_staged(N.handle(frames.device), N.ptr(frames), F, H, W, N.ptr(boxes), N.ptr(face2frame), B,
+                                                    size, int(swap_rb), N.ptr(out), N.ptr(fb), staging, N.stream_ptr(frames.device)))
+        else:
+            N.check(lib.fld_preprocess_faces(N.handle(frames.device), N.ptr(frames), F, H, W, N.ptr(boxes), N.ptr(face2frame), B, size,
+                                             int(swap_rb), N.ptr(out), N.ptr(fb), N.stream_ptr(frames.device)))
     return out, fb
 
 
@@ -203,9 +208,12 @@ class LandmarkPipeline:
         b = self._buffers(lane, B, frames.shape[3], frames.device)
         for s0 in range(0, max(B, 1), self.max_batch):
             s1 = min(B, s0 + self.max_batch)
+            # the crop / resize kernel also fills the first conv layer's operand staging when the net has one (same values as the
+            # network's own widening pass over the crops, which is then skipped)
+            stg = self.model.input_staging(s1 - s0, frames.device, self.dtype, lane) if s1 > s0 else None
             crops128, fb = preprocess_faces_device(frames, boxes[s0:s1], face2frame[s0:s1], self.input_size, True,
-                                                   out=b["crops"][s0:s1], out_boxes=b["faceboxes"][s0:s1])
-            out = self.model.forward_device(crops128, self.dtype, out=b["net_out"][s0:s1], lane=lane)
+                                                   out=b["crops"][s0:s1], out_boxes=b["faceboxes"][s0:s1], staging=stg)
+            out = self.model.forward_device(crops128, self.dtype, out=b["net_out"][s0:s1], lane=lane, staged=stg is not None)
             marks, marks_u = decode_regress_device(out, fb, want_uint, out=b["marks"][s0:s1], out_uint=b["marks_uint"][s0:s1])
             align_device(frames, face2frame[s0:s1], marks, self.template, self.out_size, True, True, out=b["aligned"][s0:s1],
                          out_matrix=b["M"][s0:s1])
@@ -342,6 +350,7 @@ class HostStream:
                 self.caps = [pipeline.capture(*self.d_in[s], lane=s) for s in range(self.n_slots)]
             self._res = [None] * self.n_slots
         self.n_submitted = 0
+        self._direct = {}
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.d_in[0])
         self.d2h_bytes = sum(t.numel() * t.element_size() for k, t in self.h_out[0].items() if k != "M")
 
@@ -363,10 +372,19 @@ class HostStream:
             if given is None:
                 src.append(stage)
                 continue
-            t = _as_cpu_tensor(given, stage.dtype)
-            if t.is_pinned() and t.shape == stage.shape:
-                src.append(t)
+            direct = self._direct.get(id(given))              # is_pinned() asks the driver: remember the answer per tensor
+            if direct is None:
+                t = _as_cpu_tensor(given, stage.dtype)
+                direct = t if (t.is_pinned() and t.shape == stage.shape) else False
+                if isinstance(given, torch.Tensor):
+                    if len(self._direct) > 256:
+                        self._direct.clear()
+                    self._direct[id(given)] = direct
+                    self._direct_keep = getattr(self, "_direct_keep", [])[-256:] + [given]   # ids stay unique while referenced
+            if direct is not False:
+                src.append(direct)
             else:
+                t = _as_cpu_tensor(given, stage.dtype)
                 if stage.dim() == 2:
                     t = t.reshape(-1, 4)
                 self.ev_in[sl].synchronize()          # the slot's previous H2D has read the staging area

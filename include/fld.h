@@ -81,6 +81,13 @@ FLD_API int fld_preprocess_faces(fld_handle* h, const uint8_t* frames, int F, in
                          const int32_t* boxes, const int32_t* face2frame, int B, int S, int swap_rb,
                          uint8_t* out, int32_t* faceboxes, fld_stream stream);
 
+/* Same, and additionally writes every resized pixel into the first conv layer's operand staging buffer of a network
+ * (fld_net_input_staging: space-to-depth planes of the crop widened to 8 bf16 channels), so that fld_net_forward_staged can skip
+ * its own widening pass over the crops.  `out` is still written (it is what prediction.py:84 hands the model).  S % 4 == 0. */
+FLD_API int fld_preprocess_faces_staged(fld_handle* h, const uint8_t* frames, int F, int H, int W,
+                         const int32_t* boxes, const int32_t* face2frame, int B, int S, int swap_rb,
+                         uint8_t* out, int32_t* faceboxes, void* staging, fld_stream stream);
+
 /* Replaces data/generator.py:50-69 get_image_array on a batch of equally sized images.
  * images: uint8 [B,H,W,3] BGR.  norm: 0 = sub_mean (:53-61; subtract [103.939,116.779,123.68] per
  * BGR channel, then reverse channels), 1 = sub_and_divide (:51; /127.5-1), 2 = divide (:63-65; /255).
@@ -139,6 +146,13 @@ FLD_API int64_t fld_net_tensor_offset(const fld_net* net, int tensor, int B);
  * the activations of ONE forward: forwards that overlap on different streams need a workspace each; the net object (weights,
  * kernel plans) is shared. */
 FLD_API int fld_net_forward(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream);
+
+/* Producer-side fusion of the first layer's operand staging.  fld_net_input_staging returns in *staging the address INSIDE
+ * `workspace` (for batch B) where the first conv layer keeps its widened copy of a uint8 input — or NULL when the net has no such
+ * buffer (other first layers, float inputs).  A producer that writes it (fld_preprocess_faces_staged, same B) lets
+ * fld_net_forward_staged run without the widening pass; `in` must still be the uint8 tensor the staging was derived from. */
+FLD_API int fld_net_input_staging(const fld_net* net, int B, void* workspace, void** staging);
+FLD_API int fld_net_forward_staged(fld_net* net, const void* in, int B, void* workspace, size_t ws_bytes, float* out, fld_stream stream);
 
 /* Forward of a segmentation graph followed by prediction.py:209 (argmax over classes, first max wins): class_map int64
  * [B, oh, ow].  In FLD_BF16 mode, when the graph ends in Conv2DTranspose(k = 2*stride) + softmax (fcn_8), the argmax runs

@@ -470,25 +470,51 @@ def test_dense_on_tensor_cores_matches_fp32_dense(dev):
         assert torch.equal(m.forward_device(x[Bn - 3:].contiguous(), "bfloat16"), out[Bn - 3:])
 
 
-def test_px8_first_layer_opt_in(dev, monkeypatch):
-    """csrc/tc_conv_px8.cu (first layer with a TMA-built operand: one halo patch per tile, taps as shifted UMMA descriptors, bias
-    through a K group) is opt-in because it measured slower than the default kernel; it must stay correct: same bars as the
-    default first layer in bf16 and bf16x3 mode, pooled and un-pooled (VGG block1_conv1), against the fp64 oracle."""
+def test_first_layer_kernels_agree(dev, monkeypatch):
+    """Two independent first-layer kernels exist: csrc/tc_conv_s2d.cu (default when the layer pools: pool window in the TMEM
+    columns, space-to-depth operand planes) and round 1's csrc/tc_conv_first.cu (FLD_C1_S2D=0; also the un-pooled case).  Same
+    bars against the fp64 oracle in bf16 and bf16x3 mode, and they agree with each other to bf16 rounding."""
     from keypoints_detector.networks.regression import landmark_regressor
     from oracle import cnn as o_cnn
-    monkeypatch.setenv("FLD_C1_PX8", "1")
-    m = landmark_regressor().init_weights(7)
     rng = np.random.default_rng(7)
     x = rng.integers(0, 256, (9, 128, 128, 3), dtype=np.uint8)
-    ref = o_cnn.regression_forward(x, m.weights, torch.float64)
-    lv = o_cnn.trunk_forward(x.astype(np.float64), m.weights, torch.float64, scale=1 / 255.0)[0]
     xt = T(x, dev)
-    for dtype, tol_out, tol_l1 in (("bfloat16", 1.25e-3, 3e-2), ("bf16x3", 1.25e-4, 5e-5)):
-        out = m.forward_device(xt, dtype).cpu().numpy()
-        assert np.abs(out - ref).max() < tol_out, (dtype, np.abs(out - ref).max())
-        got = m.intermediate(xt, 1, dtype).cpu().numpy()
-        assert np.abs(got - lv).max() < tol_l1 * np.abs(lv).max(), (dtype, np.abs(got - lv).max() / np.abs(lv).max())
-    monkeypatch.delenv("FLD_C1_PX8")
-    m2 = landmark_regressor().init_weights(7)
-    a, b = m2.forward_device(xt, "bfloat16"), m.forward_device(xt, "bfloat16")
-    assert (a - b).abs().max().item() < 2.5e-3          # default vs opt-in kernel: same bf16 operands, different bias rounding; both within 1.25e-3 of the oracle
+    outs = {}
+    for env in ("1", "0"):
+        monkeypatch.setenv("FLD_C1_S2D", env)
+        m = landmark_regressor().init_weights(7)
+        ref = o_cnn.regression_forward(x, m.weights, torch.float64)
+        lv = o_cnn.trunk_forward(x.astype(np.float64), m.weights, torch.float64, scale=1 / 255.0)[0]
+        for dtype, tol_out, tol_l1 in (("bfloat16", 1.25e-3, 3e-2), ("bf16x3", 1.25e-4, 5e-5)):
+            out = m.forward_device(xt, dtype)
+            assert np.abs(out.cpu().numpy() - ref).max() < tol_out, (env, dtype, np.abs(out.cpu().numpy() - ref).max())
+            got = m.intermediate(xt, 1, dtype).cpu().numpy()
+            assert np.abs(got - lv).max() < tol_l1 * np.abs(lv).max(), (env, dtype, np.abs(got - lv).max() / np.abs(lv).max())
+            outs[(env, dtype)] = out.clone()
+        assert (m.input_staging(9, dev, "bfloat16") is not None) == (env == "1")
+    assert (outs[("1", "bfloat16")] - outs[("0", "bfloat16")]).abs().max().item() < 2.5e-3
+    assert (outs[("1", "bf16x3")] - outs[("0", "bf16x3")]).abs().max().item() < 2.5e-4
+
+
+def test_staged_first_layer_equals_unstaged(dev):
+    """The crop / resize kernel can write the first conv layer's operand staging itself (fld_preprocess_faces_staged +
+    fld_net_forward_staged, what LandmarkPipeline does); the network output must be bit-identical to running the network on the
+    uint8 crops alone (its own widening pass), in both tensor-core modes, and the ABI refuses a staged forward on a net without
+    a staging buffer."""
+    from keypoints_detector import _native as N, prediction
+    from keypoints_detector.data import synthetic
+    from keypoints_detector.networks.regression import landmark_regressor
+    m = landmark_regressor().init_weights(seed=13)
+    frames = T(synthetic.make_frames(2, 480, 640, seed=14), dev)
+    boxes = T(synthetic.make_boxes(37, 480, 640, seed=15, max_side=300), dev)
+    f2f = T((np.arange(37) % 2).astype(np.int32), dev)
+    for dtype in ("bfloat16", "bf16x3"):
+        assert m.input_staging(37, dev, dtype, lane=0) is not None
+        r = prediction.LandmarkPipeline(m, dtype=dtype).run_device(frames, boxes, f2f, lane=0)
+        crops = r["crops"].clone()
+        plain = m.forward_device(crops, dtype, lane=9)
+        marks, _ = prediction.decode_regress_device(plain, r["faceboxes"], False)
+        assert torch.equal(marks, r["marks"]), dtype
+    assert m.input_staging(37, dev, "float32", lane=0) is None               # the CUDA-core mode keeps no staging
+    with pytest.raises(N.FldError):
+        m.forward_device(crops, "float32", lane=9, staged=True)
