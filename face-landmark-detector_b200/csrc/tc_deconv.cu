@@ -44,11 +44,41 @@ struct DeconvParams {
   int stages;
   int mode;             // 0 logits, 1 softmax probabilities, 2 int64 argmax class map, 3 per-class soft-centroid sums
   float* acc;           // mode 3: [B][Cout][3] fp32 (sum p, sum p*col, sum p*row), accumulated with atomics
+  int walk;             // mode 3: 1 = round 1's per-class walk over the staged block (FLD_TC_DECONV_WALK=1), 0 = tf32 tensor-core reduction
   unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
 };
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+
+// ---- fused soft centroid on the tensor cores (mode 3).  The per-class sums over a tile's 128 pixels are a tiny GEMM
+//   D[class][j] = sum_px P[px][class] * W[px][j],   W = (1, col, row) of the tile's first image | the same for its second image,
+// evaluated with tcgen05.mma kind::tf32 (fp32 storage, 10-bit mantissa inputs, fp32 accumulation: the column / row indices are
+// exact, the probabilities carry 2^-11 relative error that largely cancels in the ratio).  It replaces a per-class walk of 68
+// threads down the staged block (128 x (2 LDS + 3 FMA) per thread per tile: ~60 % of the epilogue's instructions).
+// A = P^T, K-major no-swizzle: element (class c, pixel k) at (k / 4) * kRedLbo + (c / 8) * 128 + (c % 8) * 16 + (k % 4) * 4.
+constexpr int kRedCols = 160;                                     // TMEM columns [160, 192): two 16-column reduction accumulators
+__host__ __device__ constexpr int red_lbo(int cout) { return ((cout + 7) / 8) * 128 + 16; }   // +16: skews the K groups over the banks
+__host__ __device__ constexpr int red_a_bytes(int cout) { return 32 * red_lbo(cout); }        // 32 K groups of 4 pixels
+// B: ten 16-byte rows j of [4 px] fp32 per K group.  The N = 16 operand's second 8-row block starts 32 B after the first (SBO = 32),
+// so operand rows 8..15 alias storage rows 2..9: D columns 0..7 are rows 0..7, D columns 14, 15 are rows 8, 9.
+constexpr int kRedBLbo = 176;                                     // 160 B of rows + 16 B bank skew
+constexpr int kRedBBytes = 32 * kRedBLbo;
+// 16-warp variant: B = six rows (1, col, row | 1, col, row) of centred integers; operand rows 8..15 alias rows 0..7 (SBO = 0)
+constexpr int kRedB16Lbo = 144;                                   // 128 B of rows + 16 B bank skew
+constexpr int kRedB16Bytes = 32 * kRedB16Lbo;
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8v(uint32_t taddr, uint32_t* r) { tmem_ld8(taddr, r); }
 constexpr int kMaxStages = 8;
 constexpr int kTraceN = 2048;
 
@@ -57,11 +87,11 @@ constexpr int kTraceN = 2048;
     if (p.trace && blockIdx.x == 0 && (idx) < kTraceN) p.trace[(role) * kTraceN + (idx)++] = ((unsigned long long)clock64() << 4) | (tag); \
   } while (0)
 
-template <int COUT>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int COUT, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DeconvParams p) {
   extern __shared__ uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], afull_bar, afree_bar;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], afull_bar, afree_bar, red_bar[2];
   __shared__ long long goff[2][128];
   __shared__ uint32_t tmem_base_s;
 
@@ -77,9 +107,11 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EW); }
     mbar_init(afull, 1);
     mbar_init(afree, 1);
+    mbar_init(smem_u32(&red_bar[0]), 1);
+    mbar_init(smem_u32(&red_bar[1]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -162,6 +194,168 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
+    if constexpr (EW == 16) {
+      // ---- soft-centroid epilogue with SIXTEEN warps (mode 3, 68 classes).  Two threads share a pixel: thread ch = 0 holds
+      // classes [0, 32), ch = 1 classes [32, 68), so a thread carries 32..36 logits instead of 68 and every scheduler has four
+      // epilogue warps to hide the MUFU / TMEM / shared-memory latencies behind (with eight warps the epilogue ran at 0.27
+      // instructions per clock per scheduler and bounded the kernel: 3600 clk per tile-phase against 840 clk of MMA issue).
+      // Each thread exponentiates against ITS OWN maximum; the pair exchanges (max, sum) through four unused rows of the
+      // staging block and rescales, p = e * 2^(m_own - m) / (s_own 2^(m_own - m) + s_other 2^(m_other - m)), as it stages
+      // P^T (A operand).  B = (1, col, row) of the tile's first | second image, centred integers: exact in tf32.
+      static_assert(COUT == 68, "the 16-warp epilogue splits 68 classes at 32");
+      const int ew = warp - 2;
+      const int sub = warp & 3;              // TMEM lane quadrant (hardware rule: warp id % 4)
+      const int half = (ew >> 2) & 1;        // phase of the N tile
+      const int ch = ew >> 3;                // class half
+      const int r = sub * 32 + lane;         // tile row = pixel
+      const int OWs = p.GW * p.s, OHs = p.GH * p.s;
+      const uint32_t lbo = (uint32_t)red_lbo(COUT);
+      const uint32_t sA = smem_stg + (uint32_t)half * (uint32_t)red_a_bytes(COUT);
+      const uint32_t sB = smem_stg + 2u * (uint32_t)red_a_bytes(COUT) + (uint32_t)half * (uint32_t)kRedB16Bytes;
+      const uint32_t a_thr = sA + (uint32_t)(r >> 2) * lbo + (uint32_t)(r & 3) * 4u;
+      const uint32_t st_own = a_thr + 8u * 128u + (uint32_t)(4 + 2 * ch) * 16u;          // "classes" 68 + 2 ch, 69 + 2 ch: never read back
+      const uint32_t st_oth = a_thr + 8u * 128u + (uint32_t)(4 + 2 * (1 - ch)) * 16u;
+      const uint32_t b_thr = sB + (uint32_t)(r >> 2) * (uint32_t)kRedB16Lbo + (uint32_t)(r & 3) * 4u;
+      const uint32_t rbar = smem_u32(&red_bar[half]);
+      const uint32_t dred = tmem_base + kRedCols + (uint32_t)half * 16u;
+      const bool issuer = (ch == 0 && sub == 0 && lane == 0);
+      uint32_t acc = 0, acc_phase = 0, red_phase = 0;
+      bool red_pending = false, red_unit = false;
+      int red_mt = 0;
+      auto red_read = [&]() {
+        if (ch == 0 && sub < 3) {
+          tc_fence_after();
+          uint32_t q[8];
+          tmem_ld8(dred + ((uint32_t)(sub * 32) << 16), q);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (r < COUT) {                                 // TMEM lane r of the reduction accumulator = class r
+            const long long g0 = (long long)red_mt * 128;
+            const int per = p.GH * p.GW;
+            const long long b0 = g0 / per;
+            const int nvalid = (int)min((long long)128, p.M - g0);
+            const int split = (int)min((long long)nvalid, (b0 + 1) * per - g0);
+            float* d0 = p.acc + ((size_t)b0 * COUT + r) * 3;
+            atomicAdd(d0, __uint_as_float(q[0])); atomicAdd(d0 + 1, __uint_as_float(q[1])); atomicAdd(d0 + 2, __uint_as_float(q[2]));
+            if (split < nvalid) {
+              float* d1 = d0 + (size_t)COUT * 3;
+              atomicAdd(d1, __uint_as_float(q[3])); atomicAdd(d1 + 1, __uint_as_float(q[4])); atomicAdd(d1 + 2, __uint_as_float(q[5]));
+            }
+          }
+        }
+        red_unit = false;
+      };
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int mt = u / p.nsplit, nt0 = (u - mt * p.nsplit) * p.cn;
+        const long long g = (long long)mt * 128 + r;
+        const bool valid = g < p.M;
+        const long long b = g / (p.GH * p.GW);
+        const int rem = (int)(g - b * (p.GH * p.GW));
+        const int oy = rem / p.GW, ox = rem - oy * p.GW;
+        const long long b0 = ((long long)mt * 128) / (p.GH * p.GW);   // a tile of 128 flat rows spans at most two images
+        const float w0 = (valid && b == b0) ? 1.f : 0.f, w1 = (valid && b != b0) ? 1.f : 0.f;
+        int a = (nt0 * 2 + half) / p.s, bq = (nt0 * 2 + half) - a * p.s;
+        for (int t = 0; t < p.cn; ++t, bq += 2) {
+          if (bq >= p.s) { bq -= p.s; ++a; }
+          mbar_wait(tfull0 + 8 * acc, acc_phase);
+          tc_fence_after();
+          uint32_t rg[40];
+          const uint32_t tbase = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 256 + half * p.cpp + (uint32_t)ch * 32u;
+          tmem_ld32(tbase, *reinterpret_cast<uint32_t(*)[32]>(&rg[0]));
+          if (ch) tmem_ld8(tbase + 32, &rg[32]);          // classes 64..67 (+ 4 padding columns)
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);  // accumulator is in registers: the MMAs of the tile after next may start
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(rg[j]));
+          if (ch) {
+#pragma unroll
+            for (int j = 32; j < 36; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(rg[j]));
+          }
+          const float m = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          const float nm = -m * 1.4426950408889634f;
+          float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(rg[j]), 1.4426950408889634f, nm)));
+            rg[j] = __float_as_uint(e);
+            sum[j & 3] += e;
+          }
+          if (ch) {
+#pragma unroll
+            for (int j = 32; j < 36; ++j) {
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(rg[j]), 1.4426950408889634f, nm)));
+              rg[j] = __float_as_uint(e);
+              sum[j & 3] += e;
+            }
+          }
+          const float sm = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+
+          if (red_pending) {                              // previous tile's MMAs are done with the staging block
+            mbar_wait(rbar, red_phase);
+            red_phase ^= 1u;
+            red_pending = false;
+          }
+          if (t == 0 && red_unit) red_read();             // previous unit complete: its sums leave TMEM before they are overwritten
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_own), "f"(m) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_own + 16u), "f"(sm) : "memory");
+          if (ch == 0) {
+            // grids centred on the map (utils/metrics.py:57-64 grids, shifted back in centroid_finish_kernel): small exact integers
+            const float fx = (float)(ox * p.s + bq - OWs / 2), fy = (float)(oy * p.s + a - OHs / 2);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr), "f"(w0) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + 16u), "f"(w0 * fx) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + 32u), "f"(w0 * fy) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + 48u), "f"(w1) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + 64u), "f"(w1 * fx) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + 80u), "f"(w1 * fy) : "memory");
+          }
+          named_bar_sync(1 + half, 256);                  // the pair's (max, sum) are posted
+          float mo, so;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mo) : "r"(st_oth) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(so) : "r"(st_oth + 16u) : "memory");
+          const float mm = fmaxf(m, mo);
+          float f_own, f_oth;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f_own) : "f"((m - mm) * 1.4426950408889634f));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f_oth) : "f"((mo - mm) * 1.4426950408889634f));
+          const float scale = __fdividef(f_own, fmaf(sm, f_own, so * f_oth));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = j;                              // ch 0: class j; ch 1: class 32 + j (same offsets, 4 core matrices on)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_thr + (uint32_t)ch * 512u + (uint32_t)((c >> 3) * 128 + (c & 7) * 16)),
+                         "f"(__uint_as_float(rg[j]) * scale) : "memory");
+          }
+          if (ch) {
+#pragma unroll
+            for (int j = 32; j < 36; ++j)
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_thr + 512u + (uint32_t)((j >> 3) * 128 + (j & 7) * 16)), "f"(__uint_as_float(rg[j]) * scale) : "memory");
+          }
+          fence_async_smem();                             // generic-proxy stores -> tensor-core (async proxy) reads
+          named_bar_sync(1 + half, 256);                  // A and B complete; at t == 0 every reader has also consumed the previous D
+          if (issuer) {
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_tf32(128, 16);
+            const uint64_t ad = umma_desc(sA, lbo, 128, 0);          // K group = 4 pixels (16 B); 8-class core matrices 128 B apart
+            const uint64_t bd = umma_desc(sB, kRedB16Lbo, 0, 0);     // SBO 0: rows 8..15 of the N = 16 operand alias rows 0..7
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2)
+              umma_tf32(dred, ad + (uint64_t)(m2 * ((2 * lbo) >> 4)), bd + (uint64_t)(m2 * ((2 * kRedB16Lbo) >> 4)), idesc, (t | m2) ? 1u : 0u);
+            umma_commit(rbar);
+          }
+          red_pending = true;
+          red_unit = true;
+          red_mt = mt;
+        }
+      }
+      if (red_pending) mbar_wait(rbar, red_phase);
+      if (red_unit) red_read();
+    } else {
     // COUT > 0: the channel count is a compile-time constant (68 = the reference's n_classes), so none of the unrolled
     // per-channel loops carries a predicate; COUT == 0 is the generic runtime-count variant.
     const int Cout = COUT ? COUT : p.Cout;
@@ -181,19 +375,55 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int nper = vec ? (Cout >> 2) : Cout;
     const int px0 = gt / nper, q0 = gt - px0 * nper, px_step = 128 / nper, q_step = 128 - px_step * nper;
     float* const outp = reinterpret_cast<float*>(p.out);
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, red_phase = 0;
     int ti = 0;
     const bool tr = (warp == 2 && lane == 0);
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x)
-    for (int t = 0; t < p.cn; ++t) {
-      const int mt = u / p.nsplit, nt = (u - mt * p.nsplit) * p.cn + t;
-      const long long g = (long long)mt * 128 + r;
-      const bool valid = g < p.M;
-      const long long b = g / (p.GH * p.GW);
-      const int rem = (int)(g - b * (p.GH * p.GW));
-      const int oy = rem / p.GW, ox = rem - oy * p.GW;
-      const int ph = nt * 2 + half;
-      const int a = ph / p.s, bq = ph - a * p.s;
+    // Tensor-core soft-centroid reduction (mode 3): the sums of a unit (one M tile = the same 128 pixels under every phase pair)
+    // accumulate in TMEM across the unit's tiles; they are read back and added to acc[b][c][:] once per unit, at the first tile
+    // of the next unit (a flush per tile cost 88 M same-address atomics per 1024 images).  The MMAs of tile i run while this
+    // half loads and exponentiates tile i+1; red_bar only guards the reuse of the staging block.
+    const uint32_t rbar = smem_u32(&red_bar[half]);
+    const uint32_t dred = tmem_base + kRedCols + (uint32_t)half * 16u;
+    bool red_pending = false, red_unit = false;
+    int red_mt = 0;
+    auto red_read = [&]() {
+      tc_fence_after();
+      uint32_t q[16];
+      tmem_ld16(dred + ((uint32_t)(sub * 32) << 16), q);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (r < Cout) {                                   // TMEM lane r of the reduction accumulator = class r
+        const long long g0 = (long long)red_mt * 128;
+        const int per = p.GH * p.GW;
+        const long long b0 = g0 / per;
+        const int nvalid = (int)min((long long)128, p.M - g0);
+        const int split = (int)min((long long)nvalid, (b0 + 1) * per - g0);
+        float* d0 = p.acc + ((size_t)b0 * Cout + r) * 3;
+        atomicAdd(d0, __uint_as_float(q[0]));
+        atomicAdd(d0 + 1, __uint_as_float(q[1]) + __uint_as_float(q[2]));
+        atomicAdd(d0 + 2, __uint_as_float(q[3]) + __uint_as_float(q[4]));
+        if (split < nvalid) {
+          float* d1 = d0 + (size_t)Cout * 3;
+          atomicAdd(d1, __uint_as_float(q[5]));
+          atomicAdd(d1 + 1, __uint_as_float(q[6]) + __uint_as_float(q[7]));
+          atomicAdd(d1 + 2, __uint_as_float(q[14]) + __uint_as_float(q[15]));
+        }
+      }
+      red_unit = false;
+    };
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+    // the pixel this thread owns is fixed over the unit's run of phase pairs: the divisions are done once per unit
+    const int mt = u / p.nsplit, nt0 = (u - mt * p.nsplit) * p.cn;
+    const long long g = (long long)mt * 128 + r;
+    const bool valid = g < p.M;
+    const long long b = g / (p.GH * p.GW);
+    const int rem = (int)(g - b * (p.GH * p.GW));
+    const int oy = rem / p.GW, ox = rem - oy * p.GW;
+    const long long b0 = ((long long)mt * 128) / (p.GH * p.GW);   // a tile of 128 flat rows spans at most two images
+    const float w0 = (valid && b == b0) ? 1.f : 0.f, w1 = (valid && b != b0) ? 1.f : 0.f;
+    int a = (nt0 * 2 + half) / p.s, bq = (nt0 * 2 + half) - a * p.s;
+    for (int t = 0; t < p.cn; ++t, bq += 2) {
+      if (bq >= p.s) { bq -= p.s; ++a; }               // phase index nt*2 + half advances by 2 per tile (s >= 2)
       const long long opix = (b * OHs + (long long)oy * p.s + a) * OWs + (long long)ox * p.s + bq;
 
       if (tr) DTRACE(2, ti, 0);
@@ -237,12 +467,13 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
       float inv = 1.0f;
       if (p.mode == 1 || p.mode == 3) {
-        float mx = -INFINITY;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four chains: the warps of a half hide little latency
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (k * 32 + j < Cout) mx = fmaxf(mx, __uint_as_float(rg[k][j]));
+            if (k * 32 + j < Cout) mx4[(j >> 1) & 3] = fmaxf(mx4[(j >> 1) & 3], __uint_as_float(rg[k][j]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // exp(v - mx) = 2^(v*log2e - mx*log2e): one FFMA + one MUFU.EX2 per class (flush-to-zero: terms below 2^-126 add nothing)
         const float nmx = -mx * 1.4426950408889634f;
         float sum[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains instead of one 68-deep dependent FADD chain
@@ -257,6 +488,61 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               sum[j & 3] += e;
             }
         inv = __fdividef(1.0f, (sum[0] + sum[1]) + (sum[2] + sum[3]));
+      }
+      if (p.mode == 3 && !p.walk) {
+        // ---- fused soft centroid on the tensor cores (see the top of the file): stage E^T (A: the un-normalised exponentials)
+        // and the pixel weights (B: 1/sum folded in) of this tile; one thread issues 16 tf32 MMAs (K = 8 pixels each).
+        if (red_pending) {                               // previous tile's MMAs are done with the staging block
+          mbar_wait(rbar, red_phase);
+          red_phase ^= 1u;
+          red_pending = false;
+        }
+        if (t == 0 && red_unit) red_read();              // previous unit complete: its sums leave TMEM before they are overwritten
+        const uint32_t lbo = (uint32_t)red_lbo(Cout);
+        const uint32_t sA = smem_stg + (uint32_t)half * (uint32_t)red_a_bytes(Cout);
+        const uint32_t sB = smem_stg + 2u * (uint32_t)red_a_bytes(Cout) + (uint32_t)half * (uint32_t)kRedBBytes;
+        const uint32_t a_thr = sA + (uint32_t)(r >> 2) * lbo + (uint32_t)(r & 3) * 4u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k * 32 + j < Cout) {
+              const int c = k * 32 + j;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_thr + (uint32_t)((c >> 3) * 128 + (c & 7) * 16)), "r"(rg[k][j]) : "memory");
+            }
+        // B rows (1/sum, col hi, col lo, row hi, row lo) x (first, second image of the tile).  Everything the tensor core sees is
+        // exact in tf32: 1/sum is cut to 11 bits, its product with an (integer < 2^13) coordinate splits into an 11-bit head and
+        // an exact tail, so the numerators and the denominator carry the SAME per-pixel weight (utils/metrics.py:57-64 grids).
+        const float it = valid ? __uint_as_float(__float_as_uint(inv) & 0xffffe000u) : 0.f;
+        // grids centred on the map (signed 8..12-bit integers): the running sums stay small, which keeps the tensor core's fp32
+        // accumulation (products are aligned to the accumulator and cut, not rounded) well below the probabilities' own error
+        const float px_ = it * (float)(ox * p.s + bq - OWs / 2), py_ = it * (float)(oy * p.s + a - (int)(OHs / 2));
+        const float hx = __uint_as_float(__float_as_uint(px_) & 0xffffe000u), hy = __uint_as_float(__float_as_uint(py_) & 0xffffe000u);
+        const uint32_t b_thr = sB + (uint32_t)(r >> 2) * (uint32_t)kRedBLbo + (uint32_t)(r & 3) * 4u;
+        const uint32_t own = (b != b0) ? 5u : 0u, oth = 5u - own;      // first row of this pixel's image / of the other image
+        const float vals[5] = {it, hx, px_ - hx, hy, py_ - hy};
+#pragma unroll
+        for (uint32_t j = 0; j < 5; ++j) {
+          const uint32_t ro = own + j, rz = oth + j;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + ro * 16u), "f"(vals[j]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(b_thr + rz * 16u), "f"(0.f) : "memory");
+        }
+        fence_async_smem();                              // generic-proxy stores -> tensor-core (async proxy) reads
+        named_bar_sync(1 + half, 128);                   // A and B complete; at t == 0 every thread has also read the previous D
+        if (gt == 0) {
+          tc_fence_after();
+          const uint32_t idesc = umma_idesc_tf32(128, 16);
+          const uint64_t ad = umma_desc(sA, lbo, 128, 0);          // K group = 4 pixels (16 B); 8-class core matrices 128 B apart
+          const uint64_t bd = umma_desc(sB, kRedBLbo, 32, 0);      // overlapping 8-row blocks, see kRedBLbo
+#pragma unroll
+          for (int m2 = 0; m2 < 16; ++m2)
+            umma_tf32(dred, ad + (uint64_t)(m2 * ((2 * lbo) >> 4)), bd + (uint64_t)(m2 * ((2 * kRedBLbo) >> 4)), idesc, (t | m2) ? 1u : 0u);
+          umma_commit(rbar);
+        }
+        red_pending = true;
+        red_unit = true;
+        red_mt = mt;
+        continue;
       }
       named_bar_sync(1 + half, 128);                   // previous tile's copy-out has drained the staging buffer
 #pragma unroll
@@ -370,6 +656,10 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
+    }
+    if (red_pending) mbar_wait(rbar, red_phase);
+    if (red_unit) red_read();
+    }  // EW == 8
   }
   tc_fence_before();
   __syncthreads();
@@ -423,11 +713,13 @@ __global__ void deconv_im2col_vec4_kernel(const float4* __restrict__ in, uint2* 
 }
 
 // (x, y) = (sum p*col / sum p, sum p*row / sum p); (-1, -1) when mean(p) <= thresh (utils/metrics.py:78-80)
-__global__ void centroid_finish_kernel(const float* __restrict__ acc, long long n, double hw, double thresh, double* __restrict__ xy) {
+// (cx, cy): the origin the sums were taken about (the tensor-core reduction centres the grids, see the epilogue)
+__global__ void centroid_finish_kernel(const float* __restrict__ acc, long long n, double hw, double thresh, double cx, double cy,
+                                       double* __restrict__ xy) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double s0 = acc[i * 3], sx = acc[i * 3 + 1], sy = acc[i * 3 + 2];
-  double x = sx / s0, y = sy / s0;
+  double x = cx + sx / s0, y = cy + sy / s0;
   if (s0 / hw <= thresh) { x = -1.0; y = -1.0; }
   xy[i * 2] = x;
   xy[i * 2 + 1] = y;
@@ -439,7 +731,9 @@ constexpr size_t kSmemMax = 232448 - 4096;  // 227 KB per CTA minus the static p
 size_t fixed_smem(int Cin, int Cout) {
   const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);
   (void)cpp;
-  return (size_t)(Kp / 64) * 16384 + (size_t)2 * 128 * Cout * 4 + 1024;   // stationary A block + staging + alignment slack
+  // stationary A block + staging (modes 0 / 1: 2 x [128][Cout] fp32; mode 3: 2 x E^T + 2 x pixel weights; the MMA over-reads of A land inside the block) + alignment slack
+  const size_t stg = std::max((size_t)2 * 128 * Cout * 4, (size_t)2 * red_a_bytes(Cout) + 2 * kRedBBytes);
+  return (size_t)(Kp / 64) * 16384 + stg + 1024;
 }
 
 }  // namespace
@@ -498,7 +792,7 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
   const size_t fixed = fixed_smem(Cin, Cout);
   const size_t b_bytes = (size_t)p.BN * 128;
   p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
-  p.mode = 0; p.trace = nullptr; p.acc = nullptr;
+  p.mode = 0; p.trace = nullptr; p.acc = nullptr; p.walk = 0;
   pl->smem = fixed + (size_t)p.stages * b_bytes;
   // work units: the smallest split of the N range that still gives every SM a few units
   p.nsplit = 1;
@@ -551,6 +845,7 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
   }
   DeconvParams p = pl->p;
   p.out = out; p.mode = mode; p.trace = nullptr; p.acc = acc;
+  { const char* e = getenv("FLD_TC_DECONV_WALK"); p.walk = (e && atoi(e) != 0) ? 1 : 0; }
   if (mode == 3) {
     if (!acc) { fld_set_error("tc_deconv: mode 3 needs an accumulator buffer"); return FLD_ERR_INVALID; }
     if (pl->p.GH * pl->p.s > 65535 || pl->p.GW * pl->p.s > 65535) { fld_set_error("tc_deconv: map too large for the fused centroid"); return FLD_ERR_INVALID; }
@@ -568,18 +863,28 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
     p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
     smem = fixed + (size_t)p.stages * b_bytes;
   }
-  if (p.Cout == 68) {   // the reference's n_classes (scripts/cli.py:39, training.py:110)
-    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    deconv_gemm_kernel<68><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
+  // soft centroid over the reference's 68 classes: the 16-warp epilogue (FLD_TC_DECONV_EW8=1 keeps the 8-warp one)
+  const bool ew16 = mode == 3 && p.Cout == 68 && !p.walk && !getenv("FLD_TC_DECONV_EW8");
+  if (ew16) {
+    const size_t b_bytes = (size_t)p.BN * 128;
+    const size_t fixed = (size_t)p.kblocks * 16384 + 1024 + (size_t)2 * red_a_bytes(68) + 2 * kRedB16Bytes;
+    p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
+    smem = fixed + (size_t)p.stages * b_bytes;
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    deconv_gemm_kernel<68, 16><<<pl->grid, 64 + 32 * 16, smem, st>>>(pl->tmA, pl->tmB, p);
+  } else if (p.Cout == 68) {   // the reference's n_classes (scripts/cli.py:39, training.py:110)
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68, kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    deconv_gemm_kernel<68, kEpiWarps><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
   } else {
-    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    deconv_gemm_kernel<0><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
+    FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<0, kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    deconv_gemm_kernel<0, kEpiWarps><<<pl->grid, kThreads, smem, st>>>(pl->tmA, pl->tmB, p);
   }
   FLD_LAUNCHED();
   if (mode == 3) {
     const long long n = (long long)pl->B * p.Cout;
     const double hw = (double)(p.GH * p.s) * (double)(p.GW * p.s);
-    centroid_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, n, hw, thresh, (double*)out);
+    const double cx = p.walk ? 0.0 : (double)(p.GW * p.s / 2), cy = p.walk ? 0.0 : (double)(p.GH * p.s / 2);
+    centroid_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, n, hw, thresh, cx, cy, (double*)out);
     FLD_LAUNCHED();
   }
   if (p.trace) {  // dump CTA 0's event log: "<role> <tag> <clock>" per line
