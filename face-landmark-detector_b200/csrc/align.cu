@@ -108,18 +108,17 @@ __device__ void invert_affine(const double* M, double* iM) {
   iM[3] = i10; iM[4] = i11; iM[5] = da(dm(-i10, M[2]), -dm(i11, M[5]));
 }
 
-// Warp 0 of the CTA: fit (or take the caller's matrix), validate, invert; every thread reads `fit` after a __syncthreads.
-__device__ __forceinline__ void cta_fit(Fit& fit, int face, int F, const int32_t* __restrict__ face2frame,
-                                        const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int five_point,
-                                        const double* __restrict__ M_in, double* __restrict__ M_out, bool write_M, int tid) {
-  if (tid >= 32) return;
+// One warp: fit (or take the caller's matrix), validate, invert.  `fit` is in shared memory; lane 0 finishes it.
+__device__ __forceinline__ void warp_fit(Fit& fit, int face, int F, const int32_t* __restrict__ face2frame,
+                                         const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int five_point,
+                                         const double* __restrict__ M_in, double* __restrict__ M_out, bool write_M, int lane) {
   if (M_in) {
-    if (tid < 6) fit.M[tid] = M_in[(size_t)face * 6 + tid];
+    if (lane < 6) fit.M[lane] = M_in[(size_t)face * 6 + lane];
   } else {
-    fit_similarity_warp(marks + (size_t)face * N * 2, N, tmpl, five_point, fit.M, tid);
+    fit_similarity_warp(marks + (size_t)face * N * 2, N, tmpl, five_point, fit.M, lane);
   }
   __syncwarp();
-  if (tid == 0) {
+  if (lane == 0) {
     int ok = 1;
     for (int i = 0; i < 6; ++i) ok &= isfinite(fit.M[i]) ? 1 : 0;
     const int fr = face2frame[face];
@@ -128,6 +127,14 @@ __device__ __forceinline__ void cta_fit(Fit& fit, int face, int F, const int32_t
     fit.ok = ok;
     if (M_out && write_M) for (int i = 0; i < 6; ++i) M_out[(size_t)face * 6 + i] = fit.M[i];
   }
+}
+
+// Warp 0 of the CTA fits; every thread reads `fit` after a __syncthreads.
+__device__ __forceinline__ void cta_fit(Fit& fit, int face, int F, const int32_t* __restrict__ face2frame,
+                                        const float* __restrict__ marks, int N, const double* __restrict__ tmpl, int five_point,
+                                        const double* __restrict__ M_in, double* __restrict__ M_out, bool write_M, int tid) {
+  if (tid >= 32) return;
+  warp_fit(fit, face, F, face2frame, marks, N, tmpl, five_point, M_in, M_out, write_M, tid);
 }
 
 __device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
@@ -183,6 +190,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -221,7 +229,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 // ------------------------------------------------------------------------------------------------ tile kernel
 constexpr int kTile = 16;          // output tile edge
-constexpr int kTileThreads = 64;   // 16 rows x 4 groups of 4 pixels
+constexpr int kTileWarps = 4;      // warps of a CTA; how many of them take tiles depends on the face's box size (see the ring pool below)
+constexpr int kTileThreads = 32 * kTileWarps;
 constexpr int kNumCls = 8;
 constexpr int kMaxOut = 128;       // tables are static shared arrays
 constexpr int kMaxBuf = 4;
@@ -230,7 +239,27 @@ constexpr int kRingBytes = 27 * 1024;
 __host__ __device__ constexpr int cls_side(int k) { return k == 0 ? 16 : k == 1 ? 20 : k == 2 ? 24 : k == 3 ? 32 : k == 4 ? 40 : k == 5 ? 48 : k == 6 ? 64 : 80; }
 __host__ __device__ constexpr int cls_bw(int k) { return (3 * cls_side(k) + 15 + 15) & ~15; }
 
+// Box class of a face from the linear part of its inverse map: a 16 x 16 tile spans 15 * (|i00| + |i01|) source columns and
+// 15 * (|i10| + |i11|) rows, plus the second tap and the floor / round slack.  -1: no class fits (per-pixel global path).
+__device__ __forceinline__ int box_class(const Fit& fit, int ring_bytes) {
+  const double ex = 15.0 * (fabs(fit.iM[0]) + fabs(fit.iM[1])), ey = 15.0 * (fabs(fit.iM[3]) + fabs(fit.iM[4]));
+  const double e = fmax(ex, ey) + 3.0;
+  int cls = -1;
+  if (e < 4096.0) {
+    const int side = (int)ceil(e);
+    for (int k = 0; k < kNumCls; ++k) if (side <= cls_side(k)) { cls = k; break; }
+  }
+  if (cls >= 0 && (cls_bw(cls) * cls_side(cls) + 16 + 127) / 128 * 128 > ring_bytes) cls = -1;   // box larger than the ring
+  return cls;
+}
+
 struct AlignMaps { CUtensorMap m[kNumCls]; };
+
+// Ordered mode (large batches): the fit runs in its own kernel, one warp per face, and a counting sort orders the faces by
+// decreasing box size, so that the expensive faces (strongly reduced ones: up to 20 KB per tile box) start first and the cheap
+// ones fill the tail.  Measured on config C4 (4096 faces, scales 0.28 - 1.4): random order 0.194 ms, big-first 0.168 ms.
+struct PreFit { double iM[6]; int ok; int key; };
+constexpr int kOrderKeys = 16;        // key 0: degenerate fit (zero crop), 1 + class, kNumCls + 1: global path
 
 struct TileArgs {
   const uint8_t* frames;
@@ -242,6 +271,10 @@ struct TileArgs {
   uint8_t* crops;
   int F, H, W, N, five_point, out_h, out_w, ysplit;
   int ring_bytes;   // dynamic shared memory of the box ring (multiple of 256)
+  int min_bufs;     // buffers a warp should have before another warp is activated
+  int pair_max;     // warps pair up on a tile when at most this many boxes fit the ring
+  const struct PreFit* fits;   // ordered mode: per-face inverse maps from align_fit_kernel (null: the CTA fits its face itself)
+  const int32_t* perm;         // ordered mode: faces by decreasing box size
 };
 
 // Blend of four consecutive output pixels from the staged source box.  bxv / byv: the row's X0 / Y0; av / bv: adelta / bdelta of
@@ -256,8 +289,11 @@ __device__ __forceinline__ void blend4_smem(int bxv, int byv, const int4& a4, co
     const uint32_t fx = X & 31, fy = Y & 31;
     const uint32_t o = base + (uint32_t)(sy * BW + sx * 3 + corr);
     const uint32_t oa = o & ~3u, k8 = (o & 3u) << 3;
-    const uint32_t l0 = lds32(oa), l1 = lds32(oa + 4), l2 = lds32(oa + 8);
-    const uint32_t m0 = lds32(oa + BW), m1 = lds32(oa + BW + 4), m2 = lds32(oa + BW + 8);
+    // bytes o .. o+5 of a row: the third word is needed only when o = 3 (mod 4) — a predicated load for a quarter of the lanes
+    // (the shared-memory gathers are bank-conflict bound: 2.4 wavefronts per load with all lanes active)
+    const uint32_t l0 = lds32(oa), l1 = lds32(oa + 4), m0 = lds32(oa + BW), m1 = lds32(oa + BW + 4);
+    uint32_t l2 = 0u, m2 = 0u;
+    if (k8 == 24u) { l2 = lds32(oa + 8); m2 = lds32(oa + BW + 8); }
     const uint32_t w0 = __funnelshift_r(l0, l1, k8), w1 = __funnelshift_r(l1, l2, k8);   // row sy  : c0 c1 c2 c0' | c1' c2'
     const uint32_t v0 = __funnelshift_r(m0, m1, k8), v1 = __funnelshift_r(m1, m2, k8);   // row sy+1
     const uint32_t t0 = prmt(w0, w1, 0x5241u), t1 = prmt(v0, v1, 0x5241u);                 // c1 c1' c2 c2'
@@ -276,8 +312,8 @@ __device__ __forceinline__ void blend4_smem(int bxv, int byv, const int4& a4, co
   w[2] = prmt(q[2], q[3], 0x6542u);
 }
 
-// Warp-autonomous pipelines: the CTA (2 warps) shares the face's fit, coordinate tables and tile origins; after that each warp
-// walks its own tiles (alternate tiles of the CTA's tile rows) with its own half of the shared-memory ring and its own mbarriers:
+// Warp-autonomous pipelines: the CTA (4 warps) shares the face's fit, coordinate tables and tile origins; after that each active
+// warp walks its own tiles (every n_act-th tile of the CTA's tile rows) with its own slice of the shared-memory ring and its own mbarriers:
 // lane 0 issues the TMA load of the tile after next into the buffer the warp has just finished reading (__syncwarp), so there is
 // no CTA-wide barrier in the loop.  A lane blends 2 x 4 pixels of a tile (rows r and r + 8, four consecutive columns).
 __global__ void __launch_bounds__(kTileThreads)
@@ -286,21 +322,22 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   __shared__ Fit fit;
   __shared__ __align__(16) int s_ad[kMaxOut], s_bd[kMaxOut], s_X0[kMaxOut], s_Y0[kMaxOut];
   __shared__ int s_ox[(kMaxOut / kTile) * (kMaxOut / kTile)], s_oy[(kMaxOut / kTile) * (kMaxOut / kTile)];   // per tile of this CTA: box origin (byte column, row); ox = INT_MIN -> global path
-  __shared__ __align__(8) uint64_t full_bar[2][kMaxBuf];
+  __shared__ __align__(8) uint64_t full_bar[kTileWarps][kMaxBuf], empty_bar[kTileWarps][kMaxBuf];
   __shared__ int s_cls;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int face = blockIdx.x;
+  const int face = p.perm ? p.perm[blockIdx.x] : blockIdx.x;
   const int tiles_x = p.out_w / kTile, tiles_y = p.out_h / kTile;
   const int ty_per = (tiles_y + p.ysplit - 1) / p.ysplit;
   const int ty0 = blockIdx.y * ty_per, ty1 = min(tiles_y, ty0 + ty_per);
   const int T = max(0, ty1 - ty0) * tiles_x;
   const uint32_t ring = (smem_u32(ring_raw) + 127u) & ~127u;
 
-  cta_fit(fit, face, p.F, p.face2frame, p.marks, p.N, p.tmpl, p.five_point, p.M_in, p.M_out, blockIdx.y == 0, tid);
-  if (tid == 0) {
-    for (int i = 0; i < 2 * kMaxBuf; ++i) mbar_init(smem_u32(&full_bar[0][0]) + 8 * i, 1);
-    fence_mbar_init();
+  if (p.fits) {
+    if (tid < 6) fit.iM[tid] = p.fits[face].iM[tid];
+    if (tid == 6) fit.ok = p.fits[face].ok;
+  } else {
+    cta_fit(fit, face, p.F, p.face2frame, p.marks, p.N, p.tmpl, p.five_point, p.M_in, p.M_out, blockIdx.y == 0, tid);
   }
   __syncthreads();
   uint8_t* crop = p.crops + (size_t)face * p.out_h * p.out_w * 3;
@@ -314,17 +351,13 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   for (int x = tid; x < p.out_w; x += kTileThreads) { s_ad[x] = tab_ad(fit, x); s_bd[x] = tab_bd(fit, x); }
   for (int y = ty0 * kTile + tid; y < ty1 * kTile; y += kTileThreads) { s_X0[y] = tab_X0(fit, y); s_Y0[y] = tab_Y0(fit, y); }
   if (tid == 0) {
-    // box class from the linear part: a 16 x 16 tile spans 15 * (|i00| + |i01|) source columns and 15 * (|i10| + |i11|) rows,
-    // plus the second tap and the floor/round slack
-    const double ex = 15.0 * (fabs(fit.iM[0]) + fabs(fit.iM[1])), ey = 15.0 * (fabs(fit.iM[3]) + fabs(fit.iM[4]));
-    const double e = fmax(ex, ey) + 3.0;
-    int cls = -1;
-    if (e < 4096.0) {
-      const int side = (int)ceil(e);
-      for (int k = 0; k < kNumCls; ++k) if (side <= cls_side(k)) { cls = k; break; }
-    }
-    if (cls >= 0 && (cls_bw(cls) * cls_side(cls) + 16 + 127) / 128 * 128 > p.ring_bytes) cls = -1;   // box larger than the ring: global path
+    const int cls = box_class(fit, p.ring_bytes);
     s_cls = cls;
+    for (int i = 0; i < kTileWarps * kMaxBuf; ++i) {
+      mbar_init(smem_u32(&full_bar[0][0]) + 8 * i, 1);
+      mbar_init(smem_u32(&empty_bar[0][0]) + 8 * i, 2);     // used by warp pairs only
+    }
+    fence_mbar_init();
   }
   __syncthreads();
   const int cls = s_cls;
@@ -346,71 +379,129 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   }
   __syncthreads();
 
-  // ---- per-warp pipeline.  Buffers: each warp owns half of the ring when a box fits there at least once; a box larger than
-  // half the ring (the largest class) leaves the whole ring to warp 0 alone.
+  // ---- pipelines.  The ring is a pool shared by the CTA's warps.  A face with small boxes (magnified or 1:1 faces, where the
+  // blend is instruction / shared-memory bound) runs four autonomous warps, each with its own tiles, buffers and mbarriers and no
+  // barrier between warps.  When at most two boxes fit the pool (strongly reduced faces: HBM bound, and with one warp per box a
+  // face took 49 x ~3 us — the long poles of a mixed batch) the warps work in PAIRS on one tile, eight rows each, and hand the
+  // buffer back through an mbarrier with two arrivals.
   const int frame_idx = p.face2frame[face];
   const uint8_t* frame = p.frames + (size_t)frame_idx * p.H * p.W * 3;
   const size_t row = (size_t)p.W * 3;
   const uint32_t box_bytes = (uint32_t)(BW * BH);
   const uint32_t buf_pitch = (box_bytes + 16u + 127u) & ~127u;       // + 16: the last pixel's third word may lie past the box
-  const uint32_t half_ring = (uint32_t)(p.ring_bytes / 2) & ~127u;
-  const bool solo = cls >= 0 && buf_pitch > half_ring;               // one warp, whole ring
-  if (solo && warp != 0) return;
-  const int nbuf = cls < 0 ? 1 : solo ? max(1, min(kMaxBuf, (int)(p.ring_bytes / buf_pitch))) : max(1, min(kMaxBuf, (int)(half_ring / buf_pitch)));
-  const uint32_t my_ring = solo ? ring : ring + warp * half_ring;
-  const uint32_t my_bar = smem_u32(&full_bar[warp][0]);
-  const int t_first = solo ? 0 : warp, t_step = solo ? 1 : 2;
+  int n_grp = kTileWarps, g = 1, nbuf = 1;
+  if (cls >= 0) {
+    const int fit_boxes = (int)((uint32_t)p.ring_bytes / ((uint32_t)p.min_bufs * buf_pitch));
+    if (fit_boxes <= p.pair_max) { g = 2; n_grp = max(1, min(kTileWarps / 2, fit_boxes)); }
+    else n_grp = min(kTileWarps, fit_boxes);
+    nbuf = max(1, min(kMaxBuf, (int)((uint32_t)p.ring_bytes / ((uint32_t)n_grp * buf_pitch))));
+  }
+  const int grp = g == 2 ? warp >> 1 : warp, wi = g == 2 ? warp & 1 : 0;
+  if (grp >= n_grp) return;
+  const uint32_t my_ring = ring + (uint32_t)(grp * nbuf) * buf_pitch;
+  const uint32_t my_bar = smem_u32(&full_bar[grp][0]), my_empty = smem_u32(&empty_bar[grp][0]);
+  const int t_first = grp, t_step = n_grp;
   const int n_my = t_first < T ? (T - t_first + t_step - 1) / t_step : 0;
   const CUtensorMap* tm = &maps.m[cls >= 0 ? cls : 0];
+  const bool issuer = lane == 0 && wi == 0;
 
-  auto issue = [&](int i, int b) {   // lane 0: load the box of this warp's i-th tile into buffer b (= i % nbuf)
+  auto issue = [&](int i, int b) {   // issuer lane: load the box of this group's i-th tile into buffer b (= i % nbuf)
     const int t = t_first + i * t_step;
     const int ox = s_ox[t];
     if (ox == INT_MIN) return;
     mbar_arrive_expect_tx(my_bar + 8u * b, box_bytes);
     tma_load_3d(my_ring + b * buf_pitch, tm, my_bar + 8u * b, ox >> 2, s_oy[t], frame_idx);   // 32-bit elements: column = byte / 4
   };
-  if (lane == 0) for (int i = 0; i < min(nbuf, n_my); ++i) issue(i, i);
+  if (issuer) for (int i = 0; i < min(nbuf, n_my); ++i) issue(i, i);
 
   const int yl = lane >> 2, xg = (lane & 3) << 2;
-  uint32_t phase_bits = 0u;                 // bit b = parity the next wait on buffer b expects (global-path tiles skip their slot)
+  uint32_t phase_bits = 0u, empty_bits = 0u;   // bit b = parity the next wait on buffer b expects (global-path tiles skip their slot)
   int tx = t_first % tiles_x, ty = ty0 + t_first / tiles_x, buf = 0;
   for (int i = 0; i < n_my; ++i) {
     const int t = t_first + i * t_step;
-    const int y = ty * kTile + yl, x = tx * kTile + xg;
+    const int x = tx * kTile + xg;
     const int4 a4 = *reinterpret_cast<const int4*>(&s_ad[x]);
     const int4 b4 = *reinterpret_cast<const int4*>(&s_bd[x]);
     const int ox = s_ox[t], oy = s_oy[t];
-    uint32_t wA[3], wB[3];
-    if (ox != INT_MIN) {
+    const bool staged = ox != INT_MIN;
+    uint32_t base = 0u;
+    int corr = 0;
+    if (staged) {
       mbar_wait(my_bar + 8u * buf, (phase_bits >> buf) & 1u);
       phase_bits ^= 1u << buf;
-      const uint32_t base = my_ring + buf * buf_pitch;
-      const int corr = -oy * BW - ox;
-      blend4_smem(s_X0[y], s_Y0[y], a4, b4, base, corr, BW, wA);
-      blend4_smem(s_X0[y + 8], s_Y0[y + 8], a4, b4, base, corr, BW, wB);
-    } else {
-      const int av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-      uint32_t qa[4], qb[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        qa[j] = blend_px_global3(frame, p.H, p.W, row, (s_X0[y] + av[j]) >> 5, (s_Y0[y] + bv[j]) >> 5);
-        qb[j] = blend_px_global3(frame, p.H, p.W, row, (s_X0[y + 8] + av[j]) >> 5, (s_Y0[y + 8] + bv[j]) >> 5);
-      }
-      wA[0] = prmt(qa[0], qa[1], 0x4210u); wA[1] = prmt(qa[1], qa[2], 0x5421u); wA[2] = prmt(qa[2], qa[3], 0x6542u);
-      wB[0] = prmt(qb[0], qb[1], 0x4210u); wB[1] = prmt(qb[1], qb[2], 0x5421u); wB[2] = prmt(qb[2], qb[3], 0x6542u);
+      base = my_ring + buf * buf_pitch;
+      corr = -oy * BW - ox;
     }
-    const uint32_t off = (uint32_t)(y * p.out_w + x) * 3u;
-    uint32_t* dA = reinterpret_cast<uint32_t*>(crop + off);
-    uint32_t* dB = reinterpret_cast<uint32_t*>(crop + off + (uint32_t)(8 * p.out_w * 3));
-    dA[0] = wA[0]; dA[1] = wA[1]; dA[2] = wA[2];
-    dB[0] = wB[0]; dB[1] = wB[1]; dB[2] = wB[2];
-    __syncwarp();          // every lane has finished reading this tile's buffer
-    if (lane == 0 && i + nbuf < n_my) issue(i + nbuf, buf);
+    auto do_row = [&](int y) {      // four pixels of output row y
+      uint32_t w[3];
+      if (staged) {
+        blend4_smem(s_X0[y], s_Y0[y], a4, b4, base, corr, BW, w);
+      } else {
+        const int av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        uint32_t q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = blend_px_global3(frame, p.H, p.W, row, (s_X0[y] + av[j]) >> 5, (s_Y0[y] + bv[j]) >> 5);
+        w[0] = prmt(q[0], q[1], 0x4210u); w[1] = prmt(q[1], q[2], 0x5421u); w[2] = prmt(q[2], q[3], 0x6542u);
+      }
+      uint32_t* d = reinterpret_cast<uint32_t*>(crop + (uint32_t)(y * p.out_w + x) * 3u);
+      d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
+    };
+    if (g == 1) {
+      do_row(ty * kTile + yl);
+      do_row(ty * kTile + yl + 8);
+      __syncwarp();          // every lane has finished reading this tile's buffer
+      if (issuer && i + nbuf < n_my) issue(i + nbuf, buf);
+    } else {
+      do_row(ty * kTile + wi * 8 + yl);
+      __syncwarp();
+      if (lane == 0 && staged) mbar_arrive(my_empty + 8u * buf);
+      if (issuer && i + nbuf < n_my) {
+        if (staged) { mbar_wait(my_empty + 8u * buf, (empty_bits >> buf) & 1u); empty_bits ^= 1u << buf; }
+        issue(i + nbuf, buf);
+      }
+    }
     if (++buf == nbuf) buf = 0;
     tx += t_step;
-    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    while (tx >= tiles_x) { tx -= tiles_x; ++ty; }     // a narrow output can have fewer tile columns than the step
   }
+}
+
+// ------------------------------------------------------------------------------------------------ ordered mode: fit + order
+constexpr int kFitWarps = 4;
+__global__ void __launch_bounds__(32 * kFitWarps)
+align_fit_kernel(const int32_t* __restrict__ face2frame, int F, const float* __restrict__ marks, int N, const double* __restrict__ tmpl,
+                 int five_point, const double* __restrict__ M_in, double* __restrict__ M_out, int B, int ring_bytes,
+                 PreFit* __restrict__ fits) {
+  __shared__ Fit sfit[kFitWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int face = blockIdx.x * kFitWarps + warp;
+  if (face >= B) return;
+  Fit& fit = sfit[warp];
+  warp_fit(fit, face, F, face2frame, marks, N, tmpl, five_point, M_in, M_out, true, lane);
+  __syncwarp();
+  if (lane < 6) fits[face].iM[lane] = fit.ok ? fit.iM[lane] : 0.0;
+  if (lane == 6) {
+    const int cls = fit.ok ? box_class(fit, ring_bytes) : 0;
+    fits[face].ok = fit.ok;
+    fits[face].key = !fit.ok ? 0 : (cls < 0 ? kNumCls + 1 : cls + 1);
+  }
+}
+
+// One CTA: counting sort of the faces by key, largest key first.  Faces with equal keys land in arbitrary order (shared-memory
+// atomics) — the order only schedules the work, every face's result is independent of it.
+__global__ void __launch_bounds__(1024)
+align_order_kernel(const PreFit* __restrict__ fits, int B, int32_t* __restrict__ perm) {
+  __shared__ int hist[kOrderKeys], offs[kOrderKeys];
+  if (threadIdx.x < kOrderKeys) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&hist[fits[i].key], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = kOrderKeys - 1; k >= 0; --k) { offs[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) perm[atomicAdd(&offs[fits[i].key], 1)] = i;
 }
 
 // ------------------------------------------------------------------------------------------------ generic kernel
@@ -566,9 +657,11 @@ int get_align_maps(const fld_handle* h, const uint8_t* frames, int F, int H, int
   return FLD_OK;
 }
 
+size_t align_scratch_bytes(int B) { return (size_t)std::max(B, 0) * (sizeof(PreFit) + sizeof(int32_t)) + 64; }
+
 int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int C, const int32_t* face2frame,
                  const float* marks, int N, const double* tmpl, int Nt, int five_point, const double* M_in, int B,
-                 int out_h, int out_w, double* M_out, uint8_t* crops, cudaStream_t st) {
+                 int out_h, int out_w, double* M_out, uint8_t* crops, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   int rc = fld_enter(h);
   if (rc) return rc;
   if (B == 0) return FLD_OK;   // empty batch: nothing to read or write (empty tensors have null data pointers)
@@ -594,15 +687,35 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
     a.F = F; a.H = H; a.W = W; a.N = N; a.five_point = five_point; a.out_h = out_h; a.out_w = out_w;
     // split a face's tile rows over several CTAs while the grid would otherwise be only a few waves deep
     const int tiles_y = out_h / kTile;
-    // measured on C4 (4096 faces): 2 CTAs per face 0.199 ms, 1: 0.211, 4: 0.218, 7: 0.277 (the per-CTA fit + tables then dominate):
-    // aim at ~8 k CTAs, i.e. a few waves of the ~1000 resident ones
-    a.ysplit = (int)std::max(1ll, std::min((long long)tiles_y, (8192ll + B - 1) / B));
+    // measured (4-warp CTAs, fit fused): 1024 faces 84 / 66 / 64 / 77 us with 1 / 2 / 4 / 7 CTAs per face, 2047 faces 125 / 109 / 117 / 146,
+    // 4096 faces 202 / 187 / 220 / -: aim at ~4 k CTAs, at least two per face (the per-CTA fit + tables dominate beyond that)
+    a.ysplit = (int)std::max(1ll, std::min((long long)tiles_y, std::max(2ll, (4096ll + B - 1) / B)));
     { const char* e = getenv("FLD_ALIGN_YSPLIT"); if (e && atoi(e) > 0) a.ysplit = std::min(tiles_y, atoi(e)); }
     a.ring_bytes = kRingBytes;
+    a.min_bufs = 1; a.pair_max = 2;
+    { const char* e = getenv("FLD_ALIGN_PAIR_MAX"); if (e && atoi(e) >= 0 && atoi(e) <= 8) a.pair_max = atoi(e); }
+    { const char* e = getenv("FLD_ALIGN_MIN_BUFS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) a.min_bufs = atoi(e); }
     { const char* e = getenv("FLD_ALIGN_RING_KB"); if (e && atoi(e) >= 4 && atoi(e) <= 200) a.ring_bytes = atoi(e) * 1024; }
     const size_t smem = (size_t)a.ring_bytes + 128 + 32;
     FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FLD_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    a.fits = nullptr; a.perm = nullptr;
+    // ordered mode: worth its two small extra launches once the grid is several waves deep
+    int order_min = 2048;
+    { const char* e = getenv("FLD_ALIGN_ORDER_MIN"); if (e) order_min = atoi(e); }
+    if (scratch && B >= order_min) {
+      FLD_REQUIRE(scratch_bytes >= align_scratch_bytes(B), "fld_align: scratch of %zu bytes, need %zu", scratch_bytes, align_scratch_bytes(B));
+      FLD_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "fld_align: scratch must be 16-byte aligned");
+      PreFit* fits = reinterpret_cast<PreFit*>(scratch);
+      int32_t* perm = reinterpret_cast<int32_t*>(fits + B);
+      align_fit_kernel<<<fld_div_up(B, kFitWarps), 32 * kFitWarps, 0, st>>>(face2frame, F, marks, N, tmpl, five_point, M_in, M_out, B, a.ring_bytes, fits);
+      FLD_LAUNCHED();
+      align_order_kernel<<<1, 1024, 0, st>>>(fits, B, perm);
+      FLD_LAUNCHED();
+      a.fits = fits; a.perm = perm;
+      a.ysplit = 1;
+      { const char* e = getenv("FLD_ALIGN_YSPLIT"); if (e && atoi(e) > 0) a.ysplit = std::min(tiles_y, atoi(e)); }
+    }
     align_tile_kernel<<<dim3(B, a.ysplit), kTileThreads, smem, st>>>(maps, a);
     FLD_LAUNCHED();
     return FLD_OK;
@@ -632,12 +745,34 @@ extern "C" int fld_align(fld_handle* h, const uint8_t* frames, int F, int H, int
                          const float* marks, int N, const double* tmpl, int Nt, int five_point, int B, int out_h, int out_w,
                          double* M_out, uint8_t* crops, fld_stream stream) {
   return launch_align(h, frames, F, H, W, C, face2frame, marks, N, tmpl, Nt, five_point, nullptr, B, out_h, out_w, M_out,
-                      crops, (cudaStream_t)stream);
+                      crops, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int fld_warp_affine(fld_handle* h, const uint8_t* frames, int F, int H, int W, int C, const int32_t* face2frame,
                                const double* M, int B, int out_h, int out_w, uint8_t* crops, fld_stream stream) {
   if (!M) { fld_set_error("fld_warp_affine: null M"); return FLD_ERR_INVALID; }
   return launch_align(h, frames, F, H, W, C, face2frame, nullptr, 0, nullptr, 0, 0, M, B, out_h, out_w, nullptr, crops,
-                      (cudaStream_t)stream);
+                      nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" size_t fld_align_scratch_bytes(fld_handle* h, int B) {
+  (void)h;
+  return align_scratch_bytes(B);
+}
+
+extern "C" int fld_align_ordered(fld_handle* h, const uint8_t* frames, int F, int H, int W, int C, const int32_t* face2frame,
+                                 const float* marks, int N, const double* tmpl, int Nt, int five_point, int B, int out_h, int out_w,
+                                 double* M_out, uint8_t* crops, void* scratch, size_t scratch_bytes, fld_stream stream) {
+  if (!scratch) { fld_set_error("fld_align_ordered: null scratch"); return FLD_ERR_INVALID; }
+  return launch_align(h, frames, F, H, W, C, face2frame, marks, N, tmpl, Nt, five_point, nullptr, B, out_h, out_w, M_out,
+                      crops, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int fld_warp_affine_ordered(fld_handle* h, const uint8_t* frames, int F, int H, int W, int C, const int32_t* face2frame,
+                                       const double* M, int B, int out_h, int out_w, uint8_t* crops, void* scratch,
+                                       size_t scratch_bytes, fld_stream stream) {
+  if (!M) { fld_set_error("fld_warp_affine_ordered: null M"); return FLD_ERR_INVALID; }
+  if (!scratch) { fld_set_error("fld_warp_affine_ordered: null scratch"); return FLD_ERR_INVALID; }
+  return launch_align(h, frames, F, H, W, C, face2frame, nullptr, 0, nullptr, 0, 0, M, B, out_h, out_w, nullptr, crops,
+                      scratch, scratch_bytes, (cudaStream_t)stream);
 }

@@ -69,6 +69,9 @@ SIGNATURES = {
     "fld_decode_heatmap_xy": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _sz, _vp]),
     "fld_align": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fld_warp_affine": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "fld_align_scratch_bytes": (ctypes.c_size_t, [_vp, _i]),
+    "fld_align_ordered": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "fld_warp_affine_ordered": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, ctypes.c_size_t, _vp]),
     "fld_launch_count": (ctypes.c_uint64, []),
 }
 

@@ -87,9 +87,26 @@ def _template_device(template, device):
     return t
 
 
+ALIGN_ORDER_MIN_FACES = 2048     # from here on the library warps the faces in order of decreasing box size (needs a scratch buffer)
+
+
+def _align_scratch(lib, device, B, scratch):
+    """uint8 scratch tensor for the ordered alignment calls (fld_align_scratch_bytes), or None for small batches."""
+    if B < ALIGN_ORDER_MIN_FACES:
+        return None
+    need = int(lib.fld_align_scratch_bytes(N.handle(device), B))
+    if scratch is None:
+        return torch.empty((need,), dtype=torch.uint8, device=device)
+    if scratch.numel() * scratch.element_size() < need or scratch.device != device:
+        raise ValueError("align scratch needs %d bytes on %s" % (need, device))
+    return scratch
+
+
 def align_device(frames, face2frame, marks, template=None, out_size=(112, 112), five_point=True, return_matrix=True, out=None,
-                 out_matrix=None):
-    """Umeyama fit + cv2.warpAffine-exact warp on device.  marks float32 CUDA [B,N,2] in frame pixels."""
+                 out_matrix=None, scratch=None):
+    """Umeyama fit + cv2.warpAffine-exact warp on device.  marks float32 CUDA [B,N,2] in frame pixels.  Batches of
+    ALIGN_ORDER_MIN_FACES faces or more go through fld_align_ordered (same results; `scratch`: optional caller-owned uint8
+    tensor, else one is taken from torch's stream-ordered allocator)."""
     lib = N.load_library()
     F, H, W, C = frames.shape
     B, Np = marks.shape[0], marks.shape[1]
@@ -100,20 +117,31 @@ def align_device(frames, face2frame, marks, template=None, out_size=(112, 112), 
     if return_matrix:
         M = torch.empty((B, 2, 3), dtype=torch.float64, device=frames.device) if out_matrix is None else out_matrix
     with torch.cuda.device(frames.device):
-        N.check(lib.fld_align(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(marks), Np, N.ptr(t),
-                              t.shape[0], int(five_point), B, oh, ow, N.ptr(M), N.ptr(crops), N.stream_ptr(frames.device)))
+        sc = _align_scratch(lib, frames.device, B, scratch)
+        if sc is None:
+            N.check(lib.fld_align(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(marks), Np, N.ptr(t),
+                                  t.shape[0], int(five_point), B, oh, ow, N.ptr(M), N.ptr(crops), N.stream_ptr(frames.device)))
+        else:
+            N.check(lib.fld_align_ordered(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(marks), Np,
+                                          N.ptr(t), t.shape[0], int(five_point), B, oh, ow, N.ptr(M), N.ptr(crops), N.ptr(sc),
+                                          sc.numel(), N.stream_ptr(frames.device)))
     return crops, M
 
 
-def warp_affine_device(frames, face2frame, M, out_size=(112, 112)):
+def warp_affine_device(frames, face2frame, M, out_size=(112, 112), scratch=None):
     lib = N.load_library()
     F, H, W, C = frames.shape
     B = M.shape[0]
     oh, ow = out_size
     crops = torch.empty((B, oh, ow, C), dtype=torch.uint8, device=frames.device)
     with torch.cuda.device(frames.device):
-        N.check(lib.fld_warp_affine(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(M), B, oh, ow,
-                                    N.ptr(crops), N.stream_ptr(frames.device)))
+        sc = _align_scratch(lib, frames.device, B, scratch)
+        if sc is None:
+            N.check(lib.fld_warp_affine(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(M), B, oh, ow,
+                                        N.ptr(crops), N.stream_ptr(frames.device)))
+        else:
+            N.check(lib.fld_warp_affine_ordered(N.handle(frames.device), N.ptr(frames), F, H, W, C, N.ptr(face2frame), N.ptr(M), B,
+                                                oh, ow, N.ptr(crops), N.ptr(sc), sc.numel(), N.stream_ptr(frames.device)))
     return crops
 
 

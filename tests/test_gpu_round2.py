@@ -245,6 +245,38 @@ def test_align_tile_equals_generic_kernel_at_c4_scale(dev, monkeypatch):
     assert torch.equal(M2, Ma) and torch.equal(crops, a)
 
 
+def test_align_ordered_equals_unordered(dev):
+    """Large batches take fld_align_ordered / fld_warp_affine_ordered (fit in its own kernel, faces warped big boxes first, warp
+    pairs on the largest boxes): 4096 faces of config C4's distribution — degenerate fits and an invalid frame index among them —
+    must equal the same faces run in chunks of 1024 through the fused kernel, byte for byte, matrices included."""
+    from keypoints_detector import prediction
+    from keypoints_detector.data import synthetic
+    from oracle import align as o_al
+    F, B = 16, 4096
+    g = torch.Generator().manual_seed(4)
+    frames = torch.randint(0, 256, (F, 1080, 1920, 3), dtype=torch.uint8, generator=g).to(dev)
+    pts, _ = synthetic.make_similarity_landmarks(B, 1080, 1920, o_al.TEMPLATE_112, seed=11)
+    pts[17] = pts[17, :1]                     # all points equal: degenerate fit -> NaN matrix, zero crop
+    pts[901, 0, 0] = np.nan
+    f2f_np = (np.arange(B) % F).astype(np.int32)
+    f2f_np[3000] = F + 5                      # invalid frame index -> zero crop
+    f2f, marks = T(f2f_np, dev), T(pts, dev)
+    assert B >= prediction.ALIGN_ORDER_MIN_FACES
+    a, Ma = prediction.align_device(frames, f2f, marks, None, (112, 112), five_point=False)
+    for c0 in range(0, B, 1024):
+        b, Mb = prediction.align_device(frames, f2f[c0:c0 + 1024].contiguous(), marks[c0:c0 + 1024].contiguous(), None, (112, 112), five_point=False)
+        assert torch.equal(a[c0:c0 + 1024], b)
+        assert torch.equal(torch.nan_to_num(Ma[c0:c0 + 1024], nan=-7.0), torch.nan_to_num(Mb, nan=-7.0))
+    assert int(a[17].max()) == 0 and int(a[901].max()) == 0 and int(a[3000].max()) == 0 and bool(torch.isnan(Ma[17]).all())
+    # caller matrices: ordered warp == chunked warp; a caller-owned scratch buffer that is too small is refused
+    Mfin = torch.nan_to_num(Ma, nan=0.0)
+    w = prediction.warp_affine_device(frames, f2f, Mfin, (112, 112))
+    for c0 in range(0, B, 1024):
+        assert torch.equal(w[c0:c0 + 1024], prediction.warp_affine_device(frames, f2f[c0:c0 + 1024].contiguous(), Mfin[c0:c0 + 1024].contiguous(), (112, 112)))
+    with pytest.raises(ValueError):
+        prediction.align_device(frames, f2f, marks, None, (112, 112), five_point=False, scratch=torch.empty(64, dtype=torch.uint8, device=dev))
+
+
 # ------------------------------------------------------------------------------------------------ scratch / capture rules
 def test_decode_scratch_is_per_call_and_stream_safe(dev):
     """Two top-n decodes of DIFFERENT maps in flight on different streams (the race the handle-owned scratch of round 1 had):
