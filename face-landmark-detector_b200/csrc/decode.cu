@@ -277,88 +277,149 @@ __global__ void soft_partial_vec4_kernel(const float4* __restrict__ hm, int HW, 
   }
 }
 
-// n <= 4, L % 4 == 0: thread (r, q) owns classes 4q .. 4q+3 of pixel lane r (one 16-byte load per pixel) and keeps a SORTED top-4
-// per class; the common path is one compare per value, an insertion is three predicated compare-and-swaps.
+// n <= 4, L % 4 == 0.  Thread (r, q) reads classes 4q .. 4q+3 of pixel lane r (one 16-byte load per pixel).  The running top four
+// of a class are NOT per-thread lists (round 1 / early round 2: every thread kept 4 x 4 sorted entries in registers; a warp took the
+// ~18-instruction insertion path whenever ANY of its 128 lists inserted, which with ~560 pixels per thread was nearly every step —
+// ncu: 13 of 32 lanes active on average, 65 warp instructions per 16-byte load, 0.39 - 0.48 of HBM).  They are four 64-bit slots per
+// class in SHARED memory, common to the CTA's pixel lanes: key = (order-preserving bits of the value) << 32 | flat pixel index, so
+// a larger key is exactly the reference's "larger value, ties to the higher index" (metrics.py:66-77).  A value is first compared
+// with the class's lower bound s_thr (the value in slot 3: that element lost to three larger keys, so four elements >= it exist);
+// only values that reach it go on — about 4 ln(pixels / 4) per class and CTA instead of per thread — and bubble down the slots with
+// atomicMax: each step leaves the larger key in the slot and carries the smaller on.  The multiset {slots} + {carried} always equals
+// the keys inserted so far minus keys that lost four times, so the final slots are the slab's top four whatever the interleaving.
+// (Replacing the smallest slot with one compare-and-swap instead measured 2x slower: 82 registers, retries during the warm-up.)
+__device__ __forceinline__ unsigned long long topn_key(float v, int p) {
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t ou = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)ou << 32) | (uint32_t)p;
+}
+__device__ __forceinline__ float topn_key_value(unsigned long long key) {
+  const uint32_t ou = (uint32_t)(key >> 32);
+  return __uint_as_float((ou & 0x80000000u) ? (ou ^ 0x80000000u) : ~ou);
+}
+__device__ __noinline__ void topn4_insert(unsigned long long* slots, float* thr, float v, int p) {
+  unsigned long long key = topn_key(v, p);
+  if (key <= *reinterpret_cast<volatile unsigned long long*>(&slots[3])) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned long long old = atomicMax(&slots[k], key);
+    key = old < key ? old : key;
+    if (key == 0ull) break;               // the slot was empty: nothing to carry on
+  }
+  const unsigned long long s3 = *reinterpret_cast<volatile unsigned long long*>(&slots[3]);
+  if (s3 != 0ull) {
+    const float w = topn_key_value(s3);
+    if (w >= 0.f) atomicMax(reinterpret_cast<int*>(thr), __float_as_int(w));
+    else atomicMin(reinterpret_cast<unsigned*>(thr), __float_as_uint(w));
+  }
+}
+
+// Work split: one CTA per (image, slab of `per` pixels), B * S CTAs = one wave of resident CTAs.  (Equal shares of the whole batch
+// across exactly the resident CTAs, straddling image boundaries, measured SLOWER: 0.289 vs 0.256 ms — a second warm-up of the
+// slots per CTA costs more than the 148-SM imbalance, which an HBM-bound kernel does not feel.)
 __global__ void __launch_bounds__(512)
 topn4_vec4_kernel(const float4* __restrict__ hm, int HW, int L4, int R, int S, int n, Cand* __restrict__ partial) {
-  const int b = blockIdx.x, s = blockIdx.y;
   const int t = threadIdx.x;
   const int q = t % L4, r = t / L4;   // blockDim.x == R * L4 exactly
-  float tv[4][4];
-  int ti[4][4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { tv[c][k] = -INFINITY; ti[c][k] = -1; }
+  const int L = L4 * 4;
+  const int b = blockIdx.x, s = blockIdx.y;
+  const int Sb = S;
+  extern __shared__ __align__(16) unsigned long long s_slots[];   // [L][4] keys, then [L] floats: the lower bounds
+  float* s_thr = reinterpret_cast<float*>(s_slots + (size_t)L * 4);
+  const uint32_t thr_addr = (uint32_t)__cvta_generic_to_shared(&s_thr[4 * q]);
+  unsigned long long* my_slots = s_slots + (size_t)(4 * q) * 4;
   const int per = (HW + S - 1) / S;
   const int p0 = s * per, p1 = min(HW, p0 + per);
+  {
+  for (int i = t; i < L * 4; i += blockDim.x) s_slots[i] = 0ull;
+  for (int i = t; i < L; i += blockDim.x) s_thr[i] = -INFINITY;
+  __syncthreads();
   const float4* base = hm + (size_t)b * HW * L4 + q;
-#define FLD_TOPN4_CONSIDER(V, P, C)                                                                      \
-  if ((V) > tv[C][3] || ((V) == tv[C][3] && ti[C][3] < 0)) {                                             \
-    if (better((V), (P), tv[C][3], ti[C][3])) {                                                          \
-      tv[C][3] = (V); ti[C][3] = (P);                                                                    \
-      _Pragma("unroll") for (int k = 3; k > 0; --k)                                                      \
-        if (better(tv[C][k], ti[C][k], tv[C][k - 1], ti[C][k - 1])) {                                    \
-          const float fv = tv[C][k]; tv[C][k] = tv[C][k - 1]; tv[C][k - 1] = fv;                         \
-          const int fi = ti[C][k]; ti[C][k] = ti[C][k - 1]; ti[C][k - 1] = fi;                           \
-        }                                                                                                \
-    }                                                                                                    \
+  float thr[4];
+#define FLD_TOPN4_LOAD_THR() \
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(thr[0]), "=f"(thr[1]), "=f"(thr[2]), "=f"(thr[3]) : "r"(thr_addr))
+#define FLD_TOPN4_CONSIDER4(V4, P)                                                          \
+  {                                                                                         \
+    if ((V4).x >= thr[0]) topn4_insert(my_slots + 0, s_thr + 4 * q + 0, (V4).x, (P));       \
+    if ((V4).y >= thr[1]) topn4_insert(my_slots + 4, s_thr + 4 * q + 1, (V4).y, (P));       \
+    if ((V4).z >= thr[2]) topn4_insert(my_slots + 8, s_thr + 4 * q + 2, (V4).z, (P));       \
+    if ((V4).w >= thr[3]) topn4_insert(my_slots + 12, s_thr + 4 * q + 3, (V4).w, (P));      \
   }
-#define FLD_TOPN4_MERGE(V, P, C)                                                                            \
-  if ((V) >= tv[C][3]) {                                                                                 \
-    if (better((V), (P), tv[C][3], ti[C][3])) {                                                          \
-      tv[C][3] = (V); ti[C][3] = (P);                                                                    \
-      _Pragma("unroll") for (int k = 3; k > 0; --k)                                                      \
-        if (better(tv[C][k], ti[C][k], tv[C][k - 1], ti[C][k - 1])) {                                    \
-          const float fv = tv[C][k]; tv[C][k] = tv[C][k - 1]; tv[C][k - 1] = fv;                         \
-          const int fi = ti[C][k]; ti[C][k] = ti[C][k - 1]; ti[C][k - 1] = fi;                           \
-        }                                                                                                \
-    }                                                                                                    \
+  int p = p0 + r;
+  for (; p + 7 * R < p1; p += 8 * R) {  // eight independent 16-byte loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(base + (size_t)(p + k * R) * L4);
+    FLD_TOPN4_LOAD_THR();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) FLD_TOPN4_CONSIDER4(v[k], p + k * R)
   }
-#define FLD_TOPN4_CONSIDER4(V4, P) \
-  { FLD_TOPN4_CONSIDER((V4).x, (P), 0) FLD_TOPN4_CONSIDER((V4).y, (P), 1) FLD_TOPN4_CONSIDER((V4).z, (P), 2) FLD_TOPN4_CONSIDER((V4).w, (P), 3) }
-  // descending pixel order: ties (higher index wins) arriving later never displace an entry
-  int cnt = (p0 + r < p1) ? (p1 - (p0 + r) + R - 1) / R : 0;
-  int p = p0 + r + (cnt - 1) * R;
-  for (; cnt >= 4; cnt -= 4, p -= 4 * R) {  // four independent 16-byte loads in flight per thread
-    const float4 v0 = __ldg(base + (size_t)p * L4), v1 = __ldg(base + (size_t)(p - R) * L4);
-    const float4 v2 = __ldg(base + (size_t)(p - 2 * R) * L4), v3 = __ldg(base + (size_t)(p - 3 * R) * L4);
-    FLD_TOPN4_CONSIDER4(v0, p) FLD_TOPN4_CONSIDER4(v1, p - R) FLD_TOPN4_CONSIDER4(v2, p - 2 * R) FLD_TOPN4_CONSIDER4(v3, p - 3 * R)
-  }
-  for (; cnt > 0; --cnt, p -= R) {
+  FLD_TOPN4_LOAD_THR();
+  for (; p < p1; p += R) {
     const float4 v = __ldg(base + (size_t)p * L4);
     FLD_TOPN4_CONSIDER4(v, p)
   }
-  // block-level selection over the R pixel lanes: lane r == 0 folds the other lanes' lists into its own
-  extern __shared__ Cand cand4[];   // [R][L][4]
-  const int L = L4 * 4;
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { cand4[((size_t)r * L + 4 * q + c) * 4 + k].v = tv[c][k]; cand4[((size_t)r * L + 4 * q + c) * 4 + k].idx = ti[c][k]; }
+#undef FLD_TOPN4_CONSIDER4
+#undef FLD_TOPN4_LOAD_THR
   __syncthreads();
-  if (r == 0) {
-    for (int rr = 1; rr < R; ++rr)
+  // one thread per class: sort the four slots (descending) and emit the first n
+  if (t < L) {
+    unsigned long long k4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const Cand c0 = cand4[((size_t)rr * L + 4 * q + 0) * 4 + k], c1 = cand4[((size_t)rr * L + 4 * q + 1) * 4 + k];
-        const Cand c2 = cand4[((size_t)rr * L + 4 * q + 2) * 4 + k], c3 = cand4[((size_t)rr * L + 4 * q + 3) * 4 + k];
-        if (c0.idx >= 0) FLD_TOPN4_MERGE(c0.v, c0.idx, 0)   // other lanes' indices are not ordered against ours: exact tie rule
-        if (c1.idx >= 0) FLD_TOPN4_MERGE(c1.v, c1.idx, 1)
-        if (c2.idx >= 0) FLD_TOPN4_MERGE(c2.v, c2.idx, 2)
-        if (c3.idx >= 0) FLD_TOPN4_MERGE(c3.v, c3.idx, 3)
+    for (int k = 0; k < 4; ++k) k4[k] = s_slots[(size_t)t * 4 + k];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3 - a; ++c)
+        if (k4[c] < k4[c + 1]) { const unsigned long long x = k4[c]; k4[c] = k4[c + 1]; k4[c + 1] = x; }
+    Cand* dst = partial + (((size_t)b * Sb + s) * L + t) * n;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n) {
+        if (k4[k] == 0ull) { dst[k].v = -INFINITY; dst[k].idx = -1; }
+        else { dst[k].v = topn_key_value(k4[k]); dst[k].idx = (int)(uint32_t)k4[k]; }
       }
+  }
+  }
+}
+
+// Merge of the per-slab top-n lists of topn4_vec4_kernel (n <= 4): one thread per (image, class), the running top four as keys in
+// registers (the generic merge keeps its selection in global scratch: 18 us for 64 x 68 lists), then the reference's accumulation.
+__global__ void topn4_merge_kernel(const Cand* __restrict__ partial, int W, int L, int Sb, int n, int B, float thresh,
+                                   double* __restrict__ xy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, l)
+  if (i >= B * L) return;
+  const int b = i / L, l = i - b * L;
+  unsigned long long k4[4] = {0ull, 0ull, 0ull, 0ull};
+  for (int j = 0; j < Sb; ++j) {
+    const Cand* src = partial + (((size_t)b * Sb + j) * L + l) * n;
+    for (int k = 0; k < n; ++k) {
+      const Cand c = src[k];
+      if (c.idx < 0) continue;
+      unsigned long long key = topn_key(c.v, c.idx);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      Cand* dst = partial + (((size_t)b * S + s) * L + 4 * q + c) * n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < n) { dst[k].v = tv[c][k]; dst[k].idx = ti[c][k]; }
+      for (int a = 0; a < 4; ++a)
+        if (key > k4[a]) { const unsigned long long x = k4[a]; k4[a] = key; key = x; }
     }
   }
-#undef FLD_TOPN4_CONSIDER4
-#undef FLD_TOPN4_MERGE
-#undef FLD_TOPN4_CONSIDER
+  // accumulate in ascending order like metrics.py:70-74: hsum in float32 (np.float32 scalars), i0/i1 in float64
+  float hsum = 0.f;
+  double i0 = 0.0, i1 = 0.0;
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    if (k >= n || k4[k] == 0ull) continue;
+    const float h = topn_key_value(k4[k]);
+    const int idx = (int)(uint32_t)k4[k];
+    const int row = idx / W, col = idx - row * W;
+    hsum = __fadd_rn(hsum, h);
+    i0 = __dadd_rn(i0, __dmul_rn((double)row, (double)h));
+    i1 = __dadd_rn(i1, __dmul_rn((double)col, (double)h));
+  }
+  i0 = i0 / (double)hsum;
+  i1 = i1 / (double)hsum;
+  if (__fdiv_rn(hsum, (float)n) <= thresh) { i0 = -1.0; i1 = -1.0; }  // metrics.py:78-79
+  xy[(size_t)i * 2 + 0] = i1;
+  xy[(size_t)i * 2 + 1] = i0;
 }
 
 }  // namespace
@@ -422,7 +483,7 @@ XyPlan xy_plan(const fld_handle* h, int B, int H, int W, int L, int n_points, bo
   if (n_points < 1) {
     if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, soft_partial_vec4_kernel, threads, (size_t)R * L * 3 * sizeof(double));
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, soft_partial_kernel, threads, 0);
-  } else if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn4_vec4_kernel, threads, (size_t)R * L * 4 * sizeof(Cand));
+  } else if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn4_vec4_kernel, threads, (size_t)L * 36);
   else if (n_points <= 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<4>, threads, (size_t)R * L * n_points * sizeof(Cand));
   else if (n_points <= 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<16>, threads, (size_t)R * L * n_points * sizeof(Cand));
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topn_partial_kernel<FLD_MAX_TOPN>, threads, 0);
@@ -430,6 +491,7 @@ XyPlan xy_plan(const fld_handle* h, int B, int H, int W, int L, int n_points, bo
   int S = max(1, (h->sm_count * occ) / max(B, 1));
   S = max(1, min(S, HW / (64 * R) > 0 ? HW / (64 * R) : 1));
   p.S = min(S, 65535);
+  if (n_points >= 1 && vec4) { p.bytes = (size_t)B * p.S * L * n_points * sizeof(Cand); return p; }
   if (n_points < 1) p.bytes = (size_t)B * p.S * R * L * 3 * sizeof(double);
   else p.bytes = (size_t)B * p.S * R * L * n_points * sizeof(Cand) + (size_t)B * L * n_points * sizeof(Cand);
   return p;
@@ -485,8 +547,14 @@ extern "C" int fld_decode_heatmap_xy(fld_handle* h, const float* hm, int B, int 
     FLD_CUDA(cudaFuncSetAttribute(topn_partial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
     FLD_CUDA(cudaFuncSetAttribute(topn_partial_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   }
-  if (vec4) topn4_vec4_kernel<<<grid, threads, (size_t)R * L * 4 * sizeof(Cand), st>>>((const float4*)hm, HW, L / 4, R, S, n, partial);
-  else if (n <= 4) topn_partial_kernel<4><<<grid, threads, csm, st>>>(hm, HW, L, R, S, n, partial);
+  if (vec4) {
+    topn4_vec4_kernel<<<grid, threads, (size_t)L * 36, st>>>((const float4*)hm, HW, L / 4, R, S, n, partial);
+    FLD_LAUNCHED();
+    topn4_merge_kernel<<<fld_div_up(nBL, 128), 128, 0, st>>>(partial, W, L, S, n, B, (float)thresh, xy);
+    FLD_LAUNCHED();
+    return FLD_OK;
+  }
+  if (n <= 4) topn_partial_kernel<4><<<grid, threads, csm, st>>>(hm, HW, L, R, S, n, partial);
   else if (n <= 16) topn_partial_kernel<16><<<grid, threads, csm, st>>>(hm, HW, L, R, S, n, partial);
   else topn_partial_kernel<FLD_MAX_TOPN><<<grid, threads, 0, st>>>(hm, HW, L, R, S, n, partial);
   FLD_LAUNCHED();
