@@ -532,7 +532,7 @@ def run_gpu(args, rank, world, local_rank):
         roof = tensor_roof("tcgen05 conv trunk: conv_halo_kernel x3 (conv2..conv4) + conv_tma_kernel (conv5), 4 launches/step",
                            sum(conv_flops[1:5]) * B, float(per_layer[1:5].sum()) * 1e-3,
                            {"traffic": traffic, "traffic_source": traffic_src, "traffic_note": "DRAM bytes per launch set at batch 256"})
-        roof_cnn = tensor_roof("whole CNN: conv1 (conv_first_kernel) + conv2..conv5 + FC, 6-7 launches/step",
+        roof_cnn = tensor_roof("whole CNN: conv1 (conv_s2d_kernel) + conv2..conv5 + FC (split-K conv_tma_kernel + dense_reduce_kernel), 7 launches/step",
                                (sum(conv_flops) + fc_flops) * B, float(per_layer.sum()) * 1e-3)
     else:
         peak = 75.0  # fp32 FMA nominal: 148 SMs x 128 lanes x 2 x ~1.97 GHz

@@ -216,6 +216,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while its predecessor in
+// the stream still runs; it must wait here before touching the predecessor's results (a no-op for an ordinary launch)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -326,6 +330,7 @@ align_tile_kernel(const __grid_constant__ AlignMaps maps, const TileArgs p) {
   __shared__ int s_cls;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.perm) pdl_wait();                       // ordered mode: the order kernel's permutation (and, through it, the fit kernel's maps)
   const int face = p.perm ? p.perm[blockIdx.x] : blockIdx.x;
   const int tiles_x = p.out_w / kTile, tiles_y = p.out_h / kTile;
   const int ty_per = (tiles_y + p.ysplit - 1) / p.ysplit;
@@ -471,8 +476,9 @@ constexpr int kFitWarps = 4;
 __global__ void __launch_bounds__(32 * kFitWarps)
 align_fit_kernel(const int32_t* __restrict__ face2frame, int F, const float* __restrict__ marks, int N, const double* __restrict__ tmpl,
                  int five_point, const double* __restrict__ M_in, double* __restrict__ M_out, int B, int ring_bytes,
-                 PreFit* __restrict__ fits) {
+                 PreFit* __restrict__ fits, int32_t* __restrict__ keys) {
   __shared__ Fit sfit[kFitWarps];
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int face = blockIdx.x * kFitWarps + warp;
   if (face >= B) return;
@@ -483,25 +489,27 @@ align_fit_kernel(const int32_t* __restrict__ face2frame, int F, const float* __r
   if (lane == 6) {
     const int cls = fit.ok ? box_class(fit, ring_bytes) : 0;
     fits[face].ok = fit.ok;
-    fits[face].key = !fit.ok ? 0 : (cls < 0 ? kNumCls + 1 : cls + 1);
+    keys[face] = fits[face].key = !fit.ok ? 0 : (cls < 0 ? kNumCls + 1 : cls + 1);
   }
 }
 
 // One CTA: counting sort of the faces by key, largest key first.  Faces with equal keys land in arbitrary order (shared-memory
 // atomics) — the order only schedules the work, every face's result is independent of it.
 __global__ void __launch_bounds__(1024)
-align_order_kernel(const PreFit* __restrict__ fits, int B, int32_t* __restrict__ perm) {
+align_order_kernel(const int32_t* __restrict__ keys, int B, int32_t* __restrict__ perm) {
   __shared__ int hist[kOrderKeys], offs[kOrderKeys];
+  pdl_launch_dependents();
   if (threadIdx.x < kOrderKeys) hist[threadIdx.x] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&hist[fits[i].key], 1);
+  pdl_wait();                                   // the fit kernel's keys
+  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&hist[keys[i]], 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int k = kOrderKeys - 1; k >= 0; --k) { offs[k] = acc; acc += hist[k]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x) perm[atomicAdd(&offs[fits[i].key], 1)] = i;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) perm[atomicAdd(&offs[keys[i]], 1)] = i;
 }
 
 // ------------------------------------------------------------------------------------------------ generic kernel
@@ -657,7 +665,7 @@ int get_align_maps(const fld_handle* h, const uint8_t* frames, int F, int H, int
   return FLD_OK;
 }
 
-size_t align_scratch_bytes(int B) { return (size_t)std::max(B, 0) * (sizeof(PreFit) + sizeof(int32_t)) + 64; }
+size_t align_scratch_bytes(int B) { return (size_t)std::max(B, 0) * (sizeof(PreFit) + 2 * sizeof(int32_t)) + 64; }
 
 int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int C, const int32_t* face2frame,
                  const float* marks, int N, const double* tmpl, int Nt, int five_point, const double* M_in, int B,
@@ -707,14 +715,25 @@ int launch_align(fld_handle* h, const uint8_t* frames, int F, int H, int W, int 
       FLD_REQUIRE(scratch_bytes >= align_scratch_bytes(B), "fld_align: scratch of %zu bytes, need %zu", scratch_bytes, align_scratch_bytes(B));
       FLD_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "fld_align: scratch must be 16-byte aligned");
       PreFit* fits = reinterpret_cast<PreFit*>(scratch);
-      int32_t* perm = reinterpret_cast<int32_t*>(fits + B);
-      align_fit_kernel<<<fld_div_up(B, kFitWarps), 32 * kFitWarps, 0, st>>>(face2frame, F, marks, N, tmpl, five_point, M_in, M_out, B, a.ring_bytes, fits);
+      int32_t* keys = reinterpret_cast<int32_t*>(fits + B);
+      int32_t* perm = keys + B;
+      align_fit_kernel<<<fld_div_up(B, kFitWarps), 32 * kFitWarps, 0, st>>>(face2frame, F, marks, N, tmpl, five_point, M_in, M_out, B, a.ring_bytes, fits, keys);
       FLD_LAUNCHED();
-      align_order_kernel<<<1, 1024, 0, st>>>(fits, B, perm);
+      // the two dependents start under programmatic serialization: their launch latency and prologues overlap the predecessor
+      cudaLaunchAttribute pdl[1];
+      pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      pdl[0].val.programmaticStreamSerializationAllowed = 1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = pdl; cfg.numAttrs = 1;
+      FLD_CUDA(cudaLaunchKernelEx(&cfg, align_order_kernel, (const int32_t*)keys, B, perm));
       FLD_LAUNCHED();
       a.fits = fits; a.perm = perm;
       a.ysplit = 1;
       { const char* e = getenv("FLD_ALIGN_YSPLIT"); if (e && atoi(e) > 0) a.ysplit = std::min(tiles_y, atoi(e)); }
+      cfg.gridDim = dim3(B, a.ysplit); cfg.blockDim = dim3(kTileThreads); cfg.dynamicSmemBytes = smem;
+      FLD_CUDA(cudaLaunchKernelEx(&cfg, align_tile_kernel, maps, a));
+      FLD_LAUNCHED();
+      return FLD_OK;
     }
     align_tile_kernel<<<dim3(B, a.ysplit), kTileThreads, smem, st>>>(maps, a);
     FLD_LAUNCHED();

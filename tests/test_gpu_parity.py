@@ -655,6 +655,30 @@ def test_no_out_of_bounds_writes(dev):
         torch.cuda.synchronize(dev)
         assert intact(raw, pad), dtype
         assert (out.sum(-1) - 1).abs().max().item() < 1e-4
+    # ordered alignment (fit kernel + counting sort + tile kernel): crops, matrices and the caller's scratch, exactly sized
+    B = prediction.ALIGN_ORDER_MIN_FACES
+    pts, _ = synthetic.make_similarity_landmarks(B, 240, 320, prediction.TEMPLATE_112, seed=53, scale=(0.9, 1.4))
+    f2b = T((np.arange(B) % 2).astype(np.int32), dev)
+    lib = N_lib()
+    need = int(lib.fld_align_scratch_bytes(prediction.N.handle(dev), B))
+    rs, scratch, ps = guarded((need,), torch.uint8)
+    ra, aligned, pa = guarded((B, 112, 112, 3), torch.uint8)
+    rM, M, pM = guarded((B, 2, 3), torch.float64)
+    prediction.align_device(frames, f2b, T(pts, dev), None, (112, 112), False, True, out=aligned, out_matrix=M, scratch=scratch)
+    torch.cuda.synchronize(dev)
+    assert intact(rs, ps) and intact(ra, pa) and intact(rM, pM)
+    # top-4 heat-map decode: partial lists in the caller's scratch, exactly sized
+    from keypoints_detector.utils import metrics
+    hm = torch.rand((3, 40, 56, 68), device=dev)
+    need = int(lib.fld_decode_heatmap_scratch_bytes(prediction.N.handle(dev), 3, 40, 56, 68, 4))
+    rs, scratch, ps = guarded((need,), torch.uint8)
+    rx, xy, px = guarded((3, 136), torch.float64)
+    prediction.N.check(lib.fld_decode_heatmap_xy(prediction.N.handle(dev), prediction.N.ptr(hm), 3, 40, 56, 68, 4, 0.0, prediction.N.ptr(xy),
+                                                 prediction.N.ptr(scratch), need, prediction.N.stream_ptr(dev)))
+    torch.cuda.synchronize(dev)
+    assert intact(rs, ps) and intact(rx, px)
+    ref = metrics.heatmap_xy_device(hm, 4, 0.0)
+    assert torch.equal(ref.view(-1), xy.view(-1))
 
 
 def N_lib():

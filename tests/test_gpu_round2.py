@@ -275,6 +275,23 @@ def test_align_ordered_equals_unordered(dev):
         assert torch.equal(w[c0:c0 + 1024], prediction.warp_affine_device(frames, f2f[c0:c0 + 1024].contiguous(), Mfin[c0:c0 + 1024].contiguous(), (112, 112)))
     with pytest.raises(ValueError):
         prediction.align_device(frames, f2f, marks, None, (112, 112), five_point=False, scratch=torch.empty(64, dtype=torch.uint8, device=dev))
+    # the three launches (two of them programmatic dependents) inside a captured CUDA graph, caller-owned scratch
+    lib = prediction.N.load_library()
+    sc = torch.empty(int(lib.fld_align_scratch_bytes(prediction.N.handle(dev), B)), dtype=torch.uint8, device=dev)
+    out2, M2 = torch.empty_like(a), torch.empty_like(Ma)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        prediction.align_device(frames, f2f, marks, None, (112, 112), five_point=False, out=out2, out_matrix=M2, scratch=sc)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        prediction.align_device(frames, f2f, marks, None, (112, 112), five_point=False, out=out2, out_matrix=M2, scratch=sc)
+    for _ in range(2):
+        out2.zero_(); M2.zero_()
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        assert torch.equal(out2, a) and torch.equal(torch.nan_to_num(M2, nan=-7.0), torch.nan_to_num(Ma, nan=-7.0))
 
 
 # ------------------------------------------------------------------------------------------------ scratch / capture rules

@@ -19,7 +19,7 @@ from keypoints_detector.utils import metrics  # noqa: E402
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-which = sys.argv[1:] or ["pipeline", "fcn", "encoders"]
+which = sys.argv[1:] or ["pipeline", "fcn", "encoders", "align"]
 if "pipeline" in which:
     frames = torch.from_numpy(synthetic.make_frames(2, 240, 320, seed=1)).to(dev)
     boxes = torch.from_numpy(synthetic.make_boxes(5, 240, 320, seed=2, max_side=150)).to(dev)
@@ -47,4 +47,15 @@ if "encoders" in which:
         p = m.forward_device(torch.randn((1, 64, 64, 3), device=dev) * 40, "bfloat16")
         torch.cuda.synchronize()
         print(m.model_name, float(p.sum()))
+if "align" in which:
+    # ordered mode (fit kernel + counting sort + tile kernel with warp pairs) on a few faces of every box class
+    os.environ["FLD_ALIGN_ORDER_MIN"] = "8"
+    prediction.ALIGN_ORDER_MIN_FACES = 8
+    frames = torch.from_numpy(synthetic.make_frames(2, 1080, 1920, seed=1)).to(dev)
+    pts, _ = synthetic.make_similarity_landmarks(24, 1080, 1920, prediction.TEMPLATE_112, seed=5, scale=(0.2, 1.4))
+    f2f = torch.from_numpy((np.arange(24) % 2).astype(np.int32)).to(dev)
+    a, M = prediction.align_device(frames, f2f, torch.from_numpy(pts).to(dev), None, (112, 112), five_point=False)
+    w = prediction.warp_affine_device(frames, f2f, torch.nan_to_num(M), (112, 112))
+    torch.cuda.synchronize()
+    print("align ordered", int(a.sum()), bool(torch.equal(a, w)))
 print("sanitize target done")
