@@ -1,3 +1,5 @@
+"""Alignment kernel sweeps: run C4 and single-scale bands under the FLD_ALIGN_* environment switches given on the command line
+(e.g. `python tools/align_sweep.py none FLD_ALIGN_YSPLIT=2 FLD_ALIGN_RING_KB=24,FLD_ALIGN_PAIR_MAX=0`)."""
 import os, sys, json, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
