@@ -35,6 +35,7 @@ struct LayerRt {
   bool s2d = false;             // first layer through tc_conv_s2d.cu (pool window in the TMEM columns)
   bool dc_fuse_softmax = false; // the following SOFTMAX layer is computed in this layer's epilogue (logits never reach HBM)
   bool skip = false;            // SOFTMAX layer folded into the preceding transposed conv
+  bool x3_cmap = false;         // FLD_BF16X3: the last transposed conv has a tensor-core variant for class-map-only forwards (d_wbf)
   bool needs_weights = false, has_weights = false;
   std::vector<float> w_host;  // folded fp32: conv [K][Cout]; deconv [k][k][Cin][Cout]; dense [In][Out]
   std::vector<float> b_host;  // folded bias [Cout] (empty = none)
@@ -213,6 +214,17 @@ int infer_shapes(fld_net* net) {
         L.x3 = true;
       }
     }
+    // the final DECONV -> SOFTMAX pair: a class-map-only forward (fld_net_forward_classmap; argmax is invariant under the softmax)
+    // runs the transposed conv on the tensor cores with split operands and takes the argmax in its epilogue; probabilities and
+    // landmark decodes keep the fp32 kernels
+    if (nL >= 2 && !getenv("FLD_X3_DECONV_OFF")) {
+      LayerRt& L = net->layers[nL - 2];
+      const LayerRt& S = net->layers[nL - 1];
+      const TensorInfo& a = net->tensors[L.d.in0];
+      if (L.d.op == FLD_OP_DECONV && S.d.op == FLD_OP_SOFTMAX && S.d.in0 == nL - 1 && L.d.kh == L.d.kw && a.dtype == FLD_F32 &&
+          tc_deconv_x3_supported(L.d.kh, L.d.stride, a.c, L.d.cout))
+        L.x3_cmap = true;
+    }
   }
   return FLD_OK;
 }
@@ -239,6 +251,13 @@ uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
+}
+
+float bf2f(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
 }
 
 }  // namespace
@@ -392,6 +411,12 @@ extern "C" int fld_net_finalize(fld_net* net) {
     } else if (L.path == PATH_SIMT) {
       FLD_CUDA(cudaMalloc(&L.d_w, L.w_host.size() * sizeof(float)));
       FLD_CUDA(cudaMemcpy(L.d_w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+      if (L.d.op == FLD_OP_DECONV && L.x3_cmap) {
+        std::vector<uint16_t> pk;
+        tc_deconv_x3_pack_weights(L.w_host.data(), L.d.stride, a.c, Cout, f2bf, bf2f, pk);
+        FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
+        FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      }
     } else if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
       // strided stem (tc_conv_stem.cu): [KG][Cout/8][8][8], k' = 4*tap + c
       std::vector<uint16_t> pk((size_t)Cout * 8 * tc_conv_stem_kgroups(L.d.kh), 0);
@@ -467,6 +492,7 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && L.s2d) m = std::max(m, tc_conv_s2d_scratch_bytes(L.g, B));
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
       m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
+    if (L.d.op == FLD_OP_DECONV && L.x3_cmap) m = std::max(m, tc_deconv_x3_scratch_bytes(B, a.h, a.w, a.c));
   }
   return m;
 }
@@ -611,6 +637,18 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
           rc = tc_deconv_run(plan, (const float*)pin, dst, mode, st, acc, xy_thresh);
           if (mode == 2) cmap_done = true;
           if (mode >= 3) xy_done = true;
+        } else if (L.x3_cmap && cmap_out && !out && !xy_out) {
+          // class map only: split-operand tensor-core transposed conv, argmax in the epilogue; the SOFTMAX layer that follows is skipped
+          TcDeconvPlan* plan = nullptr;
+          for (auto& pe : L.dplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
+          if (!plan) {
+            rc = tc_deconv_plan_create(net->h, dense_scratch, L.d_wbf, B, a.h, a.w, a.c, d.cout, d.stride, &plan, 1);
+            if (rc) return rc;
+            if (L.dplans.size() >= 16 && net->retained == 0) { tc_deconv_plan_destroy(L.dplans.front().plan); L.dplans.erase(L.dplans.begin()); }
+            L.dplans.push_back({B, (const void*)dense_scratch, plan});
+          }
+          rc = tc_deconv_run(plan, (const float*)pin, cmap_out, 2, st, nullptr, 0.0);
+          cmap_done = true;
         } else if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
         else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
@@ -643,6 +681,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         break;
       case FLD_OP_SOFTMAX:
         if (L.skip) break;  // computed by the preceding transposed conv's epilogue
+        if (cmap_done && !out && !xy_out && i + 1 == net->layers.size()) break;   // only the class map was asked for, and it is done
         FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: SOFTMAX input must be fp32", i);
         rc = simt_softmax((const float*)pin, (float*)pout, (long long)B * a.h * a.w, a.c, st);
         break;

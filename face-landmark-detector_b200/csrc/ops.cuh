@@ -92,7 +92,12 @@ size_t tc_deconv_scratch_bytes(int B, int IH, int IW, int Cin);  // bf16 im2col 
 void tc_deconv_pack_weights(const float* w_phase /*[s*s][2][2][Cin][Cout]*/, int s, int Cin, int Cout, uint16_t (*f2bf)(float),
                             std::vector<uint16_t>& out /*[s*s*cpp][Kp]*/);
 int tc_deconv_plan_create(const fld_handle* h, void* scratch, const __nv_bfloat16* w_packed, int B, int IH, int IW, int Cin, int Cout,
-                          int s, TcDeconvPlan** out);
+                          int s, TcDeconvPlan** out, int x3 = 0);
+// FLD_BF16X3 variant (class maps only, tc_deconv_run mode 2): split operands, three product terms in one accumulation
+bool tc_deconv_x3_supported(int k, int s, int Cin, int Cout);
+size_t tc_deconv_x3_scratch_bytes(int B, int IH, int IW, int Cin);
+void tc_deconv_x3_pack_weights(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), float (*bf2f)(uint16_t),
+                               std::vector<uint16_t>& out);
 void tc_deconv_plan_destroy(TcDeconvPlan* p);
 // mode 0: fp32 logits, 1: softmax probabilities, 2: int64 argmax class map,
 // 3: fused soft centroid of the softmax output -> out = double [B][Cout][2] (x, y), acc = fp32 scratch of tc_deconv_acc_bytes

@@ -38,7 +38,8 @@ struct DeconvParams {
   int GH, GW;           // neighbourhood grid = (h+1, w+1)
   int s, Cout, cpp;     // stride, real / padded channels per phase
   int BN;               // 2 * cpp
-  int kblocks;          // Kp / 64
+  int kblocks;          // weight k-blocks per tile (Kp / 64; FLD_BF16X3: the three product terms' blocks, see tc_deconv_plan_create)
+  int a_blocks;         // 64-column slabs of the stationary A block; weight block kb multiplies A slab kb (kb < a_blocks) or kb - a_blocks
   int n_ntiles, mtiles, total_tiles;
   int nsplit, cn, units;  // work unit = (M tile, run of cn consecutive N tiles); units = mtiles * nsplit
   int stages;
@@ -99,7 +100,7 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
   const uint32_t smem_a = smem_base;                                   // stationary A block: kblocks slabs [128][64] (SW128)
-  const uint32_t smem_b = smem_a + (uint32_t)p.kblocks * a_bytes;      // weight ring: slabs [BN][64] (b_bytes multiple of 1024)
+  const uint32_t smem_b = smem_a + (uint32_t)p.a_blocks * a_bytes;     // weight ring: slabs [BN][64] (b_bytes multiple of 1024)
   const uint32_t smem_stg = smem_b + (uint32_t)p.stages * b_bytes;     // 2 x [128][Cout] fp32 staging
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
@@ -133,8 +134,8 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (!first) { mbar_wait(afree, afree_phase); afree_phase ^= 1; }          // MMAs reading the previous A block are done
         first = false;
         DTRACE(0, ti, 3);
-        mbar_arrive_expect_tx(afull, (uint32_t)p.kblocks * a_bytes);
-        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(smem_a + kb * a_bytes, &tmA, afull, kb * 64, mt * 128);  // rows past M: zero fill
+        mbar_arrive_expect_tx(afull, (uint32_t)p.a_blocks * a_bytes);
+        for (int kb = 0; kb < p.a_blocks; ++kb) tma_load_2d(smem_a + kb * a_bytes, &tmA, afull, kb * 64, mt * 128);  // rows past M: zero fill
         for (int nt = nc * p.cn; nt < (nc + 1) * p.cn; ++nt)
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -171,7 +172,7 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_wait(full0 + 8 * stage, phase);
             DTRACE(1, ti, 1);
             tc_fence_after();
-            const uint64_t ad = adesc0 + (uint64_t)(kb * a_step);
+            const uint64_t ad = adesc0 + (uint64_t)((kb < p.a_blocks ? kb : kb - p.a_blocks) * a_step);
             const uint64_t bd = bdesc0 + (uint64_t)(stage * b_step);
             umma_bf16(d, ad, bd, idesc, accum);
             umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
@@ -712,6 +713,32 @@ __global__ void deconv_im2col_vec4_kernel(const float4* __restrict__ in, uint2* 
   }
 }
 
+// FLD_BF16X3: A row = [hi(4C) | lo(4C) | 0 ...] with hi = bf16(v), lo = bf16(v - hi); one thread per K entry pair of a row
+__global__ void deconv_im2col_x3_kernel(const float* __restrict__ in, __nv_bfloat162* __restrict__ A, long long M, int h, int w, int C, int KpA) {
+  const int kp2 = KpA >> 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * kp2) return;
+  const long long g = i / kp2;
+  const int k0 = (int)(i - g * kp2) * 2;
+  const int GW = w + 1, GH = h + 1;
+  const long long b = g / (GH * GW);
+  const int rem = (int)(g - b * (GH * GW));
+  const int oy = rem / GW, ox = rem - oy * GW;
+  float v[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    int k = k0 + e;
+    const bool lo = k >= 4 * C;
+    if (lo) k -= 4 * C;
+    const int t = k / C, c = k - t * C;
+    const int iy = oy - 1 + (t >> 1), ix = ox - 1 + (t & 1);
+    const float x = (t < 4 && iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(in + ((b * h + iy) * w + ix) * C + c) : 0.f;
+    const float hi = __bfloat162float(__float2bfloat16_rn(x));
+    v[e] = lo ? x - hi : hi;
+  }
+  A[i] = __floats2bfloat162_rn(v[0], v[1]);
+}
+
 // (x, y) = (sum p*col / sum p, sum p*row / sum p); (-1, -1) when mean(p) <= thresh (utils/metrics.py:78-80)
 // (cx, cy): the origin the sums were taken about (the tensor-core reduction centres the grids, see the epilogue)
 __global__ void centroid_finish_kernel(const float* __restrict__ acc, long long n, double hw, double thresh, double cx, double cy,
@@ -754,6 +781,33 @@ bool tc_deconv_supported(int k, int s, int Cin, int Cout) {
 
 size_t tc_deconv_scratch_bytes(int B, int IH, int IW, int Cin) { return (size_t)B * (IH + 1) * (IW + 1) * tc_deconv_kp(Cin) * 2; }
 
+// FLD_BF16X3 (class-map mode only: no staging fits beside the larger A block).  The three product terms x_hi w_hi + x_lo w_hi +
+// x_hi w_lo run in ONE accumulation: A row = [x_hi(4C) | x_lo(4C) | 0] (KpA columns, stationary), weight row = [w_hi | w_hi | 0] over
+// the same KpA columns followed by [w_lo | 0] over Kp1 = pad64(4C) columns that multiply the A block's FIRST slabs again (their columns
+// past 4C hold x_lo where the weights are zero).  up8 of fcn_8: 9 + 5 weight blocks instead of 5, the epilogue unchanged.
+static int x3_kpa(int Cin) { return (8 * Cin + 63) / 64 * 64; }
+size_t tc_deconv_x3_scratch_bytes(int B, int IH, int IW, int Cin) { return (size_t)B * (IH + 1) * (IW + 1) * x3_kpa(Cin) * 2; }
+bool tc_deconv_x3_supported(int k, int s, int Cin, int Cout) {
+  if (!tc_deconv_supported(k, s, Cin, Cout)) return false;
+  const size_t fixed = (size_t)(x3_kpa(Cin) / 64) * 16384 + 1024, b_bytes = (size_t)2 * tc_deconv_cpp(Cout) * 128;
+  return fixed + 2 * b_bytes <= kSmemMax;
+}
+void tc_deconv_x3_pack_weights(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), float (*bf2f)(uint16_t),
+                               std::vector<uint16_t>& out) {
+  const int KpA = x3_kpa(Cin), Kp1 = tc_deconv_kp(Cin), KpW = KpA + Kp1, cpp = tc_deconv_cpp(Cout), nph = s * s;
+  out.assign((size_t)nph * cpp * KpW, 0);
+  for (int ph = 0; ph < nph; ++ph)
+    for (int t = 0; t < 4; ++t)
+      for (int c = 0; c < Cin; ++c)
+        for (int o = 0; o < Cout; ++o) {
+          const float wv = w_phase[(((size_t)ph * 4 + t) * Cin + c) * Cout + o];
+          const uint16_t hi = f2bf(wv), lo = f2bf(wv - bf2f(hi));
+          uint16_t* row = &out[((size_t)ph * cpp + o) * KpW];
+          const size_t k = (size_t)t * Cin + c;
+          row[k] = hi; row[4 * Cin + k] = hi; row[KpA + k] = lo;
+        }
+}
+
 // w_phase: [s*s][2][2][Cin][Cout] (net.cu set_weights)  ->  out bf16 [s*s*cpp][Kp], k = (u*2+v)*Cin + c
 void tc_deconv_pack_weights(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), std::vector<uint16_t>& out) {
   const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout), nph = s * s;
@@ -771,25 +825,26 @@ struct TcDeconvPlan {
   int grid;
   size_t smem;
   const void* scratch;
-  int B, h, w, C, Kp;
+  int B, h, w, C, Kp, x3;
 };
 
 int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat16* w_packed, int B, int IH, int IW, int Cin, int Cout,
-                          int s, TcDeconvPlan** out) {
+                          int s, TcDeconvPlan** out, int x3) {
   if (!hd->encode_tiled) { fld_set_error("cuTensorMapEncodeTiled entry point not available"); return FLD_ERR_CUDA; }
   if (!tc_deconv_supported(2 * s, s, Cin, Cout)) { fld_set_error("tc_deconv: unsupported geometry"); return FLD_ERR_INVALID; }
   EncodeTiledFn enc = (EncodeTiledFn)hd->encode_tiled;
   TcDeconvPlan* pl = new TcDeconvPlan();
   DeconvParams& p = pl->p;
-  const int Kp = tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);
+  const int Kp = x3 ? x3_kpa(Cin) : tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);   // columns of A
+  const int KpW = x3 ? Kp + tc_deconv_kp(Cin) : Kp;                                   // columns of the weight matrix
   p.out = nullptr;
   p.GH = IH + 1; p.GW = IW + 1;
   p.M = (long long)B * p.GH * p.GW;
-  p.s = s; p.Cout = Cout; p.cpp = cpp; p.BN = 2 * cpp; p.kblocks = Kp / 64;
+  p.s = s; p.Cout = Cout; p.cpp = cpp; p.BN = 2 * cpp; p.kblocks = KpW / 64; p.a_blocks = Kp / 64;
   p.n_ntiles = s * s / 2;
   p.mtiles = (int)((p.M + 127) / 128);
   p.total_tiles = p.mtiles * p.n_ntiles;
-  const size_t fixed = fixed_smem(Cin, Cout);
+  const size_t fixed = x3 ? (size_t)(Kp / 64) * 16384 + 1024 : fixed_smem(Cin, Cout);
   const size_t b_bytes = (size_t)p.BN * 128;
   p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
   p.mode = 0; p.trace = nullptr; p.acc = nullptr; p.walk = 0;
@@ -800,7 +855,7 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
   p.cn = p.n_ntiles / p.nsplit;
   p.units = p.mtiles * p.nsplit;
   pl->grid = std::min(p.units, hd->sm_count);
-  pl->scratch = scratch; pl->B = B; pl->h = IH; pl->w = IW; pl->C = Cin; pl->Kp = Kp;
+  pl->scratch = scratch; pl->B = B; pl->h = IH; pl->w = IW; pl->C = Cin; pl->Kp = Kp; pl->x3 = x3;
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)p.M};
     cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
@@ -811,8 +866,8 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
     if (r != CUDA_SUCCESS) { delete pl; fld_set_error("cuTensorMapEncodeTiled(deconv A) failed: %d", (int)r); return FLD_ERR_CUDA; }
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)s * s * cpp};
-    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)KpW, (cuuint64_t)s * s * cpp};
+    cuuint64_t strides[1] = {(cuuint64_t)KpW * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w_packed), dims, strides, box, es,
@@ -834,7 +889,12 @@ size_t tc_deconv_acc_bytes(int B, int Cout) { return (size_t)B * Cout * 3 * size
 
 int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st, float* acc, double thresh) {
   if (pl->p.total_tiles == 0) return FLD_OK;
-  if (pl->C % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+  if (pl->x3) {
+    if (mode != 2) { fld_set_error("tc_deconv: the FLD_BF16X3 variant produces class maps only"); return FLD_ERR_INVALID; }
+    const long long n = pl->p.M * (pl->Kp / 2);
+    deconv_im2col_x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat162*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C, pl->Kp);
+    FLD_LAUNCHED();
+  } else if (pl->C % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
     deconv_im2col_vec4_kernel<<<(unsigned)((pl->p.M + 7) / 8), 256, 0, st>>>((const float4*)in, (uint2*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C / 4,
                                                                           pl->Kp / 4);
     FLD_LAUNCHED();
@@ -859,7 +919,7 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
   }
   size_t smem = pl->smem;
   if (mode == 2) {   // class-map mode stages nothing: the staging bytes deepen the weight ring instead
-    const size_t b_bytes = (size_t)p.BN * 128, fixed = (size_t)p.kblocks * 16384 + 1024;
+    const size_t b_bytes = (size_t)p.BN * 128, fixed = (size_t)p.a_blocks * 16384 + 1024;
     p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
     smem = fixed + (size_t)p.stages * b_bytes;
   }
@@ -867,7 +927,7 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
   const bool ew16 = mode == 3 && p.Cout == 68 && !p.walk && !getenv("FLD_TC_DECONV_EW8");
   if (ew16) {
     const size_t b_bytes = (size_t)p.BN * 128;
-    const size_t fixed = (size_t)p.kblocks * 16384 + 1024 + (size_t)2 * red_a_bytes(68) + 2 * kRedB16Bytes;
+    const size_t fixed = (size_t)p.a_blocks * 16384 + 1024 + (size_t)2 * red_a_bytes(68) + 2 * kRedB16Bytes;
     p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
     smem = fixed + (size_t)p.stages * b_bytes;
     FLD_CUDA(cudaFuncSetAttribute(deconv_gemm_kernel<68, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));

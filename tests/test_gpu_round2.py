@@ -147,6 +147,31 @@ def test_decoded_landmarks_every_encoder_bf16(dev, name, H, W):
         assert np.abs(soft - soft_ref).max() <= tol, (name, dtype, np.abs(soft - soft_ref).max())
 
 
+def test_classmap_bf16x3_tensor_core_deconv(dev, monkeypatch):
+    """keypts_predict's output is the argmax class map (prediction.py:209).  In the drop-in's default mode (bf16x3) a class-map-only
+    forward runs the LAST transposed conv on the tensor cores with split operands (x_hi w_hi + x_lo w_hi + x_hi w_lo in one
+    accumulation, argmax in the epilogue, softmax skipped).  Its class map must equal the fp64 oracle's argmax wherever the oracle's
+    top-two margin exceeds fp32-level noise, and agree with the CUDA-core fp32 path on > 99.9 % of the pixels."""
+    from keypoints_detector.networks.fcn import fcn_8
+    from oracle import cnn as o_cnn
+    for n_classes in (68, 12):
+        m = fcn_8(n_classes, input_height=64, input_width=96).init_weights(31)
+        x = np.random.default_rng(31).normal(0, 40, (3, 64, 96, 3)).astype(np.float32)
+        probs_ref = o_cnn.fcn_forward(x.astype(np.float64), m.weights, "fcn_8", torch.float64).reshape(3, 72 * 104, n_classes)
+        ref = probs_ref.argmax(-1)
+        srt = np.sort(probs_ref, -1)
+        clear = (srt[..., -1] - srt[..., -2]) > 1e-4 * srt[..., -1]          # relative margin of the winning class
+        xt = T(x, dev)
+        cm_x3 = m.forward_classmap_device(xt, "bf16x3").cpu().numpy().reshape(3, -1)
+        cm_f32 = m.forward_classmap_device(xt, "float32").cpu().numpy().reshape(3, -1)
+        assert clear.mean() > 0.99
+        assert np.array_equal(cm_x3[clear], ref[clear]), (n_classes, (cm_x3[clear] != ref[clear]).mean())
+        assert (cm_x3 == cm_f32).mean() > 0.999
+        # and the probabilities of the same model / mode are untouched by the class-map shortcut
+        p = m.forward_device(xt, "bf16x3").cpu().numpy()
+        assert np.abs(p - probs_ref).max() < 2e-4
+
+
 # ------------------------------------------------------------------------------------------------ tile-staged alignment kernel
 def _check_warps(frames, f2f, M, crops, out_hw, idx):
     oh, ow = out_hw
