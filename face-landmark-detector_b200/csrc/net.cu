@@ -208,9 +208,9 @@ int infer_shapes(fld_net* net) {
         L.path = PATH_TC_TMA;
         L.x3 = true;
         L.cout_pad = (int)align_up(L.g.Cout, L.g.Cout > 256 ? 128 : 16);
-      } else if (L.d.op == FLD_OP_CONV && out_split[i] && net->tensors[L.d.in0].dtype == FLD_U8 && tc_conv_first_supported(L.g) &&
-                 !getenv("FLD_X3_FIRST_OFF")) {
-        L.path = PATH_TC_FIRST;   // uint8 is exact in bf16: only the weights are split (tc_conv_first.cu, K = 80)
+      } else if (L.d.op == FLD_OP_CONV && out_split[i] && tc_conv_first_supported(L.g) && !getenv("FLD_X3_FIRST_OFF") &&
+                 (net->tensors[L.d.in0].dtype == FLD_U8 || (net->tensors[L.d.in0].dtype == FLD_F32 && L.d.in0 == 0 && !getenv("FLD_X3_FIRST_F32_OFF")))) {
+        L.path = PATH_TC_FIRST;   // uint8 is exact in bf16: only the weights are split (tc_conv_first.cu, K = 80); float pixels are split too (K = 128)
         L.x3 = true;
       }
     }
@@ -432,7 +432,7 @@ extern "C" int fld_net_finalize(fld_net* net) {
       FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     } else if (L.path == PATH_TC_FIRST) {
       // core-matrix packed [6 kgroups][Cout/8][8][8], k' = kh*12 + kw*4 + c (see tc_conv_first.cu)
-      const int kg = L.x3 ? 10 : 6;
+      const int kg = L.x3 ? (a.dtype == FLD_U8 ? 10 : 16) : 6;   // x3 with a float input splits the pixels too
       std::vector<uint16_t> pk((size_t)Cout * 8 * kg, 0);
       tc_conv_first_pack(L.w_host.data(), L.b_host.empty() ? nullptr : L.b_host.data(), Cout, f2bf, pk.data(), kg);
       FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));

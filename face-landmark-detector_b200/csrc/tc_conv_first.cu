@@ -60,7 +60,9 @@ __device__ __forceinline__ void load_pixel(const TIn* __restrict__ img, int H, i
 // box at a 4-byte-aligned start does); threads add the remainder.  conv1: 0.109 -> 0.105 ms per 256 faces.
 // KG = K groups of 8 elements: 6 (K = 48: 36 tap slots + 2 bias slots) in bf16 mode; 10 (K = 80) in FLD_BF16X3 mode with a uint8
 // input, which is exact in bf16, so only the weights need the hi / lo split: k 0..35 taps x w_hi, 36..38 = 1.0 x the bias split three
-// ways, 40..75 the same taps x w_lo — five K = 16 MMAs instead of three, fp32 accumulation.
+// ways, 40..75 the same taps x w_lo — five K = 16 MMAs instead of three, fp32 accumulation.  16 (K = 128) in FLD_BF16X3 mode with a
+// FLOAT input (the FCN path: get_image_array's normalised image): the pixels are split too (hi = bf16(v), lo = bf16(v - hi), two
+// parked patches) and k 80..115 carry the lo taps x w_hi; the last group is zero.
 template <typename TIn, bool DBG, int NT, bool TIN, int KG = 6>
 __global__ void __launch_bounds__(128 * NT, 8 / NT)
 conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p) {
@@ -75,8 +77,10 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
   // A NT x [6 kgroups][16 rowgroups][8 rows][16 B] = NT x 12 KB | B [6 kgroups][Cout/8][8][16 B] = Cout*96 B | patch [PH_][10] x 8 B
   uint8_t* sA = smem_raw;
   uint8_t* sB = smem_raw + ABYTES * NT;
+  constexpr int NPATCH = KG == 16 ? 2 : 1;                  // parked patches: bf16 pixels (and their bf16 remainders)
   uint2* patch = reinterpret_cast<uint2*>(sB + p.Cout * 16 * KG);
-  const TIn* raw = reinterpret_cast<const TIn*>(smem_raw + (((size_t)ABYTES * NT + (size_t)p.Cout * 16 * KG + (size_t)NPIX * 8 + 127) & ~(size_t)127));
+  uint2* patch_lo = patch + NPIX;                            // KG == 16 only
+  const TIn* raw = reinterpret_cast<const TIn*>(smem_raw + (((size_t)ABYTES * NT + (size_t)p.Cout * 16 * KG + (size_t)NPIX * 8 * NPATCH + 127) & ~(size_t)127));
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ __align__(8) uint64_t in_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -91,6 +95,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
     uint4* dst = reinterpret_cast<uint4*>(sB);
     for (int i = tid; i < p.Cout * KG; i += NTHR) dst[i] = src[i];
     if (KG == 6) *reinterpret_cast<uint4*>(sA + thalf * ABYTES + (5 * 16 + (t128 >> 3)) * 128 + (t128 & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (KG == 16) *reinterpret_cast<uint4*>(sA + thalf * ABYTES + (15 * 16 + (t128 >> 3)) * 128 + (t128 & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid == 0) {
     mbar_init(smem_u32(&mma_bar), 1);
@@ -168,6 +173,11 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
     if (!(DBG && (p.dbg & 64))) {
       patch[tid] = make_uint2(pack_bf16((float)v0.c[0], (float)v0.c[1]), pack_bf16((float)v0.c[2], 0.f));
       if (has1) patch[e1] = make_uint2(pack_bf16((float)v1.c[0], (float)v1.c[1]), pack_bf16((float)v1.c[2], 0.f));
+      if (KG == 16) {   // remainders of the float pixels
+        auto rem = [](float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); };
+        patch_lo[tid] = make_uint2(pack_bf16(rem((float)v0.c[0]), rem((float)v0.c[1])), pack_bf16(rem((float)v0.c[2]), 0.f));
+        if (has1) patch_lo[e1] = make_uint2(pack_bf16(rem((float)v1.c[0]), rem((float)v1.c[1])), pack_bf16(rem((float)v1.c[2]), 0.f));
+      }
     }
     __syncthreads();
     // ---- prefetch the next tile's pixels (in flight during im2col + MMA + epilogue)
@@ -188,13 +198,24 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
       *reinterpret_cast<uint4*>(row + 1 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
       *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
       *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
-      *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0x3f803f80u, KG == 10 ? 0x00003f80u : 0u);  // k 36,37(,38) = 1.0 (bias)
-      if (KG == 10) {   // the same taps again, against the lo halves of the weights
+      *reinterpret_cast<uint4*>(row + 4 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0x3f803f80u, KG >= 10 ? 0x00003f80u : 0u);  // k 36,37(,38) = 1.0 (bias)
+      if (KG >= 10) {   // the same taps again, against the lo halves of the weights
         *reinterpret_cast<uint4*>(row + 5 * 2048) = make_uint4(q[0][0].x, q[0][0].y, q[0][1].x, q[0][1].y);
         *reinterpret_cast<uint4*>(row + 6 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
         *reinterpret_cast<uint4*>(row + 7 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
         *reinterpret_cast<uint4*>(row + 8 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
         *reinterpret_cast<uint4*>(row + 9 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0u, 0u);
+      }
+      if (KG == 16) {   // the pixels' remainders against the hi halves of the weights
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) q[kh][kw] = patch_lo[(ly + kh) * PW_ + lx + kw];
+        *reinterpret_cast<uint4*>(row + 10 * 2048) = make_uint4(q[0][0].x, q[0][0].y, q[0][1].x, q[0][1].y);
+        *reinterpret_cast<uint4*>(row + 11 * 2048) = make_uint4(q[0][2].x, q[0][2].y, q[1][0].x, q[1][0].y);
+        *reinterpret_cast<uint4*>(row + 12 * 2048) = make_uint4(q[1][1].x, q[1][1].y, q[1][2].x, q[1][2].y);
+        *reinterpret_cast<uint4*>(row + 13 * 2048) = make_uint4(q[2][0].x, q[2][0].y, q[2][1].x, q[2][1].y);
+        *reinterpret_cast<uint4*>(row + 14 * 2048) = make_uint4(q[2][2].x, q[2][2].y, 0u, 0u);
       }
     }
     if (!(DBG && (p.dbg & 128))) fence_async_smem();
@@ -226,10 +247,10 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
     if (p.pool) {
       const int py = (y0 + ly) >> 1, px = (x0 + lx) >> 1;
       eo.valid = (py < PH) && (px < PW);
-      eo.ptr = p.out + (((size_t)b * PH + py) * PW + px) * (KG == 10 ? 2 * p.Cout : p.Cout);
+      eo.ptr = p.out + (((size_t)b * PH + py) * PW + px) * (KG >= 10 ? 2 * p.Cout : p.Cout);
     } else {
       eo.valid = (y0 + ly < p.H) && (x0 + lx < p.W);
-      eo.ptr = p.out + (((size_t)b * p.H + (y0 + ly)) * p.W + (x0 + lx)) * (KG == 10 ? 2 * p.Cout : p.Cout);
+      eo.ptr = p.out + (((size_t)b * p.H + (y0 + ly)) * p.W + (x0 + lx)) * (KG >= 10 ? 2 * p.Cout : p.Cout);
     }
     for (int ch = 0; ch < p.Cout; ch += 32) {
       uint32_t acc[32];
@@ -256,7 +277,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmIn, const FirstParams p)
       EpiOut e2 = eo;
       e2.ptr = reinterpret_cast<__nv_bfloat16*>(eo.ptr) + ch;
       e2.c_left = p.Cout - ch;
-      if (KG == 10) {   // SPLIT output (eo.ptr was computed with the 2 * Cout pixel pitch)
+      if (KG >= 10) {   // SPLIT output (eo.ptr was computed with the 2 * Cout pixel pitch)
         if (p.pool) epilogue_chunk_split<true, false>(acc, p.bias + ch, p.act, lane, TWc, e2, p.Cout);
         else epilogue_chunk_split<false, false>(acc, p.bias + ch, p.act, lane, TWc, e2, p.Cout);
         continue;
@@ -294,18 +315,19 @@ void tc_conv_first_pack(const float* w_host, const float* bias_host, int Cout, u
       for (int r = 0; r < 8; ++r)
         for (int e = 0; e < 8; ++e) {
           const int kp = kg * 8 + e, o = ng * 8 + r;
-          const bool lo_blk = kg_n == 10 && kp >= 40;
-          const int kq = lo_blk ? kp - 40 : kp;
+          const bool lo_blk = kg_n >= 10 && kp >= 40 && kp < 80;       // taps x w_lo
+          const bool hi2_blk = kg_n == 16 && kp >= 80 && kp < 120;     // (pixel remainders) x w_hi
+          const int kq = lo_blk ? kp - 40 : hi2_blk ? kp - 80 : kp >= 120 ? 127 : kp;
           const int kh = kq / 12, kw = (kq % 12) / 4, c = kq % 4;
           float v = 0.f;
           if (kq < 36 && c < 3) {
             const float w = w_host[(size_t)((kh * 3 + kw) * 3 + c) * Cout + o];
             v = lo_blk ? w - bf_to_float(f2bf(w)) : w;
           }
-          if (bias_host && !lo_blk && kp >= 36 && kp <= (kg_n == 10 ? 38 : 37)) {  // bias = hi + mid (+ lo), multiplied by A[k] = 1.0
+          if (bias_host && !lo_blk && !hi2_blk && kp >= 36 && kp <= (kg_n >= 10 ? 38 : 37)) {  // bias = hi + mid (+ lo), multiplied by A[k] = 1.0
             const float b0 = bf_to_float(f2bf(bias_host[o]));
             const float b1 = bf_to_float(f2bf(bias_host[o] - b0));
-            v = kp == 36 ? b0 : kp == 37 ? (kg_n == 10 ? b1 : bias_host[o] - b0) : bias_host[o] - b0 - b1;
+            v = kp == 36 ? b0 : kp == 37 ? (kg_n >= 10 ? b1 : bias_host[o] - b0) : bias_host[o] - b0 - b1;
           }
           out[(((size_t)kg * (Cout / 8) + ng) * 8 + r) * 8 + e] = f2bf(v);
         }
@@ -314,8 +336,8 @@ void tc_conv_first_pack(const float* w_host, const float* bias_host, int Cout, u
 int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_bfloat16* w_packed, const float* bias,
                   __nv_bfloat16* out, const ConvGeom& g, int B, cudaStream_t st, int x3) {
   if (B == 0) return FLD_OK;
-  if (x3 && in_dtype != FLD_U8) { fld_set_error("tc_conv_first: the FLD_BF16X3 variant takes a uint8 input"); return FLD_ERR_INVALID; }
-  const int KG = x3 ? 10 : 6;
+  if (x3 && in_dtype != FLD_U8 && in_dtype != FLD_F32) { fld_set_error("tc_conv_first: the FLD_BF16X3 variant takes a uint8 or float32 input"); return FLD_ERR_INVALID; }
+  const int KG = x3 ? (in_dtype == FLD_U8 ? 10 : 16) : 6;
   FirstParams p;
   p.split = x3;
   p.in = in; p.w = w_packed; p.bias = bias; p.out = out;
@@ -339,7 +361,7 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
   const int epa = (int)(16 / esz);
   const int raww = ((30 + epa) * (int)esz + 15) / 16 * 16 / (int)esz;      // box width in elements (same formula as the kernel)
   const size_t rawb = (size_t)(TH + 2) * raww * esz;
-  const size_t smem_base_bytes = (size_t)KG * 2048 * NT + (size_t)g.Cout * 16 * KG + (size_t)PW_ * (TH + 2) * 8;
+  const size_t smem_base_bytes = (size_t)KG * 2048 * NT + (size_t)g.Cout * 16 * KG + (size_t)PW_ * (TH + 2) * 8 * (KG == 16 ? 2 : 1);
   const size_t smem = tin ? ((smem_base_bytes + 127) & ~(size_t)127) + 2 * ((rawb + 127) & ~(size_t)127) + 128 : smem_base_bytes + 64;
   const int cta_per_sm = std::max(1, std::min(512 / (ncols1 * NT), 8 / NT));
   const int grid = std::min(p.n_tiles, h->sm_count * cta_per_sm);
@@ -363,7 +385,9 @@ int tc_conv_first(const fld_handle* h, const void* in, int in_dtype, const __nv_
     return FLD_OK;
   };
   int rc;
-  if (x3) {
+  if (x3 && in_dtype == FLD_F32) {
+    rc = tin ? launch(conv_first_kernel<float, false, 1, true, 16>) : launch(conv_first_kernel<float, false, 1, false, 16>);
+  } else if (x3) {
     rc = tin ? launch(conv_first_kernel<uint8_t, false, 1, true, 10>) : launch(conv_first_kernel<uint8_t, false, 1, false, 10>);
   } else if (in_dtype == FLD_U8) {
     if (tin) rc = launch(conv_first_kernel<uint8_t, false, 1, true>);
