@@ -358,7 +358,18 @@ def sub_c3(dev, peaks, batch=1024):
            "achieved_TFLOPs": tf, "frac_burst": tf / burst, "frac_sustained": tf / sust,
            "up8_ms": lt.get("up8"), "up8_share": (lt.get("up8", 0.0) / sum(lt.values())) if lt else None,
            "layer_ms_top": {k: round(v, 4) for k, v in top}}
-    del x
+    # the reference's own FCN output is the argmax class map (prediction.py:209): the same net as class maps, in plain bf16 and in
+    # the drop-in's default fp32-accurate mode (bf16x3: split-operand tensor-core convs, first layer and last transposed conv)
+    xs = x[:256]
+    cm = {}
+    for mode in ("bfloat16", "bf16x3"):
+        f2 = lambda: m.forward_classmap_device(xs, mode)
+        for _ in range(2):
+            f2()
+        med2, _ = _cuda_time(f2, 5, dev)
+        cm[mode] = {"ms_per_256": med2, "images_per_s": 256 / med2 * 1e3}
+    rec["classmap"] = cm
+    del x, xs
     m._release()
     torch.cuda.empty_cache()
     return rec
