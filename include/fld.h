@@ -55,7 +55,10 @@ typedef enum { FLD_U8 = 0, FLD_F32 = 1, FLD_BF16 = 2, FLD_BF16X3 = 3 } fld_dtype
  *              x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation in TMEM (relative error ~2^-17 per product, 250x below
  *              plain bf16); activations travel between tensor-core convs as SPLIT tensors [hi(C) | lo(C)] bf16 per pixel
  *              (fld_net_tensor_shape reports them as FLD_BF16X3).  Layers the tensor-core kernels do not cover run the FLD_F32
- *              kernels.  Meets the <=0.05 px bar; the drop-in package's default. */
+ *              kernels.  Meets the <=0.05 px bar; the drop-in package's default.  Segmentation nets: a float32 first-layer input is
+ *              split like the weights, and fld_net_forward_classmap runs the final transposed conv on the tensor cores with split
+ *              operands and takes the argmax in its epilogue (the softmax is skipped: argmax is invariant under it); probability and
+ *              landmark outputs of such nets use the fp32 transposed conv. */
 
 typedef struct fld_handle fld_handle;
 typedef struct fld_net fld_net;
