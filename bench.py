@@ -369,6 +369,11 @@ def sub_c3(dev, peaks, batch=1024):
         med2, _ = _cuda_time(f2, 5, dev)
         cm[mode] = {"ms_per_256": med2, "images_per_s": 256 / med2 * 1e3}
     rec["classmap"] = cm
+    f3 = lambda: m.forward_landmarks_device(xs, "bf16x3", n_points=0)
+    for _ in range(2):
+        f3()
+    med3, _ = _cuda_time(f3, 5, dev)
+    rec["soft_argmax_bf16x3"] = {"ms_per_256": med3, "images_per_s": 256 / med3 * 1e3}
     del x, xs
     m._release()
     torch.cuda.empty_cache()

@@ -23,7 +23,7 @@ enum Path { PATH_SIMT = 0, PATH_TC_FIRST = 1, PATH_TC_TMA = 2 };
 
 struct PlanEntry { int B; const void* in; TcConvPlan* plan; };
 struct HaloPlanEntry { int B; const void* in; TcHaloPlan* plan; };
-struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; };
+struct DeconvPlanEntry { int B; const void* scratch; TcDeconvPlan* plan; int kind = 0; };   // kind: tc_deconv_plan_create's x3 variant
 struct S2dPlanEntry { int B; const void* scratch; TcS2dPlan* plan; };
 
 struct LayerRt {
@@ -42,6 +42,8 @@ struct LayerRt {
   float* d_w = nullptr;
   float* d_bias = nullptr;
   __nv_bfloat16* d_wbf = nullptr;
+  __nv_bfloat16* d_wbf_hilo = nullptr;  // FLD_BF16X3 two-pass transposed conv: [w_hi | w_lo] (pass 1)
+  __nv_bfloat16* d_wbf_hi = nullptr;    //   and plain bf16(w) (pass 2)
   float* d_zero = nullptr;      // all-zero bias for split-K partial sums (tensor-core dense)
   std::vector<PlanEntry> plans;
   std::vector<HaloPlanEntry> hplans;
@@ -235,6 +237,9 @@ void free_layer(LayerRt& L) {
   if (L.d_wbf) cudaFree(L.d_wbf);
   if (L.d_zero) cudaFree(L.d_zero);
   L.d_zero = nullptr;
+  if (L.d_wbf_hilo) cudaFree(L.d_wbf_hilo);
+  if (L.d_wbf_hi) cudaFree(L.d_wbf_hi);
+  L.d_wbf_hilo = nullptr; L.d_wbf_hi = nullptr;
   for (auto& pe : L.plans) tc_conv_plan_destroy(pe.plan);
   for (auto& pe : L.hplans) tc_halo_plan_destroy(pe.plan);
   L.hplans.clear();
@@ -416,6 +421,12 @@ extern "C" int fld_net_finalize(fld_net* net) {
         tc_deconv_x3_pack_weights(L.w_host.data(), L.d.stride, a.c, Cout, f2bf, bf2f, pk);
         FLD_CUDA(cudaMalloc(&L.d_wbf, pk.size() * 2));
         FLD_CUDA(cudaMemcpy(L.d_wbf, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+        tc_deconv_x3_pack_weights_hilo(L.w_host.data(), L.d.stride, a.c, Cout, f2bf, bf2f, pk);
+        FLD_CUDA(cudaMalloc(&L.d_wbf_hilo, pk.size() * 2));
+        FLD_CUDA(cudaMemcpy(L.d_wbf_hilo, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+        tc_deconv_pack_weights(L.w_host.data(), L.d.stride, a.c, Cout, f2bf, pk);
+        FLD_CUDA(cudaMalloc(&L.d_wbf_hi, pk.size() * 2));
+        FLD_CUDA(cudaMemcpy(L.d_wbf_hi, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
       }
     } else if (L.path == PATH_TC_FIRST && !tc_conv_first_supported(L.g)) {
       // strided stem (tc_conv_stem.cu): [KG][Cout/8][8][8], k' = 4*tap + c
@@ -492,7 +503,10 @@ static size_t dense_scratch_bytes(const fld_net* net, int B) {
     if (L.d.op == FLD_OP_CONV && L.path == PATH_TC_FIRST && L.s2d) m = std::max(m, tc_conv_s2d_scratch_bytes(L.g, B));
     if (L.d.op == FLD_OP_DECONV && L.path == PATH_TC_TMA)
       m = std::max(m, align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));
-    if (L.d.op == FLD_OP_DECONV && L.x3_cmap) m = std::max(m, tc_deconv_x3_scratch_bytes(B, a.h, a.w, a.c));
+    if (L.d.op == FLD_OP_DECONV && L.x3_cmap) {
+      m = std::max(m, tc_deconv_x3_scratch_bytes(B, a.h, a.w, a.c));
+      m = std::max(m, 2 * align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256) + tc_deconv_acc_bytes(B, L.d.cout));   // two passes: x_hi, x_lo, sums
+    }
   }
   return m;
 }
@@ -555,7 +569,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
   std::vector<void*> ptr(nT);
   ptr[0] = const_cast<void*>(in);
   float* dense_scratch = nullptr;
-  bool cmap_done = false, xy_done = false;
+  bool cmap_done = false, xy_done = false, softmax_done = false;
   {
     size_t off = 0;
     for (int t = 1; t < nT; ++t) {
@@ -640,15 +654,49 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
         } else if (L.x3_cmap && cmap_out && !out && !xy_out) {
           // class map only: split-operand tensor-core transposed conv, argmax in the epilogue; the SOFTMAX layer that follows is skipped
           TcDeconvPlan* plan = nullptr;
-          for (auto& pe : L.dplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch) { plan = pe.plan; break; }
+          for (auto& pe : L.dplans) if (pe.B == B && pe.scratch == (const void*)dense_scratch && pe.kind == 1) { plan = pe.plan; break; }
           if (!plan) {
             rc = tc_deconv_plan_create(net->h, dense_scratch, L.d_wbf, B, a.h, a.w, a.c, d.cout, d.stride, &plan, 1);
             if (rc) return rc;
             if (L.dplans.size() >= 16 && net->retained == 0) { tc_deconv_plan_destroy(L.dplans.front().plan); L.dplans.erase(L.dplans.begin()); }
-            L.dplans.push_back({B, (const void*)dense_scratch, plan});
+            L.dplans.push_back({B, (const void*)dense_scratch, plan, 1});
           }
           rc = tc_deconv_run(plan, (const float*)pin, cmap_out, 2, st, nullptr, 0.0);
           cmap_done = true;
+        } else if (L.x3_cmap && !getenv("FLD_X3_DECONV_2PASS_OFF")) {
+          // probabilities / soft centroid in the fp32-accurate mode: two tensor-core passes (tc_deconv.cu).  Pass 1: x_hi against
+          // [w_hi | w_lo] -> fp32 logits (this layer's tensor); pass 2: x_lo against w_hi, pass 1's logits added in the epilogue,
+          // softmax (-> the SOFTMAX layer's tensor, that layer is then skipped) or the fused soft centroid.
+          const size_t a_bytes = align_up(tc_deconv_scratch_bytes(B, a.h, a.w, a.c), 256);
+          void* scr_hi = dense_scratch;
+          void* scr_lo = (char*)dense_scratch + a_bytes;
+          float* acc = (float*)((char*)dense_scratch + 2 * a_bytes);
+          TcDeconvPlan *p1 = nullptr, *p2 = nullptr;
+          for (auto& pe : L.dplans) {
+            if (pe.B == B && pe.scratch == (const void*)scr_hi && pe.kind == 2) p1 = pe.plan;
+            if (pe.B == B && pe.scratch == (const void*)scr_lo && pe.kind == 3) p2 = pe.plan;
+          }
+          if ((!p1 || !p2) && L.dplans.size() >= 24 && net->retained == 0) {        // bounded cache: drop everything for other shapes
+            for (auto& pe : L.dplans) tc_deconv_plan_destroy(pe.plan);
+            L.dplans.clear();
+            p1 = p2 = nullptr;
+          }
+          if (!p1) {
+            rc = tc_deconv_plan_create(net->h, scr_hi, L.d_wbf_hilo, B, a.h, a.w, a.c, d.cout, d.stride, &p1, 2);
+            if (rc) return rc;
+            L.dplans.push_back({B, (const void*)scr_hi, p1, 2});
+          }
+          if (!p2) {
+            rc = tc_deconv_plan_create(net->h, scr_lo, L.d_wbf_hi, B, a.h, a.w, a.c, d.cout, d.stride, &p2, 3);
+            if (rc) return rc;
+            L.dplans.push_back({B, (const void*)scr_lo, p2, 3});
+          }
+          rc = tc_deconv_run(p1, (const float*)pin, pout, 0, st);
+          if (rc) return rc;
+          const bool xy_fused = xy_out && xy_n < 1;
+          rc = tc_deconv_run(p2, (const float*)pin, xy_fused ? (void*)xy_out : ptr[i + 2], xy_fused ? 3 : 1, st, acc, xy_thresh, (const float*)pout);
+          softmax_done = true;
+          if (xy_fused) xy_done = true;
         } else if (d.kh == 2 * d.stride) rc = simt_deconv_phase(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.c, d.stride, st);
         else rc = simt_deconv(pin, a.dtype, L.d_w, (float*)pout, B, a.h, a.w, a.c, o.h, o.w, o.c, d.kh, d.stride, st);
         break;
@@ -682,6 +730,7 @@ static int net_forward(fld_net* net, const void* in, int B, void* workspace, siz
       case FLD_OP_SOFTMAX:
         if (L.skip) break;  // computed by the preceding transposed conv's epilogue
         if (cmap_done && !out && !xy_out && i + 1 == net->layers.size()) break;   // only the class map was asked for, and it is done
+        if (softmax_done && i + 1 == net->layers.size()) break;                  // computed by the two-pass transposed conv's epilogue
         FLD_REQUIRE(a.dtype == FLD_F32, "layer %zu: SOFTMAX input must be fp32", i);
         rc = simt_softmax((const float*)pin, (float*)pout, (long long)B * a.h * a.w, a.c, st);
         break;

@@ -98,8 +98,11 @@ bool tc_deconv_x3_supported(int k, int s, int Cin, int Cout);
 size_t tc_deconv_x3_scratch_bytes(int B, int IH, int IW, int Cin);
 void tc_deconv_x3_pack_weights(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), float (*bf2f)(uint16_t),
                                std::vector<uint16_t>& out);
+void tc_deconv_x3_pack_weights_hilo(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), float (*bf2f)(uint16_t),
+                                    std::vector<uint16_t>& out);   // plan variants 2 (this) / 3 (tc_deconv_pack_weights)
 void tc_deconv_plan_destroy(TcDeconvPlan* p);
 // mode 0: fp32 logits, 1: softmax probabilities, 2: int64 argmax class map,
 // 3: fused soft centroid of the softmax output -> out = double [B][Cout][2] (x, y), acc = fp32 scratch of tc_deconv_acc_bytes
 size_t tc_deconv_acc_bytes(int B, int Cout);
-int tc_deconv_run(const TcDeconvPlan* p, const float* in, void* out, int mode, cudaStream_t st, float* acc = nullptr, double thresh = 0.0);
+int tc_deconv_run(const TcDeconvPlan* p, const float* in, void* out, int mode, cudaStream_t st, float* acc = nullptr, double thresh = 0.0,
+                  const float* addend = nullptr);

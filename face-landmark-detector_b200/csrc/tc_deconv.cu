@@ -44,6 +44,7 @@ struct DeconvParams {
   int nsplit, cn, units;  // work unit = (M tile, run of cn consecutive N tiles); units = mtiles * nsplit
   int stages;
   int mode;             // 0 logits, 1 softmax probabilities, 2 int64 argmax class map, 3 per-class soft-centroid sums
+  const float* addend;  // fp32 [B][(h+1)s][(w+1)s][Cout] added to the accumulators before the epilogue's decode (FLD_BF16X3 second pass), or null
   float* acc;           // mode 3: [B][Cout][3] fp32 (sum p, sum p*col, sum p*row), accumulated with atomics
   int walk;             // mode 3: 1 = round 1's per-class walk over the staged block (FLD_TC_DECONV_WALK=1), 0 = tf32 tensor-core reduction
   unsigned long long* trace;  // FLD_TC_TRACE: clock64 event log of CTA 0, [3 roles][kTraceN]
@@ -467,6 +468,29 @@ deconv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
 
       float inv = 1.0f;
+      if (p.addend != nullptr && valid) {
+        // FLD_BF16X3 second pass: the first pass's logits (x_hi w_hi + x_hi w_lo) join this pass's x_lo w_hi before the decode
+        const float* ad = p.addend + opix * Cout;
+        if (vec) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (k * 32 + 4 * q + 4 <= Cout) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ad) + k * 8 + q);
+                rg[k][4 * q] = __float_as_uint(__uint_as_float(rg[k][4 * q]) + a4.x);
+                rg[k][4 * q + 1] = __float_as_uint(__uint_as_float(rg[k][4 * q + 1]) + a4.y);
+                rg[k][4 * q + 2] = __float_as_uint(__uint_as_float(rg[k][4 * q + 2]) + a4.z);
+                rg[k][4 * q + 3] = __float_as_uint(__uint_as_float(rg[k][4 * q + 3]) + a4.w);
+              }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (k * 32 + j < Cout) rg[k][j] = __float_as_uint(__uint_as_float(rg[k][j]) + __ldg(ad + k * 32 + j));
+        }
+      }
       if (p.mode == 1 || p.mode == 3) {
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four chains: the warps of a half hide little latency
 #pragma unroll
@@ -714,7 +738,9 @@ __global__ void deconv_im2col_vec4_kernel(const float4* __restrict__ in, uint2* 
 }
 
 // FLD_BF16X3: A row = [hi(4C) | lo(4C) | 0 ...] with hi = bf16(v), lo = bf16(v - hi); one thread per K entry pair of a row
-__global__ void deconv_im2col_x3_kernel(const float* __restrict__ in, __nv_bfloat162* __restrict__ A, long long M, int h, int w, int C, int KpA) {
+// part 0: [hi | lo] (class-map variant); part 1: the lo parts alone in the standard K layout (second pass of the two-pass variant)
+__global__ void deconv_im2col_x3_kernel(const float* __restrict__ in, __nv_bfloat162* __restrict__ A, long long M, int h, int w, int C, int KpA,
+                                        int part) {
   const int kp2 = KpA >> 1;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * kp2) return;
@@ -728,8 +754,8 @@ __global__ void deconv_im2col_x3_kernel(const float* __restrict__ in, __nv_bfloa
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     int k = k0 + e;
-    const bool lo = k >= 4 * C;
-    if (lo) k -= 4 * C;
+    const bool lo = part == 1 || k >= 4 * C;
+    if (part == 0 && lo) k -= 4 * C;
     const int t = k / C, c = k - t * C;
     const int iy = oy - 1 + (t >> 1), ix = ox - 1 + (t & 1);
     const float x = (t < 4 && iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(in + ((b * h + iy) * w + ix) * C + c) : 0.f;
@@ -792,6 +818,24 @@ bool tc_deconv_x3_supported(int k, int s, int Cin, int Cout) {
   const size_t fixed = (size_t)(x3_kpa(Cin) / 64) * 16384 + 1024, b_bytes = (size_t)2 * tc_deconv_cpp(Cout) * 128;
   return fixed + 2 * b_bytes <= kSmemMax;
 }
+// two-pass variant (probabilities / soft centroid, where the staging leaves no room for the [hi | lo] A block): pass 1 multiplies
+// A = x_hi with [w_hi | w_lo] (the second half of the weight blocks wraps onto the same A slabs) into fp32 logits, pass 2 multiplies
+// A = x_lo with w_hi, adds pass 1's logits in the epilogue (DeconvParams::addend) and decodes.
+void tc_deconv_x3_pack_weights_hilo(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), float (*bf2f)(uint16_t),
+                                    std::vector<uint16_t>& out) {
+  const int Kp = tc_deconv_kp(Cin), KpW = 2 * Kp, cpp = tc_deconv_cpp(Cout), nph = s * s;
+  out.assign((size_t)nph * cpp * KpW, 0);
+  for (int ph = 0; ph < nph; ++ph)
+    for (int t = 0; t < 4; ++t)
+      for (int c = 0; c < Cin; ++c)
+        for (int o = 0; o < Cout; ++o) {
+          const float wv = w_phase[(((size_t)ph * 4 + t) * Cin + c) * Cout + o];
+          const uint16_t hi = f2bf(wv);
+          uint16_t* row = &out[((size_t)ph * cpp + o) * KpW];
+          row[(size_t)t * Cin + c] = hi;
+          row[Kp + (size_t)t * Cin + c] = f2bf(wv - bf2f(hi));
+        }
+}
 void tc_deconv_x3_pack_weights(const float* w_phase, int s, int Cin, int Cout, uint16_t (*f2bf)(float), float (*bf2f)(uint16_t),
                                std::vector<uint16_t>& out) {
   const int KpA = x3_kpa(Cin), Kp1 = tc_deconv_kp(Cin), KpW = KpA + Kp1, cpp = tc_deconv_cpp(Cout), nph = s * s;
@@ -835,8 +879,9 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
   EncodeTiledFn enc = (EncodeTiledFn)hd->encode_tiled;
   TcDeconvPlan* pl = new TcDeconvPlan();
   DeconvParams& p = pl->p;
-  const int Kp = x3 ? x3_kpa(Cin) : tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);   // columns of A
-  const int KpW = x3 ? Kp + tc_deconv_kp(Cin) : Kp;                                   // columns of the weight matrix
+  // x3: 0 plain bf16; 1 FLD_BF16X3 class maps (A = [hi | lo]); 2 / 3 the two passes of the FLD_BF16X3 probability / centroid variant
+  const int Kp = x3 == 1 ? x3_kpa(Cin) : tc_deconv_kp(Cin), cpp = tc_deconv_cpp(Cout);   // columns of A
+  const int KpW = x3 == 1 ? Kp + tc_deconv_kp(Cin) : x3 == 2 ? 2 * Kp : Kp;             // columns of the weight matrix
   p.out = nullptr;
   p.GH = IH + 1; p.GW = IW + 1;
   p.M = (long long)B * p.GH * p.GW;
@@ -844,10 +889,10 @@ int tc_deconv_plan_create(const fld_handle* hd, void* scratch, const __nv_bfloat
   p.n_ntiles = s * s / 2;
   p.mtiles = (int)((p.M + 127) / 128);
   p.total_tiles = p.mtiles * p.n_ntiles;
-  const size_t fixed = x3 ? (size_t)(Kp / 64) * 16384 + 1024 : fixed_smem(Cin, Cout);
+  const size_t fixed = x3 == 1 ? (size_t)(Kp / 64) * 16384 + 1024 : fixed_smem(Cin, Cout);
   const size_t b_bytes = (size_t)p.BN * 128;
   p.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / b_bytes);
-  p.mode = 0; p.trace = nullptr; p.acc = nullptr; p.walk = 0;
+  p.mode = 0; p.trace = nullptr; p.acc = nullptr; p.walk = 0; p.addend = nullptr;
   pl->smem = fixed + (size_t)p.stages * b_bytes;
   // work units: the smallest split of the N range that still gives every SM a few units
   p.nsplit = 1;
@@ -887,12 +932,13 @@ void tc_deconv_plan_destroy(TcDeconvPlan* p) { delete p; }
 // pixels per class, so every warp stays on the divergent insertion path for the whole scan; it was removed.
 size_t tc_deconv_acc_bytes(int B, int Cout) { return (size_t)B * Cout * 3 * sizeof(float); }
 
-int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st, float* acc, double thresh) {
+int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, cudaStream_t st, float* acc, double thresh, const float* addend) {
   if (pl->p.total_tiles == 0) return FLD_OK;
-  if (pl->x3) {
-    if (mode != 2) { fld_set_error("tc_deconv: the FLD_BF16X3 variant produces class maps only"); return FLD_ERR_INVALID; }
+  if (pl->x3 == 1 || pl->x3 == 3) {
+    if (pl->x3 == 1 && mode != 2) { fld_set_error("tc_deconv: the [hi | lo] FLD_BF16X3 variant produces class maps only"); return FLD_ERR_INVALID; }
     const long long n = pl->p.M * (pl->Kp / 2);
-    deconv_im2col_x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat162*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C, pl->Kp);
+    deconv_im2col_x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (__nv_bfloat162*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C, pl->Kp,
+                                                                      pl->x3 == 3 ? 1 : 0);
     FLD_LAUNCHED();
   } else if (pl->C % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
     deconv_im2col_vec4_kernel<<<(unsigned)((pl->p.M + 7) / 8), 256, 0, st>>>((const float4*)in, (uint2*)pl->scratch, pl->p.M, pl->h, pl->w, pl->C / 4,
@@ -904,7 +950,7 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
     FLD_LAUNCHED();
   }
   DeconvParams p = pl->p;
-  p.out = out; p.mode = mode; p.trace = nullptr; p.acc = acc;
+  p.out = out; p.mode = mode; p.trace = nullptr; p.acc = acc; p.addend = addend;
   { const char* e = getenv("FLD_TC_DECONV_WALK"); p.walk = (e && atoi(e) != 0) ? 1 : 0; }
   if (mode == 3) {
     if (!acc) { fld_set_error("tc_deconv: mode 3 needs an accumulator buffer"); return FLD_ERR_INVALID; }
@@ -924,7 +970,7 @@ int tc_deconv_run(const TcDeconvPlan* pl, const float* in, void* out, int mode, 
     smem = fixed + (size_t)p.stages * b_bytes;
   }
   // soft centroid over the reference's 68 classes: the 16-warp epilogue (FLD_TC_DECONV_EW8=1 keeps the 8-warp one)
-  const bool ew16 = mode == 3 && p.Cout == 68 && !p.walk && !getenv("FLD_TC_DECONV_EW8");
+  const bool ew16 = mode == 3 && p.Cout == 68 && !p.walk && !addend && !getenv("FLD_TC_DECONV_EW8");   // (the addend lives in the 8-warp epilogue)
   if (ew16) {
     const size_t b_bytes = (size_t)p.BN * 128;
     const size_t fixed = (size_t)p.a_blocks * 16384 + 1024 + (size_t)2 * red_a_bytes(68) + 2 * kRedB16Bytes;

@@ -58,7 +58,8 @@ typedef enum { FLD_U8 = 0, FLD_F32 = 1, FLD_BF16 = 2, FLD_BF16X3 = 3 } fld_dtype
  *              kernels.  Meets the <=0.05 px bar; the drop-in package's default.  Segmentation nets: a float32 first-layer input is
  *              split like the weights, and fld_net_forward_classmap runs the final transposed conv on the tensor cores with split
  *              operands and takes the argmax in its epilogue (the softmax is skipped: argmax is invariant under it); probability and
- *              landmark outputs of such nets use the fp32 transposed conv. */
+ *              landmark outputs take two tensor-core passes (x_hi against [w_hi | w_lo], then x_lo against w_hi with the first
+ *              pass's logits added before the softmax / soft-centroid epilogue). */
 
 typedef struct fld_handle fld_handle;
 typedef struct fld_net fld_net;
