@@ -35,6 +35,17 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.fld_launch_count() == 0
 
 
+def test_align_scratch_size_query(lib):
+    """fld_align_scratch_bytes is pure arithmetic (no device needed): per face the fit record, its key and its slot in the
+    permutation; monotone in the batch; the ordered entry points refuse a null scratch without touching a GPU."""
+    assert lib.fld_align_scratch_bytes(None, 0) < 256
+    a, b = lib.fld_align_scratch_bytes(None, 4096), lib.fld_align_scratch_bytes(None, 65536)
+    assert 4096 * 64 <= a <= 4096 * 96 and b > a
+    assert lib.fld_align_ordered(None, None, 1, 8, 8, 3, None, None, 5, None, 5, 0, 1, 112, 112, None, None, None, 0, None) != 0
+    assert b"null scratch" in lib.fld_last_error()
+    assert lib.fld_warp_affine_ordered(None, None, 1, 8, 8, 3, None, None, 1, 112, 112, None, None, 0, None) != 0
+
+
 def test_no_gpu_fails_loudly(lib):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
