@@ -62,6 +62,35 @@ def _T(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev).contiguous()
 
 
+def _bf16(a):
+    """round-to-nearest-even bf16 of a float32 array (what the library's f2bf / __float2bfloat16_rn do)"""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@settings(max_examples=30, deadline=None)
+@given(seed=st.integers(0, 10_000), scale=st.sampled_from([1e-3, 1.0, 50.0, 4e3]))
+def test_bf16x3_split_product_error_bound(seed, scale):
+    """The arithmetic FLD_BF16X3 rests on: with hi = bf16(v), lo = bf16(v - hi), the three-term product
+    x_hi w_hi + x_lo w_hi + x_hi w_lo (exact products of bf16 values, fp32 / here fp64 accumulation) misses x w by the dropped
+    x_lo w_lo term and the remainders' own rounding: every product within 3 * 2^-16 |x w| (worst case: operands just above a power
+    of two), half of them within 2^-17, two orders of magnitude tighter than plain bf16 operands — and a K = 2304 dot product (conv3's
+    depth) stays within 2^-16 of the sum of |terms|."""
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(2304) * scale).astype(np.float32)
+    w = (rng.standard_normal(2304) * 0.05).astype(np.float32)
+    xh, wh = _bf16(x), _bf16(w)
+    xl, wl = _bf16(x - xh), _bf16(w - wh)
+    exact = x.astype(np.float64) * w.astype(np.float64)
+    three = xh.astype(np.float64) * wh + xl.astype(np.float64) * wh + xh.astype(np.float64) * wl
+    rel = np.abs(three - exact) / np.maximum(np.abs(exact), 1e-300)
+    assert rel.max() <= 3 * 2.0 ** -16 and np.median(rel) <= 2.0 ** -17
+    one = xh.astype(np.float64) * wh
+    assert np.abs(one - exact).max() > 20 * np.abs(three - exact).max()          # what plain bf16 operands would lose
+    assert abs(three.sum() - exact.sum()) <= 2.0 ** -16 * np.abs(exact).sum()
+
+
 @pytest.mark.gpu
 def test_gpu_fit_recovers_known_similarity_and_identity_warp_is_a_crop(dev):
     from keypoints_detector import prediction
