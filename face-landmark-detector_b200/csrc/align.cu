@@ -11,7 +11,8 @@
 // Two warp kernels:
 //   * align_tile_kernel (round 2; C == 3, 16-byte-aligned frame rows, output a multiple of 16 x 16, <= 256 x 256):
 //     round 1's per-pixel global gathers were L1-tag / issue bound (ncu: ~21 sectors per warp load, 107 instructions per
-//     output pixel, DRAM at 16 %).  Here the two warps of a CTA walk the 16 x 16-pixel output tiles of a face (alternate tiles each); the source
+//     output pixel, DRAM at 16 %).  Here the four warps of a CTA walk the 16 x 16-pixel output tiles of a face over a pooled box ring
+//     (as many warps take tiles as boxes fit; warp pairs share a tile when at most two fit — see the kernel); the source
 //     bounding box of a tile (a square for a similarity transform) arrives by ONE TMA load into a shared-memory ring
 //     (out-of-frame bytes are zero-filled by the tensor map = BORDER_CONSTANT 0, so the blend has no bounds checks and
 //     32-bit addresses), with the next tiles' boxes in flight while the current one is blended.  The tensor-map box is
@@ -21,6 +22,8 @@
 //     cannot change the rounded byte), computed as two IDP.2A per channel (16-bit weights a_i b_j against the gathered (p00, p01, p10, p11) bytes).
 //     Tiles whose box does not fit the class (never for similarity transforms; possible for caller matrices with
 //     shear) and faces scaled down by more than ~3.7x take the per-pixel global path below.
+//     Batches of >= 2048 faces with a caller scratch buffer (fld_align_ordered) run the fit in align_fit_kernel (one warp per
+//     face) and a counting sort in align_order_kernel, and the tile kernel then takes the faces big boxes first (no scheduling tail).
 //   * align_warp_kernel (round 1): any C in {1, 3, 4}, any shape; one CTA per (face, row block), per-pixel global loads.
 #include <limits.h>
 #include <stdlib.h>
